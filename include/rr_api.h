@@ -1,0 +1,294 @@
+/*
+ * rr_api.h -- C ABI of the B200-native render path (librr_b200.so).
+ *
+ * This is the drop-in boundary for the render hot path of ripoff-raytracer:
+ * the free functions of the reference's host driver (src/image.hpp) that
+ * main() calls, plus the POD layouts they upload.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference checkout).
+ * Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * Every function returns an rr_status (0 = RR_OK).  Where the reference
+ * prints getCLErrorString(err) and calls exit(1) (e.g. src/image.hpp:33-36,
+ * 236-239), this library returns a code; rr_error_string() gives the text and
+ * rr_last_error() the detail (CUDA error string) of the calling thread.
+ */
+#ifndef RR_API_H
+#define RR_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------
+ * Wire format: byte-identical to the reference's host structs
+ * (src/readobj.hpp:15-89) and their kernel mirrors (src/Trace.cl:9-74).
+ * cl_float3 == cl_float4: 16 bytes, 16-byte aligned (src/math.hpp:4).
+ * ---------------------------------------------------------------------- */
+#if defined(__GNUC__) || defined(__clang__) || defined(__CUDACC__)
+#define RR_ALIGN16 __attribute__((aligned(16)))
+#else
+#define RR_ALIGN16
+#endif
+
+typedef struct RR_ALIGN16 rr_float3 {
+  float s[4]; /* x, y, z, (pad) */
+} rr_float3;
+
+/* MaterialType, src/readobj.hpp:40-46 / src/Trace.cl:28-34 */
+enum {
+  RR_MATERIAL_SOLID = 0,
+  RR_MATERIAL_CHECKER = 1,
+  RR_MATERIAL_INVISIBLE = 2,
+  RR_MATERIAL_GLASSY = 3,
+  RR_MATERIAL_ONESIDED = 4
+};
+
+/* RayTracingMaterial, 64 bytes (src/readobj.hpp:48-56) */
+typedef struct RR_ALIGN16 rr_material {
+  int32_t type;            /* @0  */
+  float ior;               /* @4  */
+  float _pad0[2];          /* @8  */
+  rr_float3 color;         /* @16 */
+  rr_float3 emissionColor; /* @32 */
+  float emissionStrength;  /* @48 */
+  float reflectiveness;    /* @52 */
+  float specularProbability; /* @56 */
+  float _pad1;             /* @60 */
+} rr_material;
+
+/* Triangle, 96 bytes (src/readobj.hpp:69-73) */
+typedef struct RR_ALIGN16 rr_triangle {
+  rr_float3 posA, posB, posC;
+  rr_float3 normalA, normalB, normalC;
+} rr_triangle;
+
+/* MeshInfo, 112 bytes (src/readobj.hpp:75-81).  nodeIdx is the index of the
+ * mesh's root in the reference's nodeList; this library reads it only in
+ * rr_upload_scene_ref(), to recover the mesh's triangle range. */
+typedef struct RR_ALIGN16 rr_mesh {
+  uint64_t nodeIdx;     /* @0  */
+  uint64_t _pad0;       /* @8  */
+  rr_float3 pos;        /* @16 */
+  float pitch, yaw, roll; /* @32 */
+  float scale;          /* @44 */
+  rr_material material; /* @48 */
+} rr_mesh;
+
+/* Host-side BVH node of the reference, 64 bytes (src/readobj.hpp:20-25). */
+typedef struct RR_ALIGN16 rr_ref_node {
+  rr_float3 bmin, bmax;
+  uint64_t childIndex;
+  uint64_t firstTriangleIdx;
+  uint64_t numTriangles;
+  uint64_t _pad0;
+} rr_ref_node;
+
+/* CameraInformation, 48 bytes (src/readobj.hpp:33-38) */
+typedef struct RR_ALIGN16 rr_camera {
+  rr_float3 position;
+  float pitch, yaw, roll;
+  float fov;
+  float aspectRatio;
+  float _pad0[3];
+} rr_camera;
+
+/* Sphere, 96 bytes (src/readobj.hpp:58-62).  The reference declares this
+ * struct but its kernel has no sphere routine; sphere rendering is an
+ * extension whose semantics are defined by oracle/rr_oracle.c. */
+typedef struct RR_ALIGN16 rr_sphere {
+  rr_float3 center;     /* @0  */
+  float radius;         /* @16 */
+  float _pad0[3];
+  rr_material material; /* @32 */
+} rr_sphere;
+
+/* Triangle range of one mesh inside the uploaded triangle array. */
+typedef struct rr_mesh_range {
+  uint64_t firstTriangle;
+  uint64_t numTriangles;
+} rr_mesh_range;
+
+/* ------------------------------------------------------------------------ */
+typedef enum rr_status {
+  RR_OK = 0,
+  RR_ERR_INVALID_ARGUMENT = 1,
+  RR_ERR_NO_DEVICE = 2,      /* reference: "Failed to select a usable device" (src/main.cpp:186-189) */
+  RR_ERR_CUDA = 3,           /* any CUDA runtime failure; see rr_last_error() */
+  RR_ERR_OUT_OF_MEMORY = 4,
+  RR_ERR_NO_SCENE = 5,       /* rr_render before rr_upload_scene */
+  RR_ERR_BAD_MESH_RANGE = 6, /* mesh range outside the triangle array */
+  RR_ERR_BVH_DEPTH = 7,      /* hierarchy deeper than the traversal stack */
+  RR_ERR_IO = 8,             /* file could not be opened / parsed */
+  RR_ERR_UNSUPPORTED = 9
+} rr_status;
+
+const char* rr_error_string(int status);
+/* Detail text of the last failure on the calling thread ("" if none). */
+const char* rr_last_error(void);
+/* Library/ABI version: major*10000 + minor*100 + patch. */
+int rr_version(void);
+
+typedef struct rr_ctx rr_ctx;
+
+/* Replaces generateKernelForDevice (src/image.hpp:30-71; called
+ * src/main.cpp:239-244): one context over `n` CUDA devices (ordinals).  The
+ * reference JIT-builds its OpenCL program here; this library ships sm_100a
+ * SASS and only creates streams.  Fails with RR_ERR_NO_DEVICE when no CUDA
+ * device is usable -- there is no CPU fallback. */
+int rr_create(const int* cuda_ordinals, int n, rr_ctx** out);
+
+/* Replaces releaseBuffers + releaseKernelContext (src/image.hpp:73-95,
+ * 186-209; src/main.cpp:728-730). */
+void rr_destroy(rr_ctx* ctx);
+
+int rr_device_count(int* out);
+/* Device table line of src/main.cpp:137-140: name, SM count, memory. */
+int rr_device_info(int ordinal, char* name, size_t name_len, int* sm_count, uint64_t* mem_bytes);
+
+/* Replaces generateBuffers (src/image.hpp:97-175; called src/main.cpp:711).
+ * COPIES the host arrays (CL_MEM_COPY_HOST_PTR semantics) to every device of
+ * the context and builds the per-mesh LBVH on the device.  `ranges[i]` is the
+ * triangle range of meshes[i].  spheres may be NULL (n_spheres == 0). */
+int rr_upload_scene(rr_ctx* ctx, const rr_triangle* tris, size_t n_tris, const rr_mesh* meshes,
+                    const rr_mesh_range* ranges, size_t n_meshes, const rr_sphere* spheres, size_t n_spheres);
+
+/* Same, with the reference's exact argument list (triangleList, meshList,
+ * nodeList): the triangle range of each mesh is recovered from the subtree
+ * under nodes[meshes[i].nodeIdx]; the reference's SAH hierarchy itself is
+ * ignored (the device builds its own LBVH). */
+int rr_upload_scene_ref(rr_ctx* ctx, const rr_triangle* tris, size_t n_tris, const rr_mesh* meshes, size_t n_meshes,
+                        const rr_ref_node* nodes, size_t n_nodes);
+
+/* Counters of one render (exact, from device atomics). */
+typedef struct rr_stats {
+  uint64_t samples;      /* Trace() calls = W*H*spp                         */
+  uint64_t rays;         /* path segments traced (closest-hit queries)      */
+  uint64_t rays_reused;  /* segments answered from the per-pixel primary-hit cache */
+  uint64_t box_tests;    /* ray/AABB tests                                  */
+  uint64_t tri_tests;    /* ray/triangle tests                              */
+  uint64_t sphere_tests; /* ray/sphere tests                                */
+  uint64_t tiles;        /* tiles this context rendered                     */
+  float render_ms;       /* device time of the render kernel(s), CUDA events */
+  float build_ms;        /* device time of the last LBVH build              */
+} rr_stats;
+
+/* Replaces singleThreadedCompute / multiThreadedCompute + renderTile
+ * (src/image.hpp:218-381; dispatch src/main.cpp:719-723) and kernel args
+ * 4-10 (src/image.hpp:161-172, src/main.cpp:657-676).
+ * rgba_out: width*height*4 bytes, row 0 = top, RGBA, alpha = 255
+ * (src/image.hpp:267-271).  Blocking.  frameIndex is kernel arg 7, which the
+ * reference always evaluates to 0 (src/image.hpp:228).  tile_size == 0 picks
+ * the library default; the image does not depend on it. */
+int rr_render(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_bounces,
+              int32_t frame_index, uint32_t tile_size, uint8_t* rgba_out);
+
+/* rr_render plus optional extras: radiance_out (width*height*3 floats, the
+ * mean accumulator of src/Trace.cl:643 before clamp/gamma) and stats_out.
+ * count_tests != 0 selects the instrumented kernel (box/tri counters). */
+int rr_render_ex(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
+                 uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, uint8_t* rgba_out,
+                 float* radiance_out, rr_stats* stats_out, int count_tests);
+
+/* Device-resident variant used for kernel-only timing: renders into the
+ * context's own frame buffer on the device and does not copy it back.
+ * rr_read_frame() fetches it afterwards. */
+int rr_render_device(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
+                     uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, rr_stats* stats_out);
+int rr_read_frame(rr_ctx* ctx, uint8_t* rgba_out, size_t bytes);
+
+/* Primary-ray closest hit per pixel (MakeRay + CalculateRayCollisionWithTriangle,
+ * src/Trace.cl:596-621, 434-485).  mesh_out: mesh index (spheres: n_meshes),
+ * -1 on miss.  prim_out: index of the triangle in the UPLOADED array (or
+ * sphere index).  dst_out: world distance.  Any output may be NULL. */
+int rr_primary_hits(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, int32_t* mesh_out,
+                    int32_t* prim_out, float* dst_out);
+
+/* LBVH read-back for build-order parity (oracle/rr_oracle.c rro_lbvh_build).
+ * which = 0: triangles, 1: spheres.  Arrays sized by rr_bvh_size(). Any
+ * output may be NULL.
+ *   codes[n], order[n]     sorted Morton keys and the primitive index at each sorted slot
+ *   left/right[n]          children of inner node i: >= 0 inner index, < 0 ~sorted-slot (leaf)
+ *   parent[n]              parent inner index of inner node i (-1 root / unused slot)
+ *   bounds[n*6]            min.xyz,max.xyz of inner node i                                  */
+int rr_bvh_size(rr_ctx* ctx, int which, uint64_t* n_prims);
+int rr_bvh_read(rr_ctx* ctx, int which, uint64_t* codes, uint32_t* order, int32_t* left, int32_t* right,
+                int32_t* parent, float* bounds);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU tile queue (replaces the mutex-guarded std::queue of
+ * src/image.hpp:280-350).  One process per GPU: rank 0 owns a 64-bit tile
+ * counter and the frame buffer in its HBM and exports CUDA IPC handles; the
+ * other ranks import them and their persistent CTAs pop tiles with
+ * system-scope atomics and store finished pixels straight into rank 0's frame
+ * over NVLink.  handle buffers are RR_IPC_HANDLE_BYTES each.
+ * ---------------------------------------------------------------------- */
+#define RR_IPC_HANDLE_BYTES 64
+int rr_queue_export(rr_ctx* ctx, uint32_t width, uint32_t height, uint8_t* queue_handle, uint8_t* frame_handle);
+int rr_queue_import(rr_ctx* ctx, uint32_t width, uint32_t height, const uint8_t* queue_handle,
+                    const uint8_t* frame_handle);
+/* rank 0, before every shared frame: counter = 0. */
+int rr_queue_reset(rr_ctx* ctx);
+/* Render the tiles this rank manages to pop from the shared queue.  Pixels go
+ * to the shared frame if one is attached (peer stores), else to the local
+ * frame buffer (tiles not owned stay 0).  Non-blocking pairs are not offered:
+ * returns when this rank's kernel has drained the queue. */
+int rr_render_shared(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
+                     uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, rr_stats* stats_out);
+/* Static partition fallback (no peer access): render only tiles t with
+ * t % world == rank into the local frame buffer. */
+int rr_render_strided(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
+                      uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, uint32_t rank, uint32_t world,
+                      rr_stats* stats_out);
+/* Device pointer of the local frame buffer (for an NCCL gather by the caller). */
+int rr_frame_device_ptr(rr_ctx* ctx, uint64_t* ptr_out, uint64_t* bytes_out);
+
+/* ------------------------------------------------------------------------
+ * Host helpers that sit either side of the path (same formats as the reference).
+ * ---------------------------------------------------------------------- */
+
+/* placeImageDataIntoBMP (src/math.hpp:117-164): 24-bit BGR, bottom-up, rows
+ * padded to 4 bytes, 54-byte header.  Unlike the reference (which silently
+ * returns) an unopenable file yields RR_ERR_IO. */
+int rr_write_bmp(const char* path, const uint8_t* rgba, uint32_t width, uint32_t height);
+
+/* Scene builder mirroring the reference's global triangleList / meshList
+ * (src/readobj.hpp:91-94) without the globals. */
+typedef struct rr_scene rr_scene;
+int rr_scene_create(rr_scene** out);
+void rr_scene_destroy(rr_scene* s);
+/* loadMeshFromOBJFile (src/readobj.hpp:270-376): `v`, `vn`, `f a/b/c` or
+ * `f a//c` triangles.  The mesh is NOT appended to the mesh list (the
+ * reference appends it last, src/main.cpp:298): mesh_out receives the
+ * MeshInfo defaults, range_out its triangles; add it with rr_scene_add_mesh. */
+int rr_scene_load_obj(rr_scene* s, const char* path, rr_mesh* mesh_out, rr_mesh_range* range_out);
+/* Local-space bounds of a triangle range (root node bounds, src/readobj.hpp:353-362). */
+int rr_scene_range_bounds(const rr_scene* s, const rr_mesh_range* range, float* min3, float* max3);
+/* addQuad (src/readobj.hpp:378-408): two triangles + a Solid mesh, appended. */
+int rr_scene_add_quad(rr_scene* s, const float* a3, const float* b3, const float* c3, const float* d3,
+                      const float* normal3, const float* color3);
+/* addCornellBoxToScene (src/image.hpp:401-448) around the given mesh bounds. */
+int rr_scene_add_cornell(rr_scene* s, const rr_mesh* mesh, const rr_mesh_range* range);
+int rr_scene_add_mesh(rr_scene* s, const rr_mesh* mesh, const rr_mesh_range* range);
+int rr_scene_add_triangles(rr_scene* s, const rr_triangle* tris, size_t n, rr_mesh_range* range_out);
+int rr_scene_add_sphere(rr_scene* s, const rr_sphere* sphere);
+/* Last mesh's material / transform (meshList.back() edits in src/image.hpp:389, 413-421). */
+rr_mesh* rr_scene_mesh(rr_scene* s, size_t index);
+size_t rr_scene_mesh_count(const rr_scene* s);
+size_t rr_scene_triangle_count(const rr_scene* s);
+size_t rr_scene_sphere_count(const rr_scene* s);
+const rr_triangle* rr_scene_triangles(const rr_scene* s);
+const rr_mesh* rr_scene_meshes(const rr_scene* s);
+const rr_mesh_range* rr_scene_ranges(const rr_scene* s);
+const rr_sphere* rr_scene_spheres(const rr_scene* s);
+/* rr_upload_scene with the builder's arrays. */
+int rr_scene_upload(rr_ctx* ctx, const rr_scene* s);
+/* Default camera of src/main.cpp:299-304 + src/settings.hpp:23-28. */
+void rr_default_camera(rr_camera* cam, uint32_t width, uint32_t height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RR_API_H */
