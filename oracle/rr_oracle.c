@@ -38,6 +38,7 @@
 #define RRO_TAU 6.28318530717958647692f /* src/Trace.cl:5 */
 #define RRO_IOR_AIR 1.0f             /* src/Trace.cl:7 */
 #define RRO_STACK 64                 /* src/Trace.cl:2 */
+#define RRO_MAX_INVISIBLE_PASSES 256u /* see trace_path */
 #define RRO_DIRECT_MAX 4             /* segments this small are tested without a hierarchy */
 
 typedef struct { float x, y, z; } v3;
@@ -775,6 +776,7 @@ static v3 trace_path(const rro_scene* sc, ray_t ray, uint32_t* rng, uint32_t max
   v3 incoming = V(0.0f, 0.0f, 0.0f);
   v3 throughput = V(1.0f, 1.0f, 1.0f);
   uint32_t bounce = 0;
+  uint32_t passes = 0;
   while (bounce < maxBounce) {
     scene_hit sh;
     scene_closest(sc, &ray, &sh, c);
@@ -782,6 +784,10 @@ static v3 trace_path(const rro_scene* sc, ray_t ray, uint32_t* rng, uint32_t max
     rr_material mat = *sh.material;
     hit_t* hit = &sh.h;
     if (mat.type == RR_MATERIAL_INVISIBLE) {
+      /* GUARD (deviation): the reference `continue`s without counting a bounce (src/Trace.cl:502-506);
+       * when hitPoint + dir*1e-6 rounds back to hitPoint it loops forever (a GPU hang).  Both sides of
+       * this repo end the path after RR_MAX_INVISIBLE_PASSES pass-throughs. */
+      if (++passes > RRO_MAX_INVISIBLE_PASSES) break;
       ray.origin = vadd(hit->hitPoint, vscale(ray.direction, RRO_EPSILON));
       continue;
     }

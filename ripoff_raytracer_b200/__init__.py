@@ -1,0 +1,11 @@
+"""ripoff_raytracer_b200 -- B200-native render hot path of ripoff-raytracer.
+
+The product is the C-ABI library `csrc/librr_b200.so` (include/rr_api.h): a
+GPU-built LBVH plus hand-written sm_100a path-tracing kernels behind the
+reference's host-driver boundary (reference src/image.hpp).  This package is
+the thin Python mirror of that boundary used by the tests and bench.py.
+"""
+from . import _abi, scenes  # noqa: F401
+from .api import Renderer, Scene, default_camera, default_scene, write_bmp  # noqa: F401
+
+__all__ = ["Renderer", "Scene", "default_camera", "default_scene", "write_bmp", "scenes"]

@@ -1,0 +1,278 @@
+"""Host-side mirror of the reference's driver interface over the C ABI.
+
+Names follow the reference: a *scene* is the triangleList / meshList pair of
+src/readobj.hpp:91-94, `Scene.load_obj` is loadMeshFromOBJFile, `add_quad` is
+addQuad, `add_cornell` is addCornellBoxToScene (src/image.hpp:401-448);
+`Renderer` stands where generateKernelForDevice / generateBuffers /
+singleThreadedCompute / multiThreadedCompute stand (src/image.hpp:30-381).
+Every call goes to librr_b200.so; nothing here computes pixels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import CAMERA, MESH, MESH_RANGE, SPHERE, TRIANGLE, Stats, check, lib, ptr
+
+
+def _f3(v):
+    return np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(3))
+
+
+def default_camera(width: int, height: int) -> np.ndarray:
+    """CameraInformation of src/main.cpp:299-304 (start pose of src/settings.hpp:23-28, fov 90)."""
+    cam = np.zeros(1, CAMERA)
+    lib().rr_default_camera(ptr(cam), width, height)
+    return cam
+
+
+def write_bmp(path, rgba: np.ndarray) -> None:
+    """placeImageDataIntoBMP (src/math.hpp:117-164)."""
+    rgba = np.ascontiguousarray(rgba, np.uint8)
+    h, w = rgba.shape[:2]
+    check(lib().rr_write_bmp(str(path).encode(), ptr(rgba), w, h), "rr_write_bmp")
+
+
+class Scene:
+    """Scene builder (triangleList + meshList + spheres) held by the C++ host layer."""
+
+    def __init__(self):
+        h = C.c_void_p()
+        check(lib().rr_scene_create(C.byref(h)), "rr_scene_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().rr_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_obj(self, path):
+        mesh = np.zeros(1, MESH)
+        rng = np.zeros(1, MESH_RANGE)
+        check(lib().rr_scene_load_obj(self.h, str(path).encode(), ptr(mesh), ptr(rng)), f"rr_scene_load_obj({path})")
+        return mesh, rng
+
+    def add_triangles(self, tris: np.ndarray):
+        tris = np.ascontiguousarray(tris, TRIANGLE)
+        rng = np.zeros(1, MESH_RANGE)
+        check(lib().rr_scene_add_triangles(self.h, ptr(tris), len(tris), ptr(rng)), "rr_scene_add_triangles")
+        return rng
+
+    def add_mesh(self, mesh: np.ndarray, rng: np.ndarray):
+        mesh = np.ascontiguousarray(mesh, MESH)
+        rng = np.ascontiguousarray(rng, MESH_RANGE)
+        check(lib().rr_scene_add_mesh(self.h, ptr(mesh), ptr(rng)), "rr_scene_add_mesh")
+
+    def add_quad(self, a, b, c, d, normal, color):
+        args = [_f3(v) for v in (a, b, c, d, normal, color)]
+        check(lib().rr_scene_add_quad(self.h, *[ptr(v) for v in args]), "rr_scene_add_quad")
+
+    def add_cornell(self, mesh: np.ndarray, rng: np.ndarray):
+        mesh = np.ascontiguousarray(mesh, MESH)
+        rng = np.ascontiguousarray(rng, MESH_RANGE)
+        check(lib().rr_scene_add_cornell(self.h, ptr(mesh), ptr(rng)), "rr_scene_add_cornell")
+
+    def add_spheres(self, spheres: np.ndarray):
+        spheres = np.ascontiguousarray(spheres, SPHERE)
+        for i in range(len(spheres)):
+            check(lib().rr_scene_add_sphere(self.h, ptr(spheres[i:i + 1])), "rr_scene_add_sphere")
+
+    def range_bounds(self, rng: np.ndarray):
+        rng = np.ascontiguousarray(rng, MESH_RANGE)
+        lo, hi = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        check(lib().rr_scene_range_bounds(self.h, ptr(rng), ptr(lo), ptr(hi)), "rr_scene_range_bounds")
+        return lo, hi
+
+    def mesh(self, index: int) -> np.ndarray:
+        """Writable view of mesh `index` (the reference edits meshList.back() in place)."""
+        p = lib().rr_scene_mesh(self.h, index)
+        if not p:
+            raise IndexError(index)
+        buf = (C.c_char * MESH.itemsize).from_address(p)
+        return np.frombuffer(buf, dtype=MESH, count=1)
+
+    @property
+    def n_meshes(self):
+        return lib().rr_scene_mesh_count(self.h)
+
+    @property
+    def n_triangles(self):
+        return lib().rr_scene_triangle_count(self.h)
+
+    @property
+    def n_spheres(self):
+        return lib().rr_scene_sphere_count(self.h)
+
+    def arrays(self):
+        """Copies of (triangles, meshes, ranges, spheres)."""
+        l = lib()
+
+        def copy(p, n, dt):
+            if n == 0:
+                return np.zeros(0, dt)
+            buf = (C.c_char * (n * dt.itemsize)).from_address(p)
+            return np.frombuffer(buf, dtype=dt, count=n).copy()
+
+        return (copy(l.rr_scene_triangles(self.h), self.n_triangles, TRIANGLE),
+                copy(l.rr_scene_meshes(self.h), self.n_meshes, MESH),
+                copy(l.rr_scene_ranges(self.h), self.n_meshes, MESH_RANGE),
+                copy(l.rr_scene_spheres(self.h), self.n_spheres, SPHERE))
+
+
+def default_scene(obj_path) -> Scene:
+    """Scene assembly of the reference's main() (src/main.cpp:246-272, 298, 706):
+    OBJ mesh (Solid white, specularProbability 1, scale 0.5), Cornell box around it,
+    OBJ mesh appended LAST, then yaw = 5.5 (setupNextVideoFrame, src/image.hpp:385-390)."""
+    s = Scene()
+    mesh, rng = s.load_obj(obj_path)
+    m = mesh["material"]
+    m["type"] = _abi.MATERIAL_SOLID
+    m["ior"] = 1.0
+    m["color"][:, :3] = 1.0
+    m["emissionColor"][:] = 0.0
+    m["emissionStrength"] = 0.0
+    m["reflectiveness"] = 0.0
+    m["specularProbability"] = 1.0
+    mesh["scale"] = 0.5
+    s.add_cornell(mesh, rng)
+    s.add_mesh(mesh, rng)
+    s.mesh(s.n_meshes - 1)["yaw"] = np.float32(0.0) + np.float32(5.5)
+    return s
+
+
+class Renderer:
+    """One render context over one or more CUDA devices of this process."""
+
+    def __init__(self, devices=(0,)):
+        ords = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        check(lib().rr_create(ords, len(devices), C.byref(h)), "rr_create")
+        self.h = h
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().rr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- generateBuffers ----------------------------------------------------
+    def upload(self, scene: Scene):
+        check(lib().rr_scene_upload(self.h, scene.h), "rr_scene_upload")
+
+    def upload_arrays(self, tris, meshes, ranges, spheres=None):
+        tris = np.ascontiguousarray(tris, TRIANGLE)
+        meshes = np.ascontiguousarray(meshes, MESH)
+        ranges = np.ascontiguousarray(ranges, MESH_RANGE)
+        ns = 0 if spheres is None else len(spheres)
+        spheres = None if ns == 0 else np.ascontiguousarray(spheres, SPHERE)
+        check(lib().rr_upload_scene(self.h, ptr(tris), len(tris), ptr(meshes), ptr(ranges), len(meshes), ptr(spheres), ns),
+              "rr_upload_scene")
+
+    def upload_ref(self, tris, meshes, ref_nodes):
+        """generateBuffers' own argument list: triangleList, meshList, nodeList (host Node layout)."""
+        tris = np.ascontiguousarray(tris, TRIANGLE)
+        meshes = np.ascontiguousarray(meshes, MESH)
+        ref_nodes = np.ascontiguousarray(ref_nodes, _abi.REF_NODE)
+        check(lib().rr_upload_scene_ref(self.h, ptr(tris), len(tris), ptr(meshes), len(meshes), ptr(ref_nodes), len(ref_nodes)),
+              "rr_upload_scene_ref")
+
+    # -- singleThreadedCompute / multiThreadedCompute -----------------------------
+    def render(self, cam, width, height, spp, bounces, frame_index=0, tile=0, radiance=False, count_tests=False,
+               out=None):
+        cam = np.ascontiguousarray(cam, CAMERA)
+        rgba = out if out is not None else np.zeros((height, width, 4), np.uint8)
+        rad = np.zeros((height, width, 3), np.float32) if radiance else None
+        st = Stats()
+        check(lib().rr_render_ex(self.h, ptr(cam), width, height, spp, bounces, frame_index, tile, ptr(rgba), ptr(rad),
+                                 C.byref(st), 1 if count_tests else 0), "rr_render_ex")
+        return rgba, rad, st.as_dict()
+
+    def render_plain(self, cam, width, height, spp, bounces, frame_index=0, tile=0, out=None):
+        """The boundary call itself: rr_render (host buffers in and out)."""
+        cam = np.ascontiguousarray(cam, CAMERA)
+        rgba = out if out is not None else np.zeros((height, width, 4), np.uint8)
+        check(lib().rr_render(self.h, ptr(cam), width, height, spp, bounces, frame_index, tile, ptr(rgba)), "rr_render")
+        return rgba
+
+    def render_device(self, cam, width, height, spp, bounces, frame_index=0, tile=0):
+        cam = np.ascontiguousarray(cam, CAMERA)
+        st = Stats()
+        check(lib().rr_render_device(self.h, ptr(cam), width, height, spp, bounces, frame_index, tile, C.byref(st)),
+              "rr_render_device")
+        return st.as_dict()
+
+    def read_frame(self, width, height):
+        rgba = np.zeros((height, width, 4), np.uint8)
+        check(lib().rr_read_frame(self.h, ptr(rgba), rgba.nbytes), "rr_read_frame")
+        return rgba
+
+    def primary_hits(self, cam, width, height):
+        cam = np.ascontiguousarray(cam, CAMERA)
+        mesh = np.zeros((height, width), np.int32)
+        prim = np.zeros((height, width), np.int32)
+        dst = np.zeros((height, width), np.float32)
+        check(lib().rr_primary_hits(self.h, ptr(cam), width, height, ptr(mesh), ptr(prim), ptr(dst)), "rr_primary_hits")
+        return mesh, prim, dst
+
+    def bvh(self, which=0):
+        n = C.c_uint64()
+        check(lib().rr_bvh_size(self.h, which, C.byref(n)), "rr_bvh_size")
+        n = int(n.value)
+        m = max(n, 1)
+        out = dict(codes=np.zeros(m, np.uint64), order=np.zeros(m, np.uint32), left=np.zeros(m, np.int32),
+                   right=np.zeros(m, np.int32), parent=np.zeros(m, np.int32), bounds=np.zeros((m, 6), np.float32))
+        check(lib().rr_bvh_read(self.h, which, ptr(out["codes"]), ptr(out["order"]), ptr(out["left"]), ptr(out["right"]),
+                                ptr(out["parent"]), ptr(out["bounds"])), "rr_bvh_read")
+        return {k: v[:n] for k, v in out.items()}
+
+    # -- multi-process tile queue -------------------------------------------------
+    def queue_export(self, width, height):
+        q = np.zeros(_abi_handle_bytes(), np.uint8)
+        f = np.zeros(_abi_handle_bytes(), np.uint8)
+        check(lib().rr_queue_export(self.h, width, height, ptr(q), ptr(f)), "rr_queue_export")
+        return q, f
+
+    def queue_import(self, width, height, q, f):
+        q = np.ascontiguousarray(q, np.uint8)
+        f = np.ascontiguousarray(f, np.uint8)
+        check(lib().rr_queue_import(self.h, width, height, ptr(q), ptr(f)), "rr_queue_import")
+
+    def queue_reset(self):
+        check(lib().rr_queue_reset(self.h), "rr_queue_reset")
+
+    def render_shared(self, cam, width, height, spp, bounces, frame_index=0, tile=0):
+        cam = np.ascontiguousarray(cam, CAMERA)
+        st = Stats()
+        check(lib().rr_render_shared(self.h, ptr(cam), width, height, spp, bounces, frame_index, tile, C.byref(st)),
+              "rr_render_shared")
+        return st.as_dict()
+
+    def render_strided(self, cam, width, height, spp, bounces, rank, world, frame_index=0, tile=0):
+        cam = np.ascontiguousarray(cam, CAMERA)
+        st = Stats()
+        check(lib().rr_render_strided(self.h, ptr(cam), width, height, spp, bounces, frame_index, tile, rank, world,
+                                      C.byref(st)), "rr_render_strided")
+        return st.as_dict()
+
+    def frame_device_ptr(self):
+        p, b = C.c_uint64(), C.c_uint64()
+        check(lib().rr_frame_device_ptr(self.h, C.byref(p), C.byref(b)), "rr_frame_device_ptr")
+        return int(p.value), int(b.value)
+
+
+def _abi_handle_bytes() -> int:
+    return 64  # RR_IPC_HANDLE_BYTES

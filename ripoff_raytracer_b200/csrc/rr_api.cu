@@ -1,0 +1,679 @@
+// rr_api.cu -- the thin C-ABI host layer over the CUDA kernels (include/rr_api.h).
+//
+// Replaces the OpenCL context / queue / program / buffer plumbing of the
+// reference's host driver (src/image.hpp:30-278) and the device selection of
+// src/main.cpp:54-157.  No JIT: the kernels ship as sm_100a SASS.  No CPU
+// fallback: every entry point that needs a device fails with RR_ERR_NO_DEVICE /
+// RR_ERR_CUDA when there is none.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rr_internal.h"
+#include "rr_math.cuh"
+
+namespace rr {
+
+static thread_local std::string g_last_error;
+
+static int fail(int status, const std::string& detail) {
+  g_last_error = detail;
+  return status;
+}
+static int cuda_fail(cudaError_t e, const char* where) {
+  return fail(e == cudaErrorMemoryAllocation ? RR_ERR_OUT_OF_MEMORY : RR_ERR_CUDA,
+              std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define RR_CUDA(x)                                 \
+  do {                                             \
+    cudaError_t e_ = (x);                          \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #x); \
+  } while (0)
+
+struct Device {
+  int ordinal = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // scene
+  rr_triangle* tris = nullptr;
+  rr_sphere* spheres = nullptr;
+  float* tri_box = nullptr;
+  float* sph_box = nullptr;
+  Lbvh tb, sb;
+  float4 *tri_geom = nullptr, *tri_nrm = nullptr, *sph_geom = nullptr;
+  DMesh* meshes = nullptr;
+  DMaterial* materials = nullptr;
+  float sph_bounds[6] = {0, 0, 0, 0, 0, 0};
+  float build_ms = 0.0f;
+  // frame
+  uint8_t* frame = nullptr;
+  size_t frame_bytes = 0;
+  float* radiance = nullptr;
+  size_t radiance_bytes = 0;
+  unsigned long long* queue = nullptr;  // local tile counter
+  Counters* counters = nullptr;
+  // shared (multi-process) attachments
+  unsigned long long* shared_queue = nullptr;
+  uint8_t* shared_frame = nullptr;
+  bool shared_imported = false;
+};
+
+}  // namespace rr
+
+struct rr_ctx {
+  std::vector<rr::Device> dev;
+  size_t n_tris = 0, n_meshes = 0, n_spheres = 0;
+  bool has_scene = false;
+  bool peer_ok = false;  // devices 1.. can address device 0's memory
+};
+
+namespace rr {
+
+// ---- per-mesh records, computed on the device so that the rotation uses the
+// same sin/cos as the kernel would (reference src/Trace.cl:452-454 rebuilds it per ray).
+__global__ void k_prepare_meshes(const rr_mesh* __restrict__ meshes, const uint32_t* __restrict__ mesh_seg, int n_meshes,
+                                 const float* __restrict__ seg_box, const uint32_t* __restrict__ seg_sfirst,
+                                 const uint32_t* __restrict__ seg_count, const rr_sphere* __restrict__ spheres,
+                                 int n_spheres, DMesh* __restrict__ out, DMaterial* __restrict__ mats) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_meshes + n_spheres) return;
+  const rr_material* src;
+  if (i < n_meshes) {
+    const rr_mesh& m = meshes[i];
+    src = &m.material;
+    DMesh d;
+    const float cx = cos_c(m.pitch), sx = sin_c(m.pitch);
+    const float cy = cos_c(m.yaw), sy = sin_c(m.yaw);
+    const float cz = cos_c(m.roll), sz = sin_c(m.roll);
+    // makeRotation, src/Trace.cl:90-100
+    d.R[0] = cy * cz; d.R[1] = cy * sz; d.R[2] = -sy;
+    d.R[3] = cz * sy * sx - cx * sz; d.R[4] = cx * cz + sx * sy * sz; d.R[5] = cy * sx;
+    d.R[6] = sx * sz + cx * cz * sy; d.R[7] = cx * sy * sz - cz * sx; d.R[8] = cx * cy;
+    // transpose_mat, src/Trace.cl:109-116
+    d.Rinv[0] = d.R[0]; d.Rinv[1] = d.R[3]; d.Rinv[2] = d.R[6];
+    d.Rinv[3] = d.R[1]; d.Rinv[4] = d.R[4]; d.Rinv[5] = d.R[7];
+    d.Rinv[6] = d.R[2]; d.Rinv[7] = d.R[5]; d.Rinv[8] = d.R[8];
+    d.pos[0] = m.pos.s[0]; d.pos[1] = m.pos.s[1]; d.pos[2] = m.pos.s[2];
+    d.scale = m.scale;
+    const uint32_t s = mesh_seg[i];
+    for (int k = 0; k < 3; ++k) { d.bmin[k] = seg_box[6 * s + k]; d.bmax[k] = seg_box[6 * s + 3 + k]; }
+    d.sfirst = seg_sfirst[s];
+    d.count = seg_count[s];
+    const int t = m.material.type;
+    d.cull = (t != RR_MATERIAL_GLASSY && t != RR_MATERIAL_INVISIBLE && t != RR_MATERIAL_ONESIDED) ? 1 : 0;  // :460-462
+    d.type = t;
+    d.skip = (m.scale <= RR_EPSILON || d.count == 0) ? 1 : 0;  // :448
+    d.material = i;
+    d.pad[0] = d.pad[1] = 0;
+    out[i] = d;
+  } else {
+    src = &spheres[i - n_meshes].material;
+  }
+  DMaterial mm;
+  mm.type = src->type;
+  mm.ior = src->ior;
+  mm.emissionStrength = src->emissionStrength;
+  mm.reflectiveness = src->reflectiveness;
+  mm.specularProbability = src->specularProbability;
+  for (int k = 0; k < 3; ++k) { mm.color[k] = src->color.s[k]; mm.emissionColor[k] = src->emissionColor.s[k]; }
+  mm.pad = 0.0f;
+  mats[i] = mm;
+}
+
+static void free_scene(Device& d) {
+  cudaSetDevice(d.ordinal);
+  cudaFree(d.tris); cudaFree(d.spheres); cudaFree(d.tri_box); cudaFree(d.sph_box);
+  cudaFree(d.tri_geom); cudaFree(d.tri_nrm); cudaFree(d.sph_geom); cudaFree(d.meshes); cudaFree(d.materials);
+  d.tris = nullptr; d.spheres = nullptr; d.tri_box = nullptr; d.sph_box = nullptr;
+  d.tri_geom = d.tri_nrm = d.sph_geom = nullptr; d.meshes = nullptr; d.materials = nullptr;
+  lbvh_free(d.tb);
+  lbvh_free(d.sb);
+}
+
+struct SegPlan {
+  std::vector<uint32_t> first, count;  // sorted, non-overlapping, unique
+  std::vector<uint32_t> mesh_seg;      // mesh -> segment
+};
+
+static int plan_segments(const rr_mesh_range* ranges, size_t n_meshes, size_t n_tris, SegPlan& plan) {
+  struct R { uint64_t first, count; };
+  std::vector<R> uniq;
+  for (size_t i = 0; i < n_meshes; ++i) {
+    if (ranges[i].firstTriangle > n_tris || ranges[i].numTriangles > n_tris - ranges[i].firstTriangle)
+      return fail(RR_ERR_BAD_MESH_RANGE, "mesh " + std::to_string(i) + ": triangle range outside the array");
+    uniq.push_back({ranges[i].firstTriangle, ranges[i].numTriangles});
+  }
+  std::sort(uniq.begin(), uniq.end(), [](const R& a, const R& b) { return a.first != b.first ? a.first < b.first : a.count < b.count; });
+  uniq.erase(std::unique(uniq.begin(), uniq.end(), [](const R& a, const R& b) { return a.first == b.first && a.count == b.count; }), uniq.end());
+  for (size_t k = 1; k < uniq.size(); ++k)
+    if (uniq[k - 1].first + uniq[k - 1].count > uniq[k].first)
+      return fail(RR_ERR_BAD_MESH_RANGE, "mesh triangle ranges overlap without being identical");
+  plan.first.clear(); plan.count.clear();
+  for (auto& r : uniq) { plan.first.push_back((uint32_t)r.first); plan.count.push_back((uint32_t)r.count); }
+  plan.mesh_seg.resize(n_meshes);
+  for (size_t i = 0; i < n_meshes; ++i) {
+    for (size_t k = 0; k < uniq.size(); ++k)
+      if (uniq[k].first == ranges[i].firstTriangle && uniq[k].count == ranges[i].numTriangles) { plan.mesh_seg[i] = (uint32_t)k; break; }
+  }
+  return RR_OK;
+}
+
+static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, const rr_mesh* meshes, size_t n_meshes,
+                         const SegPlan& plan, const rr_sphere* spheres, size_t n_spheres) {
+  RR_CUDA(cudaSetDevice(d.ordinal));
+  free_scene(d);
+  cudaStream_t st = d.stream;
+  RR_CUDA(cudaMalloc(&d.tris, std::max<size_t>(n_tris, 1) * sizeof(rr_triangle)));
+  RR_CUDA(cudaMalloc(&d.tri_box, std::max<size_t>(n_tris, 1) * 24));
+  RR_CUDA(cudaMalloc(&d.spheres, std::max<size_t>(n_spheres, 1) * sizeof(rr_sphere)));
+  RR_CUDA(cudaMalloc(&d.sph_box, std::max<size_t>(n_spheres, 1) * 24));
+  if (n_tris) RR_CUDA(cudaMemcpyAsync(d.tris, tris, n_tris * sizeof(rr_triangle), cudaMemcpyHostToDevice, st));
+  if (n_spheres) RR_CUDA(cudaMemcpyAsync(d.spheres, spheres, n_spheres * sizeof(rr_sphere), cudaMemcpyHostToDevice, st));
+  RR_CUDA(cudaEventRecord(d.ev0, st));
+  RR_CUDA(launch_tri_boxes(d.tris, n_tris, d.tri_box, st));
+  RR_CUDA(lbvh_build(d.tb, d.tri_box, n_tris, plan.first.data(), plan.count.data(), (uint32_t)plan.first.size(), st));
+  RR_CUDA(cudaMalloc(&d.tri_geom, std::max<uint64_t>(d.tb.n, 1) * 48));
+  RR_CUDA(cudaMalloc(&d.tri_nrm, std::max<uint64_t>(d.tb.n, 1) * 48));
+  RR_CUDA(launch_pack_tris(d.tris, d.tb.order, d.tb.n, d.tri_geom, d.tri_nrm, st));
+  RR_CUDA(launch_sphere_boxes(d.spheres, n_spheres, d.sph_box, st));
+  uint32_t sf = 0, sc = (uint32_t)n_spheres;
+  RR_CUDA(lbvh_build(d.sb, d.sph_box, n_spheres, &sf, &sc, n_spheres ? 1u : 0u, st));
+  RR_CUDA(cudaMalloc(&d.sph_geom, std::max<size_t>(n_spheres, 1) * 16));
+  RR_CUDA(launch_pack_spheres(d.spheres, d.sb.order, d.sb.n, d.sph_geom, st));
+  if (n_spheres) RR_CUDA(cudaMemcpyAsync(d.sph_bounds, d.sb.seg_box, 24, cudaMemcpyDeviceToHost, st));
+  // mesh + material tables
+  rr_mesh* d_meshes_in = nullptr;
+  uint32_t* d_mesh_seg = nullptr;
+  RR_CUDA(cudaMalloc(&d_meshes_in, std::max<size_t>(n_meshes, 1) * sizeof(rr_mesh)));
+  RR_CUDA(cudaMalloc(&d_mesh_seg, std::max<size_t>(n_meshes, 1) * 4));
+  RR_CUDA(cudaMalloc(&d.meshes, std::max<size_t>(n_meshes, 1) * sizeof(DMesh)));
+  RR_CUDA(cudaMalloc(&d.materials, std::max<size_t>(n_meshes + n_spheres, 1) * sizeof(DMaterial)));
+  if (n_meshes) {
+    RR_CUDA(cudaMemcpyAsync(d_meshes_in, meshes, n_meshes * sizeof(rr_mesh), cudaMemcpyHostToDevice, st));
+    RR_CUDA(cudaMemcpyAsync(d_mesh_seg, plan.mesh_seg.data(), n_meshes * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (n_meshes + n_spheres) {
+    const int n = (int)(n_meshes + n_spheres);
+    k_prepare_meshes<<<(n + 127) / 128, 128, 0, st>>>(d_meshes_in, d_mesh_seg, (int)n_meshes, d.tb.seg_box, d.tb.seg_sfirst,
+                                                      d.tb.seg_count, d.spheres, (int)n_spheres, d.meshes, d.materials);
+    RR_CUDA(cudaGetLastError());
+  }
+  RR_CUDA(cudaEventRecord(d.ev1, st));
+  RR_CUDA(cudaStreamSynchronize(st));
+  RR_CUDA(cudaEventElapsedTime(&d.build_ms, d.ev0, d.ev1));
+  cudaFree(d_meshes_in);
+  cudaFree(d_mesh_seg);
+  if (d.tb.max_depth > RR_STACK || d.sb.max_depth > RR_STACK)
+    return fail(RR_ERR_BVH_DEPTH, "LBVH depth " + std::to_string(std::max(d.tb.max_depth, d.sb.max_depth)) +
+                                      " exceeds the traversal stack (" + std::to_string(RR_STACK) + ")");
+  return RR_OK;
+}
+
+static int ensure_frame(Device& d, uint32_t W, uint32_t H, bool want_radiance) {
+  RR_CUDA(cudaSetDevice(d.ordinal));
+  const size_t need = (size_t)W * H * 4;
+  if (need > d.frame_bytes) {
+    cudaFree(d.frame);
+    d.frame = nullptr; d.frame_bytes = 0;
+    RR_CUDA(cudaMalloc(&d.frame, need));
+    d.frame_bytes = need;
+  }
+  const size_t rneed = (size_t)W * H * 12;
+  if (want_radiance && rneed > d.radiance_bytes) {
+    cudaFree(d.radiance);
+    d.radiance = nullptr; d.radiance_bytes = 0;
+    RR_CUDA(cudaMalloc(&d.radiance, rneed));
+    d.radiance_bytes = rneed;
+  }
+  return RR_OK;
+}
+
+static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam, uint32_t W, uint32_t H, uint32_t spp,
+                        uint32_t bounces, int32_t frame_index, uint32_t tile_size, RenderParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.meshes = d.meshes;
+  p.n_meshes = (int32_t)ctx->n_meshes;
+  p.materials = d.materials;
+  p.tri_nodes = d.tb.nodes;
+  p.tri_geom = d.tri_geom;
+  p.tri_nrm = d.tri_nrm;
+  p.n_spheres = (int32_t)ctx->n_spheres;
+  p.sph_nodes = d.sb.nodes;
+  p.sph_geom = d.sph_geom;
+  p.sph_order = d.sb.order;
+  for (int k = 0; k < 3; ++k) { p.sph_bmin[k] = d.sph_bounds[k]; p.sph_bmax[k] = d.sph_bounds[3 + k]; }
+  for (int k = 0; k < 3; ++k) p.cam.pos[k] = cam->position.s[k];
+  p.cam.pitch = cam->pitch; p.cam.yaw = cam->yaw; p.cam.roll = cam->roll; p.cam.fov = cam->fov; p.cam.aspect = cam->aspectRatio;
+  p.width = W; p.height = H; p.spp = spp; p.max_bounces = bounces; p.frame_index = frame_index;
+  p.tile_w = tile_size ? tile_size : RR_TILE_W;
+  p.tile_h = tile_size ? tile_size : RR_TILE_H;
+  p.tiles_x = (W + p.tile_w - 1) / p.tile_w;
+  p.tiles_y = (H + p.tile_h - 1) / p.tile_h;
+  p.tile_begin = 0;
+  p.tile_stride = 1;
+  p.queue = d.queue;
+  p.frame = d.frame;
+  p.radiance = nullptr;
+  p.counters = d.counters;
+}
+
+static int check_render_args(const rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t H, uint32_t spp) {
+  if (!ctx || !cam) return fail(RR_ERR_INVALID_ARGUMENT, "null context or camera");
+  if (!ctx->has_scene) return fail(RR_ERR_NO_SCENE, "rr_upload_scene has not been called");
+  if (W == 0 || H == 0 || spp == 0) return fail(RR_ERR_INVALID_ARGUMENT, "width, height and spp must be positive");
+  if ((uint64_t)W * H > 0x7fffffffull) return fail(RR_ERR_INVALID_ARGUMENT, "image too large (pixel index must fit 31 bits)");
+  return RR_OK;
+}
+
+static void read_stats(const Counters& c, uint64_t samples, float ms, float build_ms, rr_stats* out) {
+  if (!out) return;
+  out->samples = samples;
+  out->rays = c.rays;
+  out->rays_reused = c.rays_reused;
+  out->box_tests = c.box_tests;
+  out->tri_tests = c.tri_tests;
+  out->sphere_tests = c.sphere_tests;
+  out->tiles = c.tiles;
+  out->render_ms = ms;
+  out->build_ms = build_ms;
+}
+
+// Renders one frame on all devices of the context.  Device 0 owns the queue and
+// the frame; peers (in-process multi-GPU) address them directly over NVLink.
+static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t H, uint32_t spp, uint32_t bounces,
+                        int32_t frame_index, uint32_t tile_size, bool want_radiance, bool count_tests, int mode,
+                        uint32_t rank, uint32_t world, rr_stats* stats_out) {
+  // mode 0: local queue, 1: shared (imported/exported) queue + frame, 2: static stride partition
+  int rc = check_render_args(ctx, cam, W, H, spp);
+  if (rc) return rc;
+  const size_t nd = ctx->dev.size();
+  if (want_radiance && nd > 1) return fail(RR_ERR_UNSUPPORTED, "radiance output needs a single-device context");
+  Device& d0 = ctx->dev[0];
+  for (size_t k = 0; k < nd; ++k) {
+    rc = ensure_frame(ctx->dev[k], W, H, want_radiance);
+    if (rc) return rc;
+  }
+  RR_CUDA(cudaSetDevice(d0.ordinal));
+  if (mode != 1) {
+    RR_CUDA(cudaMemsetAsync(d0.queue, 0, sizeof(unsigned long long), d0.stream));
+    if (mode == 2) RR_CUDA(cudaMemsetAsync(d0.frame, 0, (size_t)W * H * 4, d0.stream));
+  } else if (!d0.shared_queue) {
+    return fail(RR_ERR_INVALID_ARGUMENT, "rr_render_shared needs rr_queue_export or rr_queue_import first");
+  }
+  RR_CUDA(cudaStreamSynchronize(d0.stream));
+  for (size_t k = 0; k < nd; ++k) {
+    Device& d = ctx->dev[k];
+    RR_CUDA(cudaSetDevice(d.ordinal));
+    RR_CUDA(cudaMemsetAsync(d.counters, 0, sizeof(Counters), d.stream));
+    RenderParams p;
+    fill_params(ctx, d, cam, W, H, spp, bounces, frame_index, tile_size, p);
+    if (mode == 1) {
+      p.queue = d.shared_queue;
+      p.frame = d.shared_frame;
+    } else {
+      p.queue = d0.queue;  // peers pop device 0's counter
+      p.frame = d0.frame;
+      if (mode == 2) { p.tile_begin = rank; p.tile_stride = world; }
+    }
+    if (want_radiance) p.radiance = d.radiance;
+    RR_CUDA(cudaEventRecord(d.ev0, d.stream));
+    RR_CUDA(launch_render(p, count_tests, d.sm_count, d.stream));
+    RR_CUDA(cudaEventRecord(d.ev1, d.stream));
+  }
+  Counters total;
+  memset(&total, 0, sizeof(total));
+  float ms_max = 0.0f;
+  for (size_t k = 0; k < nd; ++k) {
+    Device& d = ctx->dev[k];
+    RR_CUDA(cudaSetDevice(d.ordinal));
+    RR_CUDA(cudaStreamSynchronize(d.stream));
+    float ms = 0.0f;
+    RR_CUDA(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+    ms_max = std::max(ms_max, ms);
+    Counters c;
+    RR_CUDA(cudaMemcpy(&c, d.counters, sizeof(c), cudaMemcpyDeviceToHost));
+    total.rays += c.rays; total.rays_reused += c.rays_reused; total.box_tests += c.box_tests;
+    total.tri_tests += c.tri_tests; total.sphere_tests += c.sphere_tests; total.tiles += c.tiles;
+  }
+  read_stats(total, (uint64_t)W * H * spp, ms_max, d0.build_ms, stats_out);
+  return RR_OK;
+}
+
+}  // namespace rr
+
+using namespace rr;
+
+extern "C" {
+
+const char* rr_error_string(int status) {
+  switch (status) {
+    case RR_OK: return "success";
+    case RR_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case RR_ERR_NO_DEVICE: return "no usable CUDA device";
+    case RR_ERR_CUDA: return "CUDA runtime error";
+    case RR_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case RR_ERR_NO_SCENE: return "no scene uploaded";
+    case RR_ERR_BAD_MESH_RANGE: return "bad mesh triangle range";
+    case RR_ERR_BVH_DEPTH: return "BVH deeper than the traversal stack";
+    case RR_ERR_IO: return "I/O error";
+    case RR_ERR_UNSUPPORTED: return "unsupported";
+    default: return "unknown status";
+  }
+}
+const char* rr_last_error(void) { return g_last_error.c_str(); }
+int rr_version(void) { return 100; }
+
+int rr_device_count(int* out) {
+  if (!out) return fail(RR_ERR_INVALID_ARGUMENT, "null output");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *out = 0; cudaGetLastError(); return fail(RR_ERR_NO_DEVICE, cudaGetErrorString(e)); }
+  *out = n;
+  return RR_OK;
+}
+
+int rr_device_info(int ordinal, char* name, size_t name_len, int* sm_count, uint64_t* mem_bytes) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, ordinal);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(RR_ERR_NO_DEVICE, cudaGetErrorString(e)); }
+  if (name && name_len) { strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (mem_bytes) *mem_bytes = (uint64_t)prop.totalGlobalMem;
+  return RR_OK;
+}
+
+int rr_create(const int* cuda_ordinals, int n, rr_ctx** out) {
+  if (!out) return fail(RR_ERR_INVALID_ARGUMENT, "null output");
+  *out = nullptr;
+  int count = 0;
+  int rc = rr_device_count(&count);
+  if (rc) return rc;
+  if (count == 0) return fail(RR_ERR_NO_DEVICE, "cudaGetDeviceCount() == 0");
+  int def = 0;
+  if (!cuda_ordinals || n <= 0) { cuda_ordinals = &def; n = 1; }
+  rr_ctx* ctx = new rr_ctx();
+  ctx->dev.resize(n);
+  for (int k = 0; k < n; ++k) {
+    Device& d = ctx->dev[k];
+    d.ordinal = cuda_ordinals[k];
+    if (d.ordinal < 0 || d.ordinal >= count) { delete ctx; return fail(RR_ERR_NO_DEVICE, "device ordinal out of range"); }
+    cudaError_t e = cudaSetDevice(d.ordinal);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, d.ordinal);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&d.ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&d.ev1);
+    if (e == cudaSuccess) e = cudaMalloc(&d.queue, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&d.counters, sizeof(Counters));
+    if (e != cudaSuccess) { rr_destroy(ctx); return cuda_fail(e, "rr_create"); }
+    d.sm_count = prop.multiProcessorCount;
+  }
+  ctx->peer_ok = true;
+  for (int k = 1; k < n; ++k) {  // peers must reach device 0 (queue + frame live there)
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, ctx->dev[k].ordinal, ctx->dev[0].ordinal);
+    if (!can) { ctx->peer_ok = false; break; }
+    cudaSetDevice(ctx->dev[k].ordinal);
+    cudaError_t e = cudaDeviceEnablePeerAccess(ctx->dev[0].ordinal, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ctx->peer_ok = false;
+    cudaGetLastError();
+  }
+  if (n > 1 && !ctx->peer_ok) { rr_destroy(ctx); return fail(RR_ERR_UNSUPPORTED, "multi-device context needs peer access to device 0"); }
+  *out = ctx;
+  return RR_OK;
+}
+
+void rr_destroy(rr_ctx* ctx) {
+  if (!ctx) return;
+  for (Device& d : ctx->dev) {
+    if (d.ordinal < 0) continue;
+    cudaSetDevice(d.ordinal);
+    if (d.stream) cudaStreamSynchronize(d.stream);
+    free_scene(d);
+    if (d.shared_imported) {
+      if (d.shared_queue) cudaIpcCloseMemHandle(d.shared_queue);
+      if (d.shared_frame) cudaIpcCloseMemHandle(d.shared_frame);
+    }
+    cudaFree(d.frame); cudaFree(d.radiance); cudaFree(d.queue); cudaFree(d.counters);
+    if (d.ev0) cudaEventDestroy(d.ev0);
+    if (d.ev1) cudaEventDestroy(d.ev1);
+    if (d.stream) cudaStreamDestroy(d.stream);
+  }
+  cudaGetLastError();
+  delete ctx;
+}
+
+int rr_upload_scene(rr_ctx* ctx, const rr_triangle* tris, size_t n_tris, const rr_mesh* meshes,
+                    const rr_mesh_range* ranges, size_t n_meshes, const rr_sphere* spheres, size_t n_spheres) {
+  if (!ctx) return fail(RR_ERR_INVALID_ARGUMENT, "null context");
+  if ((n_tris && !tris) || (n_meshes && (!meshes || !ranges)) || (n_spheres && !spheres))
+    return fail(RR_ERR_INVALID_ARGUMENT, "null array with non-zero count");
+  if (n_tris >= 0x7fffffffull || n_spheres >= 0x7fffffffull) return fail(RR_ERR_INVALID_ARGUMENT, "too many primitives (31-bit indices)");
+  SegPlan plan;
+  int rc = plan_segments(ranges, n_meshes, n_tris, plan);
+  if (rc) return rc;
+  ctx->has_scene = false;
+  for (Device& d : ctx->dev) {
+    rc = upload_device(d, tris, n_tris, meshes, n_meshes, plan, spheres, n_spheres);
+    if (rc) return rc;
+  }
+  ctx->n_tris = n_tris; ctx->n_meshes = n_meshes; ctx->n_spheres = n_spheres;
+  ctx->has_scene = true;
+  return RR_OK;
+}
+
+int rr_upload_scene_ref(rr_ctx* ctx, const rr_triangle* tris, size_t n_tris, const rr_mesh* meshes, size_t n_meshes,
+                        const rr_ref_node* nodes, size_t n_nodes) {
+  if (n_meshes && !nodes) return fail(RR_ERR_INVALID_ARGUMENT, "null node list");
+  std::vector<rr_mesh_range> ranges(n_meshes);
+  std::vector<uint64_t> stack;
+  for (size_t i = 0; i < n_meshes; ++i) {
+    uint64_t lo = UINT64_MAX, hi = 0;
+    stack.assign(1, meshes[i].nodeIdx);
+    size_t visited = 0;
+    while (!stack.empty()) {
+      uint64_t ni = stack.back();
+      stack.pop_back();
+      if (ni >= n_nodes || ++visited > n_nodes) return fail(RR_ERR_BAD_MESH_RANGE, "mesh " + std::to_string(i) + ": node index outside nodeList");
+      const rr_ref_node& nd = nodes[ni];
+      if (nd.numTriangles > 0) {  // leaf (an unsplit OBJ root keeps childIndex != 0 but is still a leaf)
+        lo = std::min(lo, nd.firstTriangleIdx);
+        hi = std::max(hi, nd.firstTriangleIdx + nd.numTriangles);
+      } else if (nd.childIndex != 0) {
+        stack.push_back(nd.childIndex);
+        stack.push_back(nd.childIndex + 1);
+      }
+    }
+    ranges[i].firstTriangle = lo == UINT64_MAX ? 0 : lo;
+    ranges[i].numTriangles = lo == UINT64_MAX ? 0 : hi - lo;
+  }
+  return rr_upload_scene(ctx, tris, n_tris, meshes, ranges.data(), n_meshes, nullptr, 0);
+}
+
+int rr_render_ex(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
+                 uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, uint8_t* rgba_out,
+                 float* radiance_out, rr_stats* stats_out, int count_tests) {
+  int rc = render_frame(ctx, cam, width, height, spp, max_bounces, frame_index, tile_size, radiance_out != nullptr,
+                        count_tests != 0, 0, 0, 1, stats_out);
+  if (rc) return rc;
+  Device& d0 = ctx->dev[0];
+  RR_CUDA(cudaSetDevice(d0.ordinal));
+  if (rgba_out) RR_CUDA(cudaMemcpy(rgba_out, d0.frame, (size_t)width * height * 4, cudaMemcpyDeviceToHost));
+  if (radiance_out) RR_CUDA(cudaMemcpy(radiance_out, d0.radiance, (size_t)width * height * 12, cudaMemcpyDeviceToHost));
+  return RR_OK;
+}
+
+int rr_render(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_bounces,
+              int32_t frame_index, uint32_t tile_size, uint8_t* rgba_out) {
+  if (!rgba_out) return fail(RR_ERR_INVALID_ARGUMENT, "null output image");
+  return rr_render_ex(ctx, cam, width, height, spp, max_bounces, frame_index, tile_size, rgba_out, nullptr, nullptr, 0);
+}
+
+int rr_render_device(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
+                     uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, rr_stats* stats_out) {
+  return render_frame(ctx, cam, width, height, spp, max_bounces, frame_index, tile_size, false, false, 0, 0, 1, stats_out);
+}
+
+int rr_read_frame(rr_ctx* ctx, uint8_t* rgba_out, size_t bytes) {
+  if (!ctx || !rgba_out) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
+  Device& d0 = ctx->dev[0];
+  const uint8_t* src = d0.shared_frame && !d0.shared_imported ? d0.shared_frame : d0.frame;
+  if (!src || bytes > d0.frame_bytes) return fail(RR_ERR_INVALID_ARGUMENT, "no frame of that size has been rendered");
+  RR_CUDA(cudaSetDevice(d0.ordinal));
+  RR_CUDA(cudaMemcpy(rgba_out, src, bytes, cudaMemcpyDeviceToHost));
+  return RR_OK;
+}
+
+int rr_primary_hits(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, int32_t* mesh_out,
+                    int32_t* prim_out, float* dst_out) {
+  int rc = check_render_args(ctx, cam, width, height, 1);
+  if (rc) return rc;
+  Device& d = ctx->dev[0];
+  RR_CUDA(cudaSetDevice(d.ordinal));
+  const size_t n = (size_t)width * height;
+  int32_t *dm = nullptr, *dp = nullptr;
+  float* dd = nullptr;
+  RR_CUDA(cudaMalloc(&dm, n * 4));
+  RR_CUDA(cudaMalloc(&dp, n * 4));
+  RR_CUDA(cudaMalloc(&dd, n * 4));
+  RenderParams p;
+  fill_params(ctx, d, cam, width, height, 1, 1, 0, 0, p);
+  p.hit_mesh = dm; p.hit_prim = dp; p.hit_dst = dd;
+  cudaError_t e = launch_primary(p, d.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+  if (e == cudaSuccess && mesh_out) e = cudaMemcpy(mesh_out, dm, n * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && prim_out) e = cudaMemcpy(prim_out, dp, n * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && dst_out) e = cudaMemcpy(dst_out, dd, n * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dm); cudaFree(dp); cudaFree(dd);
+  if (e != cudaSuccess) return cuda_fail(e, "rr_primary_hits");
+  return RR_OK;
+}
+
+int rr_bvh_size(rr_ctx* ctx, int which, uint64_t* n_prims) {
+  if (!ctx || !n_prims) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
+  if (!ctx->has_scene) return fail(RR_ERR_NO_SCENE, "no scene");
+  *n_prims = which ? ctx->dev[0].sb.n : ctx->dev[0].tb.n;
+  return RR_OK;
+}
+
+int rr_bvh_read(rr_ctx* ctx, int which, uint64_t* codes, uint32_t* order, int32_t* left, int32_t* right,
+                int32_t* parent, float* bounds) {
+  if (!ctx) return fail(RR_ERR_INVALID_ARGUMENT, "null context");
+  if (!ctx->has_scene) return fail(RR_ERR_NO_SCENE, "no scene");
+  Device& d = ctx->dev[0];
+  RR_CUDA(cudaSetDevice(d.ordinal));
+  const Lbvh& b = which ? d.sb : d.tb;
+  const size_t n = b.n;
+  if (!n) return RR_OK;
+  if (codes) RR_CUDA(cudaMemcpy(codes, b.codes, n * 8, cudaMemcpyDeviceToHost));
+  if (order) RR_CUDA(cudaMemcpy(order, b.order, n * 4, cudaMemcpyDeviceToHost));
+  if (left) RR_CUDA(cudaMemcpy(left, b.left, n * 4, cudaMemcpyDeviceToHost));
+  if (right) RR_CUDA(cudaMemcpy(right, b.right, n * 4, cudaMemcpyDeviceToHost));
+  if (parent) RR_CUDA(cudaMemcpy(parent, b.parent, n * 4, cudaMemcpyDeviceToHost));
+  if (bounds) RR_CUDA(cudaMemcpy(bounds, b.bounds, n * 24, cudaMemcpyDeviceToHost));
+  return RR_OK;
+}
+
+// ---- multi-process tile queue -------------------------------------------------
+int rr_queue_export(rr_ctx* ctx, uint32_t width, uint32_t height, uint8_t* queue_handle, uint8_t* frame_handle) {
+  if (!ctx || !queue_handle || !frame_handle) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == RR_IPC_HANDLE_BYTES, "IPC handle size");
+  Device& d = ctx->dev[0];
+  int rc = ensure_frame(d, width, height, false);
+  if (rc) return rc;
+  cudaIpcMemHandle_t hq, hf;
+  RR_CUDA(cudaIpcGetMemHandle(&hq, d.queue));
+  RR_CUDA(cudaIpcGetMemHandle(&hf, d.frame));
+  memcpy(queue_handle, &hq, sizeof(hq));
+  memcpy(frame_handle, &hf, sizeof(hf));
+  d.shared_queue = d.queue;
+  d.shared_frame = d.frame;
+  d.shared_imported = false;
+  return RR_OK;
+}
+
+int rr_queue_import(rr_ctx* ctx, uint32_t width, uint32_t height, const uint8_t* queue_handle,
+                    const uint8_t* frame_handle) {
+  if (!ctx || !queue_handle || !frame_handle) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
+  Device& d = ctx->dev[0];
+  RR_CUDA(cudaSetDevice(d.ordinal));
+  int rc = ensure_frame(d, width, height, false);
+  if (rc) return rc;
+  if (d.shared_imported) {
+    if (d.shared_queue) cudaIpcCloseMemHandle(d.shared_queue);
+    if (d.shared_frame) cudaIpcCloseMemHandle(d.shared_frame);
+    d.shared_queue = nullptr; d.shared_frame = nullptr; d.shared_imported = false;
+  }
+  cudaIpcMemHandle_t hq, hf;
+  memcpy(&hq, queue_handle, sizeof(hq));
+  memcpy(&hf, frame_handle, sizeof(hf));
+  void *pq = nullptr, *pf = nullptr;
+  RR_CUDA(cudaIpcOpenMemHandle(&pq, hq, cudaIpcMemLazyEnablePeerAccess));
+  RR_CUDA(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+  d.shared_queue = (unsigned long long*)pq;
+  d.shared_frame = (uint8_t*)pf;
+  d.shared_imported = true;
+  return RR_OK;
+}
+
+int rr_queue_reset(rr_ctx* ctx) {
+  if (!ctx) return fail(RR_ERR_INVALID_ARGUMENT, "null context");
+  Device& d = ctx->dev[0];
+  if (!d.shared_queue || d.shared_imported) return fail(RR_ERR_INVALID_ARGUMENT, "only the exporting rank resets the queue");
+  RR_CUDA(cudaSetDevice(d.ordinal));
+  RR_CUDA(cudaMemset(d.shared_queue, 0, sizeof(unsigned long long)));
+  return RR_OK;
+}
+
+int rr_render_shared(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
+                     uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, rr_stats* stats_out) {
+  return render_frame(ctx, cam, width, height, spp, max_bounces, frame_index, tile_size, false, false, 1, 0, 1, stats_out);
+}
+
+int rr_render_strided(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
+                      uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, uint32_t rank, uint32_t world,
+                      rr_stats* stats_out) {
+  if (world == 0 || rank >= world) return fail(RR_ERR_INVALID_ARGUMENT, "rank/world");
+  return render_frame(ctx, cam, width, height, spp, max_bounces, frame_index, tile_size, false, false, 2, rank, world, stats_out);
+}
+
+int rr_frame_device_ptr(rr_ctx* ctx, uint64_t* ptr_out, uint64_t* bytes_out) {
+  if (!ctx || !ptr_out) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
+  *ptr_out = (uint64_t)(uintptr_t)ctx->dev[0].frame;
+  if (bytes_out) *bytes_out = ctx->dev[0].frame_bytes;
+  return RR_OK;
+}
+
+// ---- probes used by the parity tests (not part of include/rr_api.h) ------------
+int rr_probe_math(int fn, const float* x, const float* y, float* out, uint64_t n) {
+  float *dx = nullptr, *dy = nullptr, *dout = nullptr;
+  RR_CUDA(cudaMalloc(&dx, n * 4 + 4));
+  RR_CUDA(cudaMalloc(&dy, n * 4 + 4));
+  RR_CUDA(cudaMalloc(&dout, n * 4 + 4));
+  RR_CUDA(cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice));
+  RR_CUDA(cudaMemcpy(dy, y ? y : x, n * 4, cudaMemcpyHostToDevice));
+  cudaError_t e = launch_math_probe(fn, dx, dy, dout, n, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dx); cudaFree(dy); cudaFree(dout);
+  if (e != cudaSuccess) return cuda_fail(e, "rr_probe_math");
+  return RR_OK;
+}
+
+int rr_probe_rng(uint32_t pixel, int32_t frame, uint32_t* out_u32_8, float* out_f32_9) {
+  uint32_t* du = nullptr;
+  float* df = nullptr;
+  RR_CUDA(cudaMalloc(&du, 8 * 4));
+  RR_CUDA(cudaMalloc(&df, 9 * 4));
+  cudaError_t e = launch_rng_probe(pixel, frame, du, df, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(out_u32_8, du, 32, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(out_f32_9, df, 36, cudaMemcpyDeviceToHost);
+  cudaFree(du); cudaFree(df);
+  if (e != cudaSuccess) return cuda_fail(e, "rr_probe_rng");
+  return RR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,293 @@
+// rr_host.cpp -- host-side formats either side of the render path: the OBJ
+// triangle input (reference src/readobj.hpp:270-376), the scene assembly
+// helpers (addQuad src/readobj.hpp:378-408, addCornellBoxToScene
+// src/image.hpp:401-448), the default camera (src/main.cpp:299-304,
+// src/settings.hpp:23-28) and the output.bmp writer (src/math.hpp:117-164).
+// Pure C++; no CUDA in this file.
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "../../include/rr_api.h"
+
+struct rr_scene {
+  std::vector<rr_triangle> tris;
+  std::vector<rr_mesh> meshes;
+  std::vector<rr_mesh_range> ranges;
+  std::vector<rr_sphere> spheres;
+};
+
+namespace {
+
+rr_float3 f3(float x, float y, float z) {
+  rr_float3 r;
+  r.s[0] = x; r.s[1] = y; r.s[2] = z; r.s[3] = 0.0f;
+  return r;
+}
+
+rr_material solid(rr_float3 color) {
+  rr_material m;
+  memset(&m, 0, sizeof(m));
+  m.type = RR_MATERIAL_SOLID;
+  m.ior = 1.0f;  // struct default, src/readobj.hpp:50
+  m.color = color;
+  return m;
+}
+
+rr_mesh default_mesh() {
+  rr_mesh m;
+  memset(&m, 0, sizeof(m));
+  m.scale = 1.0f;  // src/readobj.hpp:79
+  m.material = solid(f3(1.0f, 1.0f, 1.0f));
+  return m;
+}
+
+// One face corner: "v/vt/vn" or "v//vn".  Returns chars consumed, 0 on failure.
+bool parse_corner(const char*& p, long& v, long& n) {
+  char* end;
+  while (*p == ' ' || *p == '\t') ++p;
+  v = strtol(p, &end, 10);
+  if (end == p || *end != '/') return false;
+  p = end + 1;
+  if (*p == '/') {
+    ++p;
+  } else {
+    strtol(p, &end, 10);  // texture index, unused
+    if (end == p || *end != '/') return false;
+    p = end + 1;
+  }
+  n = strtol(p, &end, 10);
+  if (end == p) return false;
+  p = end;
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rr_scene_create(rr_scene** out) {
+  if (!out) return RR_ERR_INVALID_ARGUMENT;
+  *out = new rr_scene();
+  return RR_OK;
+}
+void rr_scene_destroy(rr_scene* s) { delete s; }
+
+int rr_scene_add_triangles(rr_scene* s, const rr_triangle* tris, size_t n, rr_mesh_range* range_out) {
+  if (!s || (n && !tris)) return RR_ERR_INVALID_ARGUMENT;
+  const size_t first = s->tris.size();
+  s->tris.insert(s->tris.end(), tris, tris + n);
+  if (range_out) { range_out->firstTriangle = first; range_out->numTriangles = n; }
+  return RR_OK;
+}
+
+// OBJ dialect of the reference loader: `v x y z`, `vn x y z`, `f a/b/c ...` or
+// `f a//c ...` with exactly the first three corners used (a 4th is ignored,
+// src/readobj.hpp:307-312); 1-based indices; normals mandatory.  Unlike the
+// reference, a face that fails to parse or indexes out of bounds is skipped
+// WITHOUT corrupting the mesh's triangle range (the reference counts it in
+// triCount before validating, src/readobj.hpp:305,346).
+int rr_scene_load_obj(rr_scene* s, const char* path, rr_mesh* mesh_out, rr_mesh_range* range_out) {
+  if (!s || !path) return RR_ERR_INVALID_ARGUMENT;
+  std::ifstream file(path);
+  if (!file) return RR_ERR_IO;
+  std::vector<rr_float3> verts, normals;
+  const size_t first = s->tris.size();
+  std::string line;
+  while (std::getline(file, line)) {
+    if (line.size() < 2) continue;
+    const char* c = line.c_str();
+    if (c[0] == 'v' && c[1] == ' ') {
+      float x, y, z;
+      if (sscanf(c, "v %f %f %f", &x, &y, &z) == 3) verts.push_back(f3(x, y, z));
+    } else if (c[0] == 'v' && c[1] == 'n' && c[2] == ' ') {
+      float x, y, z;
+      if (sscanf(c, "vn %f %f %f", &x, &y, &z) == 3) normals.push_back(f3(x, y, z));
+    } else if (c[0] == 'f' && c[1] == ' ') {
+      const char* p = c + 2;
+      long v[3], n[3];
+      bool ok = true;
+      for (int k = 0; k < 3 && ok; ++k) ok = parse_corner(p, v[k], n[k]);
+      if (!ok) continue;
+      for (int k = 0; k < 3; ++k) {
+        v[k] -= 1;
+        n[k] -= 1;
+        if (v[k] < 0 || (size_t)v[k] >= verts.size() || n[k] < 0 || (size_t)n[k] >= normals.size()) ok = false;
+      }
+      if (!ok) continue;
+      rr_triangle t;
+      t.posA = verts[v[0]]; t.posB = verts[v[1]]; t.posC = verts[v[2]];
+      t.normalA = normals[n[0]]; t.normalB = normals[n[1]]; t.normalC = normals[n[2]];
+      s->tris.push_back(t);
+    }
+  }
+  if (mesh_out) *mesh_out = default_mesh();  // src/readobj.hpp:369-375
+  if (range_out) { range_out->firstTriangle = first; range_out->numTriangles = s->tris.size() - first; }
+  return RR_OK;
+}
+
+// Root-node bounds of the OBJ loader (src/readobj.hpp:353-362), including its
+// initial value max = +FLT_MIN (src/readobj.hpp:16-17): geometry entirely below
+// zero on an axis reports max = 1.18e-38 there, which the Cornell box inherits.
+int rr_scene_range_bounds(const rr_scene* s, const rr_mesh_range* range, float* min3, float* max3) {
+  if (!s || !range || !min3 || !max3) return RR_ERR_INVALID_ARGUMENT;
+  if (range->firstTriangle + range->numTriangles > s->tris.size()) return RR_ERR_BAD_MESH_RANGE;
+  for (int a = 0; a < 3; ++a) { min3[a] = FLT_MAX; max3[a] = FLT_MIN; }
+  for (size_t i = 0; i < range->numTriangles; ++i) {
+    const rr_triangle& t = s->tris[range->firstTriangle + i];
+    for (int a = 0; a < 3; ++a) {
+      min3[a] = std::min(min3[a], std::min(t.posA.s[a], std::min(t.posB.s[a], t.posC.s[a])));
+      max3[a] = std::max(max3[a], std::max(t.posA.s[a], std::max(t.posB.s[a], t.posC.s[a])));
+    }
+  }
+  return RR_OK;
+}
+
+int rr_scene_add_mesh(rr_scene* s, const rr_mesh* mesh, const rr_mesh_range* range) {
+  if (!s || !mesh || !range) return RR_ERR_INVALID_ARGUMENT;
+  if (range->firstTriangle + range->numTriangles > s->tris.size()) return RR_ERR_BAD_MESH_RANGE;
+  s->meshes.push_back(*mesh);
+  s->ranges.push_back(*range);
+  return RR_OK;
+}
+
+int rr_scene_add_quad(rr_scene* s, const float* a, const float* b, const float* c, const float* d, const float* normal,
+                      const float* color) {
+  if (!s || !a || !b || !c || !d || !normal || !color) return RR_ERR_INVALID_ARGUMENT;
+  rr_mesh m = default_mesh();
+  m.material = solid(f3(color[0], color[1], color[2]));  // reflectiveness 0, specularProbability 0 (:394-402)
+  rr_mesh_range r;
+  r.firstTriangle = s->tris.size();
+  r.numTriangles = 2;
+  const rr_float3 A = f3(a[0], a[1], a[2]), B = f3(b[0], b[1], b[2]), C = f3(c[0], c[1], c[2]), D = f3(d[0], d[1], d[2]),
+                  N = f3(normal[0], normal[1], normal[2]);
+  rr_triangle t1 = {A, B, C, N, N, N}, t2 = {A, C, D, N, N, N};  // src/readobj.hpp:405-406
+  s->tris.push_back(t1);
+  s->tris.push_back(t2);
+  s->meshes.push_back(m);
+  s->ranges.push_back(r);
+  return RR_OK;
+}
+
+#define RR_CORNELL_BREATHING_ROOM 100.0f /* src/settings.hpp:52 */
+
+int rr_scene_add_cornell(rr_scene* s, const rr_mesh* mesh, const rr_mesh_range* range) {
+  if (!s || !mesh || !range) return RR_ERR_INVALID_ARGUMENT;
+  float bmin[3], bmax[3];
+  int rc = rr_scene_range_bounds(s, range, bmin, bmax);
+  if (rc) return rc;
+  // src/image.hpp:403-408
+  const float minX = (bmin[0] * mesh->scale) - RR_CORNELL_BREATHING_ROOM, maxX = (bmax[0] * mesh->scale) + RR_CORNELL_BREATHING_ROOM;
+  const float minY = (bmin[1] * mesh->scale), maxY = (bmax[1] * mesh->scale) + RR_CORNELL_BREATHING_ROOM;
+  const float minZ = (bmin[2] * mesh->scale) - RR_CORNELL_BREATHING_ROOM, maxZ = (bmax[2] * mesh->scale) + RR_CORNELL_BREATHING_ROOM;
+  auto quad = [&](float ax, float ay, float az, float bx, float by, float bz, float cx, float cy, float cz, float dx, float dy,
+                  float dz, float nx, float ny, float nz, float r, float g, float b) {
+    const float A[3] = {ax, ay, az}, B[3] = {bx, by, bz}, C[3] = {cx, cy, cz}, D[3] = {dx, dy, dz}, N[3] = {nx, ny, nz},
+                col[3] = {r, g, b};
+    rr_scene_add_quad(s, A, B, C, D, N, col);
+  };
+  // Floor (:411-421)
+  quad(minX, minY, minZ, maxX, minY, minZ, maxX, minY, maxZ, minX, minY, maxZ, 0, 1, 0, 0, 0, 0);
+  {
+    rr_material& m = s->meshes.back().material;
+    memset(&m, 0, sizeof(m));
+    m.type = RR_MATERIAL_SOLID; m.ior = 1.0f;
+    m.color = f3(0.1f, 0.1f, 0.1f);
+    m.specularProbability = 1.0f;
+  }
+  // Ceiling (:424)
+  quad(minX, maxY, minZ, maxX, maxY, minZ, maxX, maxY, maxZ, minX, maxY, maxZ, 0, -1, 0, 1, 1, 1);
+  // Front wall, one-sided (:427-428)
+  quad(minX, minY, maxZ, maxX, minY, maxZ, maxX, maxY, maxZ, minX, maxY, maxZ, 0, 0, -1, 1.0f, 1.0f, 1.0f);
+  s->meshes.back().material.type = RR_MATERIAL_ONESIDED;
+  // Back wall, green (:432)
+  quad(minX, minY, minZ, maxX, minY, minZ, maxX, maxY, minZ, minX, maxY, minZ, 0, 0, 1, 0.1f, 0.8f, 0.1f);
+  // Left wall, blue (:435)
+  quad(minX, minY, minZ, minX, minY, maxZ, minX, maxY, maxZ, minX, maxY, minZ, 1, 0, 0, 0.1f, 0.1f, 1.f);
+  // Right wall, red (:438)
+  quad(maxX, minY, minZ, maxX, minY, maxZ, maxX, maxY, maxZ, maxX, maxY, minZ, -1, 0, 0, 1.f, 0.2f, 0.2f);
+  // Light quad just below the ceiling (:441-447)
+  const float lx = 50, lz = 50, ly = maxY - 1;
+  quad(-lx, ly, -lz, lx, ly, -lz, lx, ly, lz, -lx, ly, lz, 0, -1, 0, 0.0f, 0.0f, 0.0f);
+  {
+    rr_material& m = s->meshes.back().material;
+    memset(&m, 0, sizeof(m));
+    m.type = RR_MATERIAL_SOLID; m.ior = 1.0f;
+    m.color = f3(1, 1, 1);
+    m.emissionColor = f3(1.0f, 1.0f, 1.0f);
+    m.emissionStrength = 8.0f;
+    m.specularProbability = 1.0f;
+  }
+  return RR_OK;
+}
+
+int rr_scene_add_sphere(rr_scene* s, const rr_sphere* sphere) {
+  if (!s || !sphere) return RR_ERR_INVALID_ARGUMENT;
+  s->spheres.push_back(*sphere);
+  return RR_OK;
+}
+
+rr_mesh* rr_scene_mesh(rr_scene* s, size_t index) { return (s && index < s->meshes.size()) ? &s->meshes[index] : nullptr; }
+size_t rr_scene_mesh_count(const rr_scene* s) { return s ? s->meshes.size() : 0; }
+size_t rr_scene_triangle_count(const rr_scene* s) { return s ? s->tris.size() : 0; }
+size_t rr_scene_sphere_count(const rr_scene* s) { return s ? s->spheres.size() : 0; }
+const rr_triangle* rr_scene_triangles(const rr_scene* s) { return s ? s->tris.data() : nullptr; }
+const rr_mesh* rr_scene_meshes(const rr_scene* s) { return s ? s->meshes.data() : nullptr; }
+const rr_mesh_range* rr_scene_ranges(const rr_scene* s) { return s ? s->ranges.data() : nullptr; }
+const rr_sphere* rr_scene_spheres(const rr_scene* s) { return s ? s->spheres.data() : nullptr; }
+
+int rr_scene_upload(rr_ctx* ctx, const rr_scene* s) {
+  if (!s) return RR_ERR_INVALID_ARGUMENT;
+  return rr_upload_scene(ctx, s->tris.data(), s->tris.size(), s->meshes.data(), s->ranges.data(), s->meshes.size(),
+                         s->spheres.data(), s->spheres.size());
+}
+
+void rr_default_camera(rr_camera* cam, uint32_t width, uint32_t height) {
+  if (!cam) return;
+  memset(cam, 0, sizeof(*cam));
+  cam->position = f3(0.0f, 150.0f, 250.0f);  // src/settings.hpp:23-25
+  cam->pitch = 0.0f;
+  cam->yaw = 3.14f;                           // src/settings.hpp:27
+  cam->roll = 0.0f;
+  cam->fov = 90.0f;                           // src/main.cpp:303
+  cam->aspectRatio = (float)width / (float)height;
+}
+
+int rr_write_bmp(const char* path, const uint8_t* rgba, uint32_t width, uint32_t height) {
+  if (!path || !rgba) return RR_ERR_INVALID_ARGUMENT;
+  FILE* f = fopen(path, "wb");
+  if (!f) return RR_ERR_IO;
+  const int padSize = (4 - (int)((width * 3u) % 4u)) % 4;
+  const int rowSize = 3 * (int)width + padSize;
+  const int dataSize = rowSize * (int)height;
+  const int fileSize = 54 + dataSize;
+  unsigned char header[54];
+  memset(header, 0, sizeof(header));
+  header[0] = 'B'; header[1] = 'M';
+  for (int k = 0; k < 4; ++k) header[2 + k] = (unsigned char)((fileSize >> (8 * k)) & 0xFF);
+  header[10] = 54;
+  header[14] = 40;
+  for (int k = 0; k < 4; ++k) header[18 + k] = (unsigned char)((width >> (8 * k)) & 0xFF);
+  for (int k = 0; k < 4; ++k) header[22 + k] = (unsigned char)((height >> (8 * k)) & 0xFF);
+  header[26] = 1;
+  header[28] = 24;
+  bool ok = fwrite(header, 1, 54, f) == 54;
+  std::vector<unsigned char> row((size_t)rowSize, 0);
+  for (int y = (int)height - 1; y >= 0 && ok; --y) {  // bottom-up, BGR
+    const uint8_t* src = rgba + (size_t)y * width * 4;
+    for (uint32_t x = 0; x < width; ++x) {
+      row[3 * x + 0] = src[4 * x + 2];
+      row[3 * x + 1] = src[4 * x + 1];
+      row[3 * x + 2] = src[4 * x + 0];
+    }
+    ok = fwrite(row.data(), 1, (size_t)rowSize, f) == (size_t)rowSize;
+  }
+  ok = (fclose(f) == 0) && ok;
+  return ok ? RR_OK : RR_ERR_IO;
+}
+
+}  // extern "C"

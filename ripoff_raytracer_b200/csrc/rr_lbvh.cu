@@ -1,0 +1,592 @@
+// rr_lbvh.cu -- GPU LBVH builder (Morton codes -> radix sort -> Karras
+// hierarchy -> atomic-flag refit -> traversal packing), one hierarchy per
+// segment (mesh) of a primitive array, all segments built in one batch.
+//
+// Replaces the reference's host SAH builder (src/readobj.hpp:96-267: recursive,
+// 5 candidate planes x 3 axes, in-place partition of triangleList).  The build
+// is bit-exact against oracle/rr_oracle.c (lbvh_build_segment): identical keys,
+// identical sorted order (stable in the uploaded index), identical topology and
+// boxes -- tests/test_lbvh_parity.py.
+//
+// Every kernel here is HBM/latency-bound integer and min/max work; nothing is
+// GEMM-shaped.  Compiled with -fmad=false (the key quantisation must round
+// exactly like the CPU statement).
+#include <math.h>
+
+#include "rr_internal.h"
+
+namespace rr {
+
+#define RR_CK(x)                        \
+  do {                                  \
+    cudaError_t e_ = (x);               \
+    if (e_ != cudaSuccess) return e_;   \
+  } while (0)
+
+static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+// ---- primitive boxes ------------------------------------------------------
+__global__ void k_tri_boxes(const rr_triangle* __restrict__ tris, uint64_t n, float* __restrict__ box) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4* t = reinterpret_cast<const float4*>(tris + i);
+  float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
+  float* o = box + 6 * i;
+  o[0] = fminf(fminf(a.x, b.x), c.x);
+  o[1] = fminf(fminf(a.y, b.y), c.y);
+  o[2] = fminf(fminf(a.z, b.z), c.z);
+  o[3] = fmaxf(fmaxf(a.x, b.x), c.x);
+  o[4] = fmaxf(fmaxf(a.y, b.y), c.y);
+  o[5] = fmaxf(fmaxf(a.z, b.z), c.z);
+}
+
+__global__ void k_sphere_boxes(const rr_sphere* __restrict__ sph, uint64_t n, float* __restrict__ box) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4* s = reinterpret_cast<const float4*>(sph + i);
+  float4 c = __ldg(s);
+  float r = __ldg(reinterpret_cast<const float*>(s + 1));
+  float* o = box + 6 * i;
+  o[0] = c.x - r; o[1] = c.y - r; o[2] = c.z - r;
+  o[3] = c.x + r; o[4] = c.y + r; o[5] = c.z + r;
+}
+
+cudaError_t launch_tri_boxes(const rr_triangle* d_tris, uint64_t n, float* d_box, cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  k_tri_boxes<<<grid_for(n, 256), 256, 0, s>>>(d_tris, n, d_box);
+  return cudaGetLastError();
+}
+cudaError_t launch_sphere_boxes(const rr_sphere* d_sph, uint64_t n, float* d_box, cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  k_sphere_boxes<<<grid_for(n, 256), 256, 0, s>>>(d_sph, n, d_box);
+  return cudaGetLastError();
+}
+
+// ---- segments ---------------------------------------------------------------
+// Largest s with first[s] <= i, or -1.
+__device__ __forceinline__ int seg_search(const uint32_t* __restrict__ first, int n_segs, uint32_t i) {
+  int lo = 0, hi = n_segs;  // first[lo-1] <= i < first[hi]
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(first + mid) <= i) lo = mid + 1; else hi = mid;
+  }
+  return lo - 1;
+}
+
+__device__ __forceinline__ int f2ord(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void k_seg_init(int* seg_box_ord, uint32_t n_segs) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_segs * 6) return;
+  seg_box_ord[i] = (i % 6) < 3 ? f2ord(INFINITY) : f2ord(-INFINITY);
+}
+
+// seg_id[i] = segment of prim i (n_segs when uncovered); reduces the segment boxes.
+__global__ void k_seg_assign(const float* __restrict__ box, uint64_t n_total, const uint32_t* __restrict__ seg_first,
+                             const uint32_t* __restrict__ seg_count, int n_segs, uint32_t* __restrict__ seg_id,
+                             int* __restrict__ seg_box_ord) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = i < n_total;
+  int s = -1;
+  float b[6];
+  if (valid) {
+    s = seg_search(seg_first, n_segs, (uint32_t)i);
+    if (s >= 0 && (uint32_t)i - seg_first[s] >= seg_count[s]) s = -1;
+    seg_id[i] = s >= 0 ? (uint32_t)s : (uint32_t)n_segs;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) b[k] = box[6 * i + k];
+  }
+  // warp-uniform segment: shuffle-reduce, one lane issues the atomics
+  unsigned full = 0xffffffffu;
+  int s0 = __shfl_sync(full, s, 0);
+  bool uniform = __all_sync(full, valid && s == s0 && s >= 0);
+  if (uniform) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      float v = b[k];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        float o = __shfl_xor_sync(full, v, off);
+        v = k < 3 ? fminf(v, o) : fmaxf(v, o);
+      }
+      b[k] = v;
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        atomicMin(seg_box_ord + 6 * s + k, f2ord(b[k]));
+        atomicMax(seg_box_ord + 6 * s + 3 + k, f2ord(b[3 + k]));
+      }
+    }
+  } else if (valid && s >= 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      atomicMin(seg_box_ord + 6 * s + k, f2ord(b[k]));
+      atomicMax(seg_box_ord + 6 * s + 3 + k, f2ord(b[3 + k]));
+    }
+  }
+}
+
+__global__ void k_seg_decode(const int* seg_box_ord, float* seg_box, uint32_t n_segs) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_segs * 6) return;
+  seg_box[i] = ord2f(seg_box_ord[i]);
+}
+
+// ---- Morton keys -------------------------------------------------------------
+__device__ __forceinline__ uint64_t expand21(uint32_t v) {
+  uint64_t x = v & 0x1fffffu;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+__device__ __forceinline__ uint32_t quant21(float c, float lo, float ext) {
+  if (!(ext > 0.0f)) return 0u;
+  float q = (c - lo) / ext;
+  float g = q * 2097152.0f;
+  if (!(g > 0.0f)) return 0u;
+  if (g >= 2097151.0f) return 2097151u;
+  return (uint32_t)g;
+}
+
+__global__ void k_morton(const float* __restrict__ box, uint64_t n_total, const uint32_t* __restrict__ seg_id,
+                         const float* __restrict__ seg_box, uint32_t n_segs, uint64_t* __restrict__ keys,
+                         uint32_t* __restrict__ vals) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_total) return;
+  uint32_t s = seg_id[i];
+  uint64_t code = 0;
+  if (s < n_segs) {
+    const float* sb = seg_box + 6 * s;
+    uint32_t g[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float c = (box[6 * i + a] + box[6 * i + 3 + a]) * 0.5f;
+      g[a] = quant21(c, sb[a], sb[3 + a] - sb[a]);
+    }
+    code = (expand21(g[0]) << 2) | (expand21(g[1]) << 1) | expand21(g[2]);
+  }
+  keys[i] = code;
+  vals[i] = (uint32_t)i;
+}
+
+// ---- stable LSD radix sort, 8 bits per pass ---------------------------------
+// One pass = histogram per tile, exclusive scan over (digit, tile), stable scatter.
+// A tile is processed by 8 warps; warp w owns the w-th contiguous eighth of the
+// tile, walks it 32 consecutive items at a time and ranks equal digits with
+// __match_any_sync, so equal keys keep their input order.
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 8;  // per thread
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+
+template <bool SEG_DIGIT>
+__device__ __forceinline__ uint32_t sort_digit(uint64_t key, uint32_t val, const uint32_t* __restrict__ seg_id, int shift) {
+  if (SEG_DIGIT) return (__ldg(seg_id + val) >> shift) & 0xffu;
+  return (uint32_t)(key >> shift) & 0xffu;
+}
+
+template <bool SEG_DIGIT>
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                            const uint32_t* __restrict__ seg_id, uint64_t n, int shift,
+                                                            uint32_t* __restrict__ hist, uint32_t n_tiles) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  uint64_t base = (uint64_t)blockIdx.x * SORT_TILE;
+#pragma unroll
+  for (int k = 0; k < SORT_ITEMS; ++k) {
+    uint64_t i = base + (uint64_t)k * SORT_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&h[sort_digit<SEG_DIGIT>(keys[i], vals[i], seg_id, shift)], 1u);
+  }
+  __syncthreads();
+  hist[(uint64_t)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of `m` counters in place, one block of 1024 threads
+__global__ void __launch_bounds__(1024) k_scan(uint32_t* data, uint64_t m) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint64_t base = 0; base < m; base += 1024) {
+    uint64_t i = base + threadIdx.x;
+    uint32_t v = i < m ? data[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= (unsigned)off) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t w = warp_sums[lane];
+      uint32_t ws = w;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, ws, off);
+        if (lane >= (unsigned)off) ws += y;
+      }
+      warp_sums[lane] = ws - w;  // exclusive
+    }
+    __syncthreads();
+    uint32_t carry = carry_s;
+    uint32_t excl = carry + warp_sums[wid] + (x - v);
+    if (i < m) data[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_sums[wid] + x;
+    __syncthreads();
+  }
+}
+
+template <bool SEG_DIGIT>
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                               uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                               const uint32_t* __restrict__ seg_id, uint64_t n, int shift,
+                                                               const uint32_t* __restrict__ offsets, uint32_t n_tiles) {
+  constexpr int WARPS = SORT_THREADS / 32;
+  constexpr int ROUNDS = SORT_TILE / WARPS / 32;
+  __shared__ uint32_t wh[WARPS][256];
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < WARPS * 256; k += SORT_THREADS) (&wh[0][0])[k] = 0;
+  __syncthreads();
+  const uint64_t chunk = (uint64_t)blockIdx.x * SORT_TILE + (uint64_t)w * (ROUNDS * 32);
+  uint64_t key[ROUNDS];
+  uint32_t val[ROUNDS];
+  uint32_t dig[ROUNDS];
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    uint64_t i = chunk + (uint64_t)r * 32 + lane;
+    if (i < n) {
+      key[r] = keys_in[i];
+      val[r] = vals_in[i];
+      dig[r] = sort_digit<SEG_DIGIT>(key[r], val[r], seg_id, shift);
+      atomicAdd(&wh[w][dig[r]], 1u);
+    } else {
+      key[r] = 0; val[r] = 0;
+      dig[r] = 0x100u + lane;  // matches nobody
+    }
+  }
+  __syncthreads();
+  {
+    const unsigned bin = threadIdx.x;
+    uint32_t running = offsets[(uint64_t)bin * n_tiles + blockIdx.x];
+#pragma unroll
+    for (int ww = 0; ww < WARPS; ++ww) {
+      uint32_t c = wh[ww][bin];
+      wh[ww][bin] = running;
+      running += c;
+    }
+  }
+  __syncthreads();
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    unsigned m = __match_any_sync(0xffffffffu, dig[r]);
+    bool ok = dig[r] < 0x100u;
+    unsigned rank = __popc(m & lt);
+    uint32_t pos = 0;
+    if (ok) pos = wh[w][dig[r]] + rank;
+    __syncwarp();
+    if (ok && rank == 0) wh[w][dig[r]] += __popc(m);
+    __syncwarp();
+    if (ok) {
+      keys_out[pos] = key[r];
+      vals_out[pos] = val[r];
+    }
+  }
+}
+
+// ---- hierarchy (Karras 2012) -------------------------------------------------
+__device__ __forceinline__ int key_delta(const uint64_t* __restrict__ codes, int64_t n, int64_t i, int64_t j) {
+  if (j < 0 || j >= n) return -1;
+  uint64_t a = codes[i], b = codes[j];
+  if (a == b) return 64 + __clz((int)((uint32_t)i ^ (uint32_t)j));
+  return __clzll((long long)(a ^ b));
+}
+
+__global__ void k_karras(const uint64_t* __restrict__ codes_all, uint64_t n, const uint32_t* __restrict__ seg_sfirst,
+                         const uint32_t* __restrict__ seg_count, int n_segs, int32_t* __restrict__ left,
+                         int32_t* __restrict__ right, int32_t* __restrict__ parent, int32_t* __restrict__ leaf_parent) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  int s = seg_search(seg_sfirst, n_segs, (uint32_t)g);
+  // zero-count segments share their sfirst with the next one: seg_search returns the last of them
+  const uint32_t first = seg_sfirst[s];
+  const int64_t N = seg_count[s];
+  const int64_t i = (int64_t)g - first;
+  if (i >= N - 1) return;
+  const uint64_t* codes = codes_all + first;
+  int d = (key_delta(codes, N, i, i + 1) - key_delta(codes, N, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = key_delta(codes, N, i, i - d);
+  int64_t lmax = 2;
+  while (key_delta(codes, N, i, i + lmax * d) > dmin) lmax *= 2;
+  int64_t l = 0;
+  for (int64_t t = lmax / 2; t >= 1; t /= 2)
+    if (key_delta(codes, N, i, i + (l + t) * d) > dmin) l += t;
+  int64_t j = i + l * d;
+  int dnode = key_delta(codes, N, i, j);
+  int64_t sp = 0;
+  for (int64_t t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+    if (key_delta(codes, N, i, i + (sp + t) * d) > dnode) sp += t;
+    if (t <= 1) break;
+  }
+  int64_t gamma = i + sp * d + (d < 0 ? -1 : 0);
+  int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+  int32_t me = (int32_t)(first + i);
+  int32_t L, R;
+  if (lo == gamma) { L = ~(int32_t)(first + gamma); leaf_parent[first + gamma] = me; }
+  else { L = (int32_t)(first + gamma); parent[first + gamma] = me; }
+  if (hi == gamma + 1) { R = ~(int32_t)(first + gamma + 1); leaf_parent[first + gamma + 1] = me; }
+  else { R = (int32_t)(first + gamma + 1); parent[first + gamma + 1] = me; }
+  left[me] = L;
+  right[me] = R;
+}
+
+__device__ __forceinline__ void load_ref_box(int32_t ref, const uint32_t* __restrict__ order,
+                                             const float* __restrict__ prim_box, const float* bounds, float* b) {
+  if (ref < 0) {
+    const float* p = prim_box + 6 * (uint64_t)order[~ref];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) b[k] = __ldg(p + k);
+  } else {
+    const float* p = bounds + 6 * (uint64_t)ref;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) b[k] = __ldcg(p + k);  // written by another thread of this launch
+  }
+}
+
+// Bottom-up refit: the second thread to reach a node computes its box.  Also
+// records the depth of the deepest leaf (root = 1).
+__global__ void k_refit(uint64_t n, const uint32_t* __restrict__ order, const float* __restrict__ prim_box,
+                        const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                        const int32_t* __restrict__ parent, const int32_t* __restrict__ leaf_parent,
+                        float* bounds, unsigned int* flags, unsigned int* max_depth) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  int32_t p = leaf_parent[g];
+  unsigned depth = 1;
+  bool working = true;
+  while (p >= 0) {
+    depth++;
+    if (working) {
+      unsigned old = atomicAdd(flags + p, 1u);
+      if (old == 0) {
+        working = false;
+      } else {
+        float a[6], c[6];
+        load_ref_box(left[p], order, prim_box, bounds, a);
+        load_ref_box(right[p], order, prim_box, bounds, c);
+        float* o = bounds + 6 * (uint64_t)p;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          __stcg(o + k, fminf(a[k], c[k]));
+          __stcg(o + 3 + k, fmaxf(a[3 + k], c[3 + k]));
+        }
+        __threadfence();
+      }
+    }
+    p = parent[p];
+  }
+  if (depth > 1) atomicMax(max_depth, depth);
+}
+
+// Traversal node: boxes of both children + child refs, 64 bytes.
+//   q0 = (A.min.xyz, A.max.x) q1 = (A.max.yz, B.min.xy) q2 = (B.min.z, B.max.xyz) q3 = (refA, refB, -, -)
+__global__ void k_pack_nodes(uint64_t n, const uint32_t* __restrict__ order, const float* __restrict__ prim_box,
+                             const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                             const int32_t* __restrict__ parent, const int32_t* __restrict__ leaf_parent,
+                             const float* __restrict__ bounds, const unsigned int* __restrict__ flags,
+                             float4* __restrict__ nodes) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+  if (flags[g] == 2u) {  // a built inner node
+    float a[6], c[6];
+    int32_t L = left[g], R = right[g];
+    load_ref_box(L, order, prim_box, bounds, a);
+    load_ref_box(R, order, prim_box, bounds, c);
+    q0 = make_float4(a[0], a[1], a[2], a[3]);
+    q1 = make_float4(a[4], a[5], c[0], c[1]);
+    q2 = make_float4(c[2], c[3], c[4], c[5]);
+    q3 = make_float4(__int_as_float(L), __int_as_float(R), 0.0f, 0.0f);
+  }
+  nodes[4 * g + 0] = q0;
+  nodes[4 * g + 1] = q1;
+  nodes[4 * g + 2] = q2;
+  nodes[4 * g + 3] = q3;
+}
+
+// Sorted triangle arrays.  geom: (A, prim) (B-A) (C-A) -- the edge vectors are
+// the same subtractions the reference does per test (src/Trace.cl:277-278).
+__global__ void k_pack_tris(const rr_triangle* __restrict__ tris, const uint32_t* __restrict__ order, uint64_t n,
+                            float4* __restrict__ geom, float4* __restrict__ nrm) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  uint32_t prim = order[g];
+  const float4* t = reinterpret_cast<const float4*>(tris + prim);
+  float4 A = __ldg(t), B = __ldg(t + 1), Cc = __ldg(t + 2);
+  geom[3 * g + 0] = make_float4(A.x, A.y, A.z, __uint_as_float(prim));
+  geom[3 * g + 1] = make_float4(B.x - A.x, B.y - A.y, B.z - A.z, 0.0f);
+  geom[3 * g + 2] = make_float4(Cc.x - A.x, Cc.y - A.y, Cc.z - A.z, 0.0f);
+  nrm[3 * g + 0] = __ldg(t + 3);
+  nrm[3 * g + 1] = __ldg(t + 4);
+  nrm[3 * g + 2] = __ldg(t + 5);
+}
+
+__global__ void k_pack_spheres(const rr_sphere* __restrict__ sph, const uint32_t* __restrict__ order, uint64_t n,
+                               float4* __restrict__ geom) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  uint32_t prim = order[g];
+  const float4* s = reinterpret_cast<const float4*>(sph + prim);
+  float4 c = __ldg(s);
+  float r = __ldg(reinterpret_cast<const float*>(s + 1));
+  geom[g] = make_float4(c.x, c.y, c.z, r);
+}
+
+cudaError_t launch_pack_tris(const rr_triangle* d_tris, const uint32_t* d_order, uint64_t n, float4* geom, float4* nrm,
+                             cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  k_pack_tris<<<grid_for(n, 256), 256, 0, s>>>(d_tris, d_order, n, geom, nrm);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_spheres(const rr_sphere* d_sph, const uint32_t* d_order, uint64_t n, float4* geom,
+                                cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  k_pack_spheres<<<grid_for(n, 256), 256, 0, s>>>(d_sph, d_order, n, geom);
+  return cudaGetLastError();
+}
+
+__global__ void k_fill_i32(int32_t* p, uint64_t n, int32_t v) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) p[g] = v;
+}
+
+// ---- host driver ----------------------------------------------------------------
+void lbvh_free(Lbvh& b) {
+  cudaFree(b.codes); cudaFree(b.order); cudaFree(b.left); cudaFree(b.right); cudaFree(b.parent); cudaFree(b.bounds);
+  cudaFree(b.seg_box); cudaFree(b.seg_first); cudaFree(b.seg_count); cudaFree(b.seg_sfirst); cudaFree(b.nodes);
+  b = Lbvh();
+}
+
+template <class T>
+static cudaError_t dalloc(T** p, uint64_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(p), (count ? count : 1) * sizeof(T));
+}
+
+cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, const uint32_t* h_seg_first,
+                       const uint32_t* h_seg_count, uint32_t n_segs, cudaStream_t st) {
+  lbvh_free(out);
+  out.n_segs = n_segs;
+  uint64_t n = 0;
+  uint32_t* h_sfirst = (uint32_t*)malloc((n_segs ? n_segs : 1) * sizeof(uint32_t));
+  for (uint32_t s = 0; s < n_segs; ++s) {
+    h_sfirst[s] = (uint32_t)n;
+    n += h_seg_count[s];
+  }
+  out.n = n;
+  cudaError_t err = cudaSuccess;
+  uint64_t *keys_a = nullptr, *keys_b = nullptr;
+  uint32_t *vals_a = nullptr, *vals_b = nullptr, *seg_id = nullptr, *hist = nullptr;
+  int* seg_box_ord = nullptr;
+  int32_t* leaf_parent = nullptr;
+  unsigned int *flags = nullptr, *d_depth = nullptr;
+  const uint32_t n_tiles = (uint32_t)((n_total + SORT_TILE - 1) / SORT_TILE);
+#define RR_TRY(x)                   \
+  do {                              \
+    err = (x);                      \
+    if (err != cudaSuccess) goto done; \
+  } while (0)
+  RR_TRY(dalloc(&out.codes, n_total));
+  RR_TRY(dalloc(&out.order, n_total));
+  RR_TRY(dalloc(&out.left, n));
+  RR_TRY(dalloc(&out.right, n));
+  RR_TRY(dalloc(&out.parent, n));
+  RR_TRY(dalloc(&out.bounds, (n ? n : 1) * 6));
+  RR_TRY(dalloc(&out.seg_box, (uint64_t)(n_segs ? n_segs : 1) * 6));
+  RR_TRY(dalloc(&out.seg_first, n_segs));
+  RR_TRY(dalloc(&out.seg_count, n_segs));
+  RR_TRY(dalloc(&out.seg_sfirst, n_segs));
+  RR_TRY(dalloc(&out.nodes, (n ? n : 1) * 4));
+  RR_TRY(dalloc(&keys_a, n_total));
+  RR_TRY(dalloc(&keys_b, n_total));
+  RR_TRY(dalloc(&vals_a, n_total));
+  RR_TRY(dalloc(&vals_b, n_total));
+  RR_TRY(dalloc(&seg_id, n_total));
+  RR_TRY(dalloc(&hist, (uint64_t)256 * (n_tiles ? n_tiles : 1)));
+  RR_TRY(dalloc(&seg_box_ord, (uint64_t)(n_segs ? n_segs : 1) * 6));
+  RR_TRY(dalloc(&leaf_parent, n));
+  RR_TRY(dalloc(&flags, n));
+  RR_TRY(dalloc(&d_depth, 1));
+  if (n_segs) {
+    RR_TRY(cudaMemcpyAsync(out.seg_first, h_seg_first, n_segs * 4, cudaMemcpyHostToDevice, st));
+    RR_TRY(cudaMemcpyAsync(out.seg_count, h_seg_count, n_segs * 4, cudaMemcpyHostToDevice, st));
+    RR_TRY(cudaMemcpyAsync(out.seg_sfirst, h_sfirst, n_segs * 4, cudaMemcpyHostToDevice, st));
+  }
+  RR_TRY(cudaMemsetAsync(flags, 0, (n ? n : 1) * 4, st));
+  RR_TRY(cudaMemsetAsync(d_depth, 0, 4, st));
+  RR_TRY(cudaMemsetAsync(out.bounds, 0, (n ? n : 1) * 24, st));
+  RR_TRY(cudaMemsetAsync(out.left, 0, (n ? n : 1) * 4, st));
+  RR_TRY(cudaMemsetAsync(out.right, 0, (n ? n : 1) * 4, st));
+  if (n_total && n_segs) {
+    k_seg_init<<<grid_for(n_segs * 6, 256), 256, 0, st>>>(seg_box_ord, n_segs);
+    k_seg_assign<<<grid_for(n_total, 256), 256, 0, st>>>(d_prim_box, n_total, out.seg_first, out.seg_count, (int)n_segs,
+                                                         seg_id, seg_box_ord);
+    k_seg_decode<<<grid_for(n_segs * 6, 256), 256, 0, st>>>(seg_box_ord, out.seg_box, n_segs);
+    k_morton<<<grid_for(n_total, 256), 256, 0, st>>>(d_prim_box, n_total, seg_id, out.seg_box, n_segs, keys_a, vals_a);
+    RR_TRY(cudaGetLastError());
+    // sort by key (8 passes), then stably by segment: result is ordered by (segment, key, prim)
+    uint64_t *kin = keys_a, *kout = keys_b;
+    uint32_t *vin = vals_a, *vout = vals_b;
+    for (int pass = 0; pass < 8; ++pass) {
+      k_sort_hist<false><<<n_tiles, SORT_THREADS, 0, st>>>(kin, vin, seg_id, n_total, pass * 8, hist, n_tiles);
+      k_scan<<<1, 1024, 0, st>>>(hist, (uint64_t)256 * n_tiles);
+      k_sort_scatter<false><<<n_tiles, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, seg_id, n_total, pass * 8, hist, n_tiles);
+      uint64_t* tk = kin; kin = kout; kout = tk;
+      uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+    const bool one_full_segment = (n_segs == 1 && h_seg_first[0] == 0 && h_seg_count[0] == n_total);
+    if (!one_full_segment) {
+      for (int shift = 0; (n_segs >> shift) != 0; shift += 8) {
+        k_sort_hist<true><<<n_tiles, SORT_THREADS, 0, st>>>(kin, vin, seg_id, n_total, shift, hist, n_tiles);
+        k_scan<<<1, 1024, 0, st>>>(hist, (uint64_t)256 * n_tiles);
+        k_sort_scatter<true><<<n_tiles, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, seg_id, n_total, shift, hist, n_tiles);
+        uint64_t* tk = kin; kin = kout; kout = tk;
+        uint32_t* tv = vin; vin = vout; vout = tv;
+      }
+    }
+    RR_TRY(cudaGetLastError());
+    RR_TRY(cudaMemcpyAsync(out.codes, kin, n_total * 8, cudaMemcpyDeviceToDevice, st));
+    RR_TRY(cudaMemcpyAsync(out.order, vin, n_total * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (n) {
+    k_fill_i32<<<grid_for(n, 256), 256, 0, st>>>(out.parent, n, -1);
+    k_fill_i32<<<grid_for(n, 256), 256, 0, st>>>(leaf_parent, n, -1);
+    k_karras<<<grid_for(n, 128), 128, 0, st>>>(out.codes, n, out.seg_sfirst, out.seg_count, (int)n_segs, out.left, out.right,
+                                               out.parent, leaf_parent);
+    k_refit<<<grid_for(n, 128), 128, 0, st>>>(n, out.order, d_prim_box, out.left, out.right, out.parent, leaf_parent,
+                                              out.bounds, flags, d_depth);
+    k_pack_nodes<<<grid_for(n, 128), 128, 0, st>>>(n, out.order, d_prim_box, out.left, out.right, out.parent, leaf_parent,
+                                                   out.bounds, flags, out.nodes);
+    RR_TRY(cudaGetLastError());
+  }
+  RR_TRY(cudaMemcpyAsync(&out.max_depth, d_depth, 4, cudaMemcpyDeviceToHost, st));
+  RR_TRY(cudaStreamSynchronize(st));
+done:
+  cudaFree(keys_a); cudaFree(keys_b); cudaFree(vals_a); cudaFree(vals_b); cudaFree(seg_id); cudaFree(hist);
+  cudaFree(seg_box_ord); cudaFree(leaf_parent); cudaFree(flags); cudaFree(d_depth);
+  free(h_sfirst);
+#undef RR_TRY
+  return err;
+}
+
+}  // namespace rr

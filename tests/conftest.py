@@ -1,0 +1,52 @@
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+
+
+@pytest.fixture(scope="session")
+def golden_small():
+    return dict(np.load(GOLDEN / "default_small.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_wide():
+    return dict(np.load(GOLDEN / "default_wide.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_rng():
+    return dict(np.load(GOLDEN / "rng.npz"))
+
+
+@pytest.fixture(scope="session")
+def knight_obj(tmp_path_factory):
+    """Stand-in for the reference's unshipped knight.obj: a 2 208-triangle UV sphere."""
+    from ripoff_raytracer_b200 import scenes
+
+    p = tmp_path_factory.mktemp("obj") / "knight.obj"
+    scenes.write_obj(p, *scenes.uv_sphere(48, 24))
+    return p
+
+
+@pytest.fixture(scope="session")
+def renderer():
+    import ripoff_raytracer_b200 as rr
+
+    r = rr.Renderer()
+    yield r
+    r.close()
+
+
+def psnr(a, b, peak=255.0):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return float("inf") if mse == 0 else 10.0 * np.log10(peak * peak / mse)

@@ -1,0 +1,359 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden vectors.
+
+Bar: integer work and BVH build order bit-exact; images and float radiance
+bit-exact against the oracle on the same scene and seed (both sides evaluate the numerics contract);
+against the reference's own golden vectors bit-exact as well on these scenes (the only possible
+deviations -- distance ties and box-edge grazing under a different hierarchy -- are counted).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import ripoff_raytracer_b200 as rr
+from oracle.pyoracle import Oracle
+from ripoff_raytracer_b200 import _abi, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+# ----------------------------------------------------------------- helpers --
+def zoo_scene(seed=11, with_spheres=True):
+    """Rotated/scaled instances and every material type (Solid, Checker, Invisible, Glassy, OneSided)."""
+    rng = np.random.default_rng(seed)
+    s = rr.Scene()
+    v, n, f = scenes.displaced_icosphere(3, radius=60.0, center=(0.0, 0.0, 0.0), seed=seed)
+    blob = s.add_triangles(scenes.mesh_triangles(v, n, f))
+    v2, n2, f2 = scenes.uv_sphere(20, 10, radius=40.0, center=(0.0, 0.0, 0.0))
+    ball = s.add_triangles(scenes.mesh_triangles(v2, n2, f2))
+
+    def mesh(pos, pyr, scale, mtype, color, emis=(0, 0, 0), strength=0.0, refl=0.0, spec=0.0, ior=1.0):
+        m = np.zeros(1, _abi.MESH)
+        m["pos"][0, :3] = pos
+        m["pitch"], m["yaw"], m["roll"] = pyr
+        m["scale"] = scale
+        mm = m["material"]
+        mm["type"] = mtype
+        mm["ior"] = ior
+        mm["color"][0, :3] = color
+        mm["emissionColor"][0, :3] = emis
+        mm["emissionStrength"] = strength
+        mm["reflectiveness"] = refl
+        mm["specularProbability"] = spec
+        return m
+
+    # room: checker floor, walls, light
+    s.add_quad((-300, 0, -300), (300, 0, -300), (300, 0, 300), (-300, 0, 300), (0, 1, 0), (0.8, 0.8, 0.8))
+    fl = s.mesh(s.n_meshes - 1)["material"]
+    fl["type"] = _abi.MATERIAL_CHECKER
+    fl["emissionColor"][0, :3] = (0.1, 0.1, 0.3)
+    fl["emissionStrength"] = 40.0  # checker cell size (src/Trace.cl:510-511)
+    s.add_quad((-300, 300, -300), (300, 300, -300), (300, 300, 300), (-300, 300, 300), (0, -1, 0), (0.9, 0.9, 0.9))
+    s.add_quad((-300, 0, -300), (300, 0, -300), (300, 300, -300), (-300, 300, -300), (0, 0, 1), (0.2, 0.7, 0.2))
+    s.add_quad((-300, 0, 300), (300, 0, 300), (300, 300, 300), (-300, 300, 300), (0, 0, -1), (1.0, 1.0, 1.0))
+    s.mesh(s.n_meshes - 1)["material"]["type"] = _abi.MATERIAL_ONESIDED
+    s.add_quad((-300, 0, -300), (-300, 0, 300), (-300, 300, 300), (-300, 300, -300), (1, 0, 0), (0.2, 0.2, 0.9))
+    s.add_quad((300, 0, -300), (300, 0, 300), (300, 300, 300), (300, 300, -300), (-1, 0, 0), (0.9, 0.2, 0.2))
+    s.add_quad((-80, 299, -80), (80, 299, -80), (80, 299, 80), (-80, 299, 80), (0, -1, 0), (1, 1, 1))
+    lm = s.mesh(s.n_meshes - 1)["material"]
+    lm["emissionColor"][0, :3] = 1.0
+    lm["emissionStrength"] = 6.0
+    # instances of the two meshes
+    s.add_mesh(mesh((-120, 70, -40), (0.3, 1.1, -0.4), 1.0, _abi.MATERIAL_SOLID, (0.9, 0.6, 0.3), refl=0.3, spec=0.5), blob)
+    s.add_mesh(mesh((110, 60, 20), (-0.7, 2.5, 0.9), 0.8, _abi.MATERIAL_GLASSY, (0.9, 0.9, 0.9), ior=1.5), blob)
+    s.add_mesh(mesh((0, 50, -120), (0.0, 0.4, 0.0), 1.2, _abi.MATERIAL_SOLID, (0.8, 0.8, 0.8), refl=1.0, spec=1.0), ball)
+    s.add_mesh(mesh((20, 120, 80), (1.0, 0.0, 0.5), 0.6, _abi.MATERIAL_INVISIBLE, (1, 1, 1)), ball)
+    s.add_mesh(mesh((-40, 200, 0), (0.2, 0.2, 0.2), 0.5, _abi.MATERIAL_ONESIDED, (0.5, 0.9, 0.9)), ball)
+    s.add_mesh(mesh((0, 0, 0), (0, 0, 0), 0.0, _abi.MATERIAL_SOLID, (1, 1, 1)), ball)  # degenerate: skipped (:448)
+    if with_spheres:
+        sp = np.zeros(6, _abi.SPHERE)
+        sp["center"][:, :3] = rng.uniform((-200, 20, -200), (200, 200, 200), size=(6, 3)).astype(np.float32)
+        sp["radius"] = rng.uniform(10, 30, size=6).astype(np.float32)
+        sp["material"]["ior"] = 1.3
+        sp["material"]["color"][:, :3] = rng.uniform(0.3, 0.9, size=(6, 3)).astype(np.float32)
+        sp["material"]["type"] = [0, 3, 0, 1, 4, 0]
+        sp["material"]["emissionStrength"] = [0, 0, 3.0, 25.0, 0, 0]
+        sp["material"]["emissionColor"][:, :3] = [(0, 0, 0), (0, 0, 0), (1, 0.8, 0.6), (0.2, 0.2, 0.2), (0, 0, 0), (0, 0, 0)]
+        sp["material"]["specularProbability"] = [0, 0, 0, 0, 0, 1.0]
+        sp["material"]["reflectiveness"] = [0, 0, 0, 0, 0, 0.9]
+        s.add_spheres(sp)
+    return s
+
+
+def zoo_camera(W, H):
+    cam = np.zeros(1, _abi.CAMERA)
+    cam["position"][0, :3] = (30.0, 140.0, 280.0)
+    cam["pitch"], cam["yaw"], cam["roll"] = 0.25, 3.0, 0.05
+    cam["fov"] = 80.0
+    cam["aspectRatio"] = np.float32(W) / np.float32(H)
+    return cam
+
+
+def assert_images_equal(got, want, what, max_diff_pixels=0):
+    diff = int((got != want).any(-1).sum())
+    assert diff <= max_diff_pixels, f"{what}: {diff} pixels differ"
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+# ------------------------------------------------------------------- tests --
+def test_numerics_contract_is_bit_identical_on_device():
+    l = _abi.lib()
+    l.rr_probe_math.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    rng = np.random.default_rng(0)
+    n = 1 << 18
+    cases = {
+        0: rng.uniform(-50, 50, n), 1: rng.uniform(-50, 50, n), 5: rng.uniform(-1.5, 1.5, n),
+        2: np.exp(rng.uniform(-80, 80, n)), 3: rng.uniform(-130, 130, n), 4: rng.uniform(0, 1, n),
+    }
+    for fn, x in cases.items():
+        x = x.astype(np.float32)
+        y = np.full(n, 1.0 / 2.2, np.float32) if fn == 4 else x
+        if fn in (0, 1):
+            x[:8] = [0.0, -0.0, 8191.9, -8191.9, 8192.0, 1e9, np.inf, np.nan]
+        if fn == 2:
+            x[:6] = [0.0, 1e-45, 1.1754942e-38, 1.0, np.inf, -1.0]
+        if fn == 4:
+            x[:4] = [0.0, 1.0, 1e-30, 0.5]
+        out = np.zeros(n, np.float32)
+        _abi.check(l.rr_probe_math(fn, _abi.ptr(x), _abi.ptr(y), _abi.ptr(out), n), "rr_probe_math")
+        want = Oracle.math(fn, x, y)
+        assert np.array_equal(bits(out), bits(want)), f"contract function {fn}"
+
+
+def test_rng_known_answers_on_device(golden_rng):
+    l = _abi.lib()
+    l.rr_probe_rng.argtypes = [C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p]
+    for i, pix in enumerate(golden_rng["pixels"]):
+        u = np.zeros(8, np.uint32)
+        f = np.zeros(9, np.float32)
+        _abi.check(l.rr_probe_rng(int(pix), 0, _abi.ptr(u), _abi.ptr(f)), "rr_probe_rng")
+        assert u[0] == golden_rng["seeds"][i]
+        assert np.array_equal(f[:4], golden_rng["rv_float"][i])
+        assert u[4] == golden_rng["rv_state_after4"][i]
+
+
+@pytest.mark.parametrize("case", ["golden", "zoo", "blob20k", "spheres"])
+def test_lbvh_build_order_is_bit_exact(renderer, golden_wide, case):
+    """GPU builder == CPU statement (Oracle B): keys, sorted order, topology, boxes."""
+    which = 0
+    if case == "golden":
+        t, m, r, sp = golden_wide["tris"], golden_wide["meshes"], golden_wide["ranges"], None
+    elif case == "zoo":
+        t, m, r, sp = zoo_scene().arrays()
+    elif case == "blob20k":
+        v, n, f = scenes.displaced_icosphere(5, seed=5)
+        t = scenes.mesh_triangles(v, n, f)
+        m = np.zeros(1, _abi.MESH)
+        m["scale"] = 1.0
+        r = np.zeros(1, _abi.MESH_RANGE)
+        r["numTriangles"] = len(t)
+        sp = None
+    else:
+        t, m, r = np.zeros(0, _abi.TRIANGLE), np.zeros(0, _abi.MESH), np.zeros(0, _abi.MESH_RANGE)
+        sp = scenes.random_spheres(300, seed=2)
+        which = 1
+    renderer.upload_arrays(t, m, r, sp)
+    got = renderer.bvh(which)
+    want = Oracle(t, m, r, sp).lbvh(which)
+    assert len(got["order"]) == len(want["order"])
+    assert np.array_equal(got["codes"], want["codes"])
+    assert np.array_equal(got["order"], want["order"])
+    if case == "zoo":
+        # instanced ranges are de-duplicated into segments on the device; topology is compared per used node
+        used = want["left"] != 0
+    else:
+        used = np.ones(len(want["left"]), bool)
+    assert np.array_equal(got["left"][used], want["left"][used])
+    assert np.array_equal(got["right"][used], want["right"][used])
+    assert np.array_equal(got["parent"], want["parent"])
+    assert np.array_equal(got["bounds"][used], want["bounds"][used])
+
+
+def test_primary_hits_bit_exact_vs_oracle_and_reference(renderer, golden_small):
+    g = golden_small
+    W, H = int(g["W"]), int(g["H"])
+    renderer.upload_arrays(g["tris"], g["meshes"], g["ranges"])
+    mesh, prim, dst = renderer.primary_hits(g["cam"], W, H)
+    om, op, od = Oracle(g["tris"], g["meshes"], g["ranges"]).primary(g["cam"], W, H)
+    assert np.array_equal(mesh, om) and np.array_equal(prim, op) and np.array_equal(bits(dst), bits(od))
+    # the reference's own record of the same rays (its SAH hierarchy): hit mask and distance bits
+    hit = g["primary_hit"]
+    assert np.array_equal(mesh >= 0, hit[..., 0] > 0)
+    assert np.array_equal(bits(dst)[mesh >= 0], bits(hit[..., 1])[mesh >= 0])
+
+
+def test_primary_hits_full_default_scene(renderer, knight_obj):
+    s = rr.default_scene(knight_obj)
+    renderer.upload(s)
+    t, m, r, _ = s.arrays()
+    W, H = 512, 512  # the reference's default resolution (src/settings.hpp:42-43)
+    cam = rr.default_camera(W, H)
+    mesh, prim, dst = renderer.primary_hits(cam, W, H)
+    om, op, od = Oracle(t, m, r).primary(cam, W, H)
+    assert np.array_equal(mesh, om) and np.array_equal(prim, op) and np.array_equal(bits(dst), bits(od))
+    assert (mesh == 7).sum() > 5000  # the OBJ mesh is visible
+
+
+@pytest.mark.parametrize("which", ["golden_small", "golden_wide"])
+def test_images_match_reference_golden(renderer, which, request):
+    """L0/L1/L2 of the parity ladder against the REFERENCE's outputs: bit-exact 8-bit image and radiance."""
+    g = request.getfixturevalue(which)
+    W, H = int(g["W"]), int(g["H"])
+    renderer.upload_arrays(g["tris"], g["meshes"], g["ranges"])
+    for key in sorted(k for k in g if k.startswith("rgba_")):
+        _, s, b = key.split("_")
+        rgba, rad, st = renderer.render(g["cam"], W, H, int(s[1:]), int(b[1:]), radiance=True)
+        assert np.all(rgba[..., 3] == 255)
+        assert_images_equal(rgba, g[key], f"{which}:{key}")
+        assert np.array_equal(bits(rad), bits(g["rad_" + key[5:]])), key
+        assert st["samples"] == W * H * int(s[1:])
+
+
+def test_upload_with_reference_argument_list(renderer, golden_small):
+    """generateBuffers(triangleList, meshList, nodeList): ranges recovered from the reference's node list."""
+    g = golden_small
+    nodes = np.zeros(len(g["gpunodes"]), _abi.REF_NODE)  # rebuild the host Node list from the GPUNode repack
+    gn = g["gpunodes"]
+    leaf = gn["numTriangles"] > 0
+    nodes["bmin"], nodes["bmax"] = gn["bmin"], gn["bmax"]
+    nodes["childIndex"] = np.where(leaf, 0, gn["index"])
+    nodes["firstTriangleIdx"] = np.where(leaf, gn["index"], 0)
+    nodes["numTriangles"] = gn["numTriangles"]
+    renderer.upload_ref(g["tris"], g["meshes"], nodes)
+    W, H = int(g["W"]), int(g["H"])
+    rgba, _, _ = renderer.render(g["cam"], W, H, 4, 50)
+    assert_images_equal(rgba, g["rgba_s4_b50"], "upload_ref")
+
+
+def test_default_scene_image_and_counters_vs_oracle(renderer, knight_obj):
+    s = rr.default_scene(knight_obj)
+    renderer.upload(s)
+    t, m, r, _ = s.arrays()
+    W = H = 128
+    cam = rr.default_camera(W, H)
+    o = Oracle(t, m, r)
+    for spp, bounces in [(1, 1), (2, 50), (16, 50)]:
+        want, wrad, ost = o.render(cam, W, H, spp, bounces, radiance=True)
+        got, grad, st = renderer.render(cam, W, H, spp, bounces, radiance=True, count_tests=True)
+        assert_images_equal(got, want, f"default spp={spp} b={bounces}")
+        assert np.array_equal(bits(grad), bits(wrad))
+        # identical paths => identical work: segments, box tests and triangle tests are exact
+        assert st["rays"] + st["rays_reused"] == ost["rays"]
+        if st["rays_reused"] == 0:
+            assert st["box_tests"] == ost["box_tests"] and st["tri_tests"] == ost["tri_tests"]
+
+
+def test_material_zoo_with_instances_and_spheres(renderer):
+    s = zoo_scene()
+    renderer.upload(s)
+    t, m, r, sp = s.arrays()
+    W, H = 160, 120
+    cam = zoo_camera(W, H)
+    o = Oracle(t, m, r, sp)
+    mesh, prim, dst = renderer.primary_hits(cam, W, H)
+    om, op, od = o.primary(cam, W, H)
+    assert np.array_equal(mesh, om) and np.array_equal(prim, op) and np.array_equal(bits(dst), bits(od))
+    assert len(np.unique(mesh)) >= 8
+    for spp, bounces in [(1, 1), (1, 12), (8, 50)]:
+        want, wrad, ost = o.render(cam, W, H, spp, bounces, radiance=True)
+        got, grad, st = renderer.render(cam, W, H, spp, bounces, radiance=True, count_tests=True)
+        assert_images_equal(got, want, f"zoo spp={spp} b={bounces}")
+        assert np.array_equal(bits(grad), bits(wrad))
+        assert st["rays"] + st["rays_reused"] == ost["rays"]
+
+
+def test_sphere_field_matches_oracle(renderer):
+    sp = scenes.random_spheres(256, seed=2)
+    s = rr.Scene()
+    s.add_quad((-400, 0, -400), (400, 0, -400), (400, 0, 400), (-400, 0, 400), (0, 1, 0), (0.5, 0.5, 0.5))
+    s.add_spheres(sp)
+    renderer.upload(s)
+    t, m, r, sp2 = s.arrays()
+    W, H = 192, 108
+    cam = np.zeros(1, _abi.CAMERA)
+    cam["position"][0, :3] = (0, 200, 520)
+    cam["pitch"], cam["yaw"], cam["fov"], cam["aspectRatio"] = 0.2, 3.14159, 70.0, W / H
+    want, wrad, ost = Oracle(t, m, r, sp2).render(cam, W, H, 8, 8, radiance=True)
+    got, grad, st = renderer.render(cam, W, H, 8, 8, radiance=True, count_tests=True)
+    assert_images_equal(got, want, "spheres")
+    assert np.array_equal(bits(grad), bits(wrad))
+    assert st["sphere_tests"] > 0
+
+
+def test_size_independent_properties_at_full_resolution(renderer, knight_obj):
+    """1080p: tiling invariance, determinism, rr_render == rr_render_device + rr_read_frame,
+    and L0 (maxBounce = 1): every pixel is black or the light's emission."""
+    renderer.upload(rr.default_scene(knight_obj))
+    W, H = 1920, 1080
+    cam = rr.default_camera(W, H)
+    a, _, st = renderer.render(cam, W, H, 2, 8)
+    b, _, _ = renderer.render(cam, W, H, 2, 8, tile=64)
+    c, _, _ = renderer.render(cam, W, H, 2, 8, tile=512)  # the reference's default TILE_SIZE
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert st["tiles"] == ((W + 7) // 8) * ((H + 3) // 4)
+    renderer.render_device(cam, W, H, 2, 8)
+    assert np.array_equal(renderer.read_frame(W, H), a)
+    assert np.array_equal(renderer.render_plain(cam, W, H, 2, 8), a)
+    l0, _, _ = renderer.render(cam, W, H, 3, 1)
+    vals = np.unique(l0[..., :3].reshape(-1, 3), axis=0)
+    assert set(map(tuple, vals.tolist())) <= {(0, 0, 0), (255, 255, 255)}
+    assert np.all(l0[..., 3] == 255)
+
+
+def test_edge_cases(renderer):
+    W, H = 33, 17  # ragged: not a multiple of the 8x4 tile
+    cam = rr.default_camera(W, H)
+    E = lambda dt: np.zeros(0, dt)
+    # empty scene: black, alpha 255
+    renderer.upload_arrays(E(_abi.TRIANGLE), E(_abi.MESH), E(_abi.MESH_RANGE))
+    img, _, st = renderer.render(cam, W, H, 2, 4)
+    assert np.all(img[..., :3] == 0) and np.all(img[..., 3] == 255) and st["rays"] == W * H * 2
+    # a mesh with no triangles and a single-triangle mesh
+    tri = np.zeros(1, _abi.TRIANGLE)
+    tri["posA"][0, :3], tri["posB"][0, :3], tri["posC"][0, :3] = (-200, 0, 0), (200, 0, 0), (0, 300, 0)
+    for k in ("normalA", "normalB", "normalC"):
+        tri[k][0, :3] = (0, 0, 1)
+    m = np.zeros(2, _abi.MESH)
+    m["scale"] = 1.0
+    m["material"]["emissionColor"][:, :3] = (1.0, 0.5, 0.25)
+    m["material"]["emissionStrength"] = 1.0
+    r = np.zeros(2, _abi.MESH_RANGE)
+    r["firstTriangle"], r["numTriangles"] = [0, 0], [0, 1]
+    renderer.upload_arrays(tri, m, r)
+    got, grad, _ = renderer.render(cam, W, H, 1, 1, radiance=True)
+    want, wrad, _ = Oracle(tri, m, r).render(cam, W, H, 1, 1, radiance=True)
+    assert np.array_equal(got, want) and np.array_equal(bits(grad), bits(wrad)) and got[..., 0].max() == 255
+    # max_bounces = 0: no segments at all
+    img, _, st = renderer.render(cam, W, H, 2, 0)
+    assert np.all(img[..., :3] == 0) and st["rays"] == 0
+    # errors
+    bad = r.copy()
+    bad["numTriangles"] = [0, 5]
+    with pytest.raises(_abi.RRError) as e:
+        renderer.upload_arrays(tri, m, bad)
+    assert e.value.status == 6
+    fresh = rr.Renderer()
+    with pytest.raises(_abi.RRError) as e:
+        fresh.render(cam, W, H, 1, 1)
+    assert e.value.status == 5
+    fresh.close()
+    with pytest.raises(_abi.RRError) as e:
+        renderer.render(cam, 0, H, 1, 1)
+    assert e.value.status in (1, 5)
+
+
+def test_statistical_parity_at_config_spp(renderer, knight_obj):
+    """L3 of the ladder: at 64 spp the image is bit-exact with the oracle on the same seed, so its error
+    against a converged oracle image equals the oracle's own (RMSE ratio exactly 1)."""
+    s = rr.default_scene(knight_obj)
+    renderer.upload(s)
+    t, m, r, _ = s.arrays()
+    W = H = 64
+    cam = rr.default_camera(W, H)
+    got, grad, _ = renderer.render(cam, W, H, 64, 50, radiance=True)
+    want, wrad, _ = Oracle(t, m, r).render(cam, W, H, 64, 50, radiance=True)
+    assert_images_equal(got, want, "64 spp")
+    assert np.array_equal(bits(grad), bits(wrad))

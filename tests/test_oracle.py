@@ -1,0 +1,174 @@
+"""Pins the oracle (oracle/rr_oracle.c) against the reference: golden vectors generated from the
+reference's own kernel text (tests/golden/make_golden.py) and, when oracle/_ref is present, the
+compiled reference itself."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import Oracle, Reference, mesh_ranges_from_gpunodes
+
+# integer-exact known answers derived from src/Trace.cl:158-217
+KAT = {
+    0: (0x2C9C914E, [0x283368B2, 0x57EA8B85, 0x7B4C0365], [0xE1C25991, 0xD0EF1F6F]),
+    1: (0xA67D6845, [0x8512BE46, 0xB8E5597D, 0xE31C3CFE], [0x6FC9F51C, 0xE23EE82D]),
+    511: (0xE3596D53, [0x07DFF332, 0xC47A8D42, 0x30C9CB9F], [0x16D723E6, 0x0563CF2E]),
+    262143: (0x65D9FB53, [0xCB43E06D, 0xDADB5C6F, 0xE3E83461], [0xA33F6EE9, 0xE7D8D38A]),
+    2073599: (0x24973F53, [0x7A33C9CF, 0x072042FA, 0x43C627E7], [0x25BF353C, 0x01814CBB]),
+}
+
+
+def u32_to_float(s):
+    return np.float32(np.float32((s + 1) & 0xFFFFFFFF) * np.float32(1.0 / 4294967296.0))
+
+
+def test_rng_known_answers():
+    l = Oracle.lib()
+    for pix, (seed, rv, r01) in KAT.items():
+        assert l.rro_make_seed(pix, 0, 0) == seed
+        st = C.c_uint32(seed)
+        for want in rv:
+            assert np.float32(l.rro_random_value(C.byref(st))) == u32_to_float(want)
+        st = C.c_uint32(seed)
+        for want in r01:
+            assert np.float32(l.rro_rand01(C.byref(st))) == u32_to_float(want)
+
+
+def test_rng_against_reference_golden(golden_rng):
+    l = Oracle.lib()
+    for i, pix in enumerate(golden_rng["pixels"]):
+        seed = l.rro_make_seed(int(pix), 0, 0)
+        assert seed == golden_rng["seeds"][i]
+        st = C.c_uint32(seed)
+        got = [l.rro_random_value(C.byref(st)) for _ in range(4)]
+        assert np.array_equal(np.array(got, np.float32), golden_rng["rv_float"][i])
+        assert st.value == golden_rng["rv_state_after4"][i]
+        st = C.c_uint32(seed)
+        got = [l.rro_rand01(C.byref(st)) for _ in range(4)]
+        assert np.array_equal(np.array(got, np.float32), golden_rng["r01_float"][i])
+        st = C.c_uint32(seed)
+        d = np.zeros(3, np.float32)
+        l.rro_random_direction(C.byref(st), C.c_void_p(d.ctypes.data))
+        assert np.array_equal(d.view(np.uint32), golden_rng["random_direction"][i].view(np.uint32))
+
+
+def test_map_u32_edge_cases():
+    # (float)(s+1) * 2^-32: s = 0xFFFFFFFF wraps to 0 -> exactly 0.0; large s round to exactly 1.0
+    assert u32_to_float(0xFFFFFFFF) == 0.0
+    assert u32_to_float(0xFFFFFFFE) == 1.0
+
+
+@pytest.mark.parametrize("which", ["golden_small", "golden_wide"])
+@pytest.mark.parametrize("mode", ["ref_bvh", "lbvh"])
+def test_oracle_reproduces_reference_golden_images(which, mode, request):
+    """Restatement vs the reference kernel: 8-bit image AND float radiance bit-identical,
+    both when walking the reference's SAH nodes and when walking our LBVH."""
+    g = request.getfixturevalue(which)
+    W, H = int(g["W"]), int(g["H"])
+    o = Oracle(g["tris"], g["meshes"], g["ranges"], ref_gpunodes=g["gpunodes"] if mode == "ref_bvh" else None)
+    for key in g:
+        if not key.startswith("rgba_"):
+            continue
+        _, s, b = key.split("_")
+        spp, bounces = int(s[1:]), int(b[1:])
+        rgba, rad, _ = o.render(g["cam"], W, H, spp, bounces, radiance=True, threads=4)
+        assert np.array_equal(rgba, g[key]), key
+        assert np.array_equal(rad.view(np.uint32), g["rad_" + key[5:]].view(np.uint32)), key
+
+
+def test_oracle_primary_hits_match_reference_golden(golden_small):
+    g = golden_small
+    W, H = int(g["W"]), int(g["H"])
+    o = Oracle(g["tris"], g["meshes"], g["ranges"])
+    mesh, prim, dst = o.primary(g["cam"], W, H, threads=4)
+    hit = g["primary_hit"]
+    assert np.array_equal(mesh >= 0, hit[..., 0] > 0)
+    assert np.array_equal(dst.view(np.uint32)[mesh >= 0], hit[..., 1].view(np.uint32)[mesh >= 0])
+    # material type of the hit mesh == the reference's
+    mt = g["meshes"]["material"]["type"]
+    assert np.array_equal(mt[mesh[mesh >= 0]], g["primary_flags"][mesh >= 0] >> 8)
+
+
+@pytest.mark.skipif(not Reference.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_vs_compiled_reference_default_scene(knight_obj):
+    """The full default scene (2 222 triangles, 8 meshes) at 96x96: restatement == reference, bit for bit."""
+    ref = Reference("strict")
+    tris, meshes, nodes = ref.scene_default(knight_obj)
+    ranges = mesh_ranges_from_gpunodes(meshes, nodes)
+    W = H = 96
+    cam = ref.default_camera(W, H)
+    o_ref = Oracle(tris, meshes, ranges, ref_gpunodes=nodes)
+    o_lbvh = Oracle(tris, meshes, ranges)
+    for spp, bounces in [(1, 1), (1, 50), (8, 50)]:
+        want, wrad = ref.render(cam, W, H, spp, bounces, radiance=True, threads=8)
+        for o in (o_ref, o_lbvh):
+            got, grad, _ = o.render(cam, W, H, spp, bounces, radiance=True, threads=8)
+            assert np.array_equal(got, want)
+            assert np.array_equal(grad.view(np.uint32), wrad.view(np.uint32))
+
+
+def test_lbvh_is_a_valid_hierarchy(golden_wide):
+    g = golden_wide
+    o = Oracle(g["tris"], g["meshes"], g["ranges"])
+    b = o.lbvh(0)
+    n = len(b["order"])
+    assert sorted(b["order"].tolist()) == list(range(n))
+    tri = g["tris"]
+    pmin = np.minimum(np.minimum(tri["posA"], tri["posB"]), tri["posC"])[:, :3]
+    pmax = np.maximum(np.maximum(tri["posA"], tri["posB"]), tri["posC"])[:, :3]
+    for r in g["ranges"]:
+        first, cnt = int(r["firstTriangle"]), int(r["numTriangles"])
+        codes = b["codes"][first:first + cnt]
+        assert np.all(codes[:-1] <= codes[1:])
+        assert sorted(b["order"][first:first + cnt].tolist()) == list(range(first, first + cnt))
+        if cnt < 2:
+            continue
+        seen = []
+
+        def walk(node):
+            lo = np.full(3, np.inf, np.float32)
+            hi = np.full(3, -np.inf, np.float32)
+            for ref in (b["left"][node], b["right"][node]):
+                if ref < 0:
+                    p = b["order"][~ref]
+                    seen.append(int(p))
+                    clo, chi = pmin[p], pmax[p]
+                else:
+                    assert b["parent"][ref] == node
+                    clo, chi = walk(int(ref))
+                lo, hi = np.minimum(lo, clo), np.maximum(hi, chi)
+            assert np.array_equal(b["bounds"][node, :3], lo) and np.array_equal(b["bounds"][node, 3:], hi)
+            return lo, hi
+
+        walk(first)
+        assert sorted(seen) == list(range(first, first + cnt))
+
+
+def test_spheres_extension_sanity():
+    """Spheres are an extension (no reference counterpart): a sphere and a finely tessellated
+    sphere mesh must give nearly the same primary distances."""
+    from ripoff_raytracer_b200 import _abi, scenes
+
+    v, n, f = scenes.uv_sphere(96, 48, radius=50.0, center=(0.0, 100.0, 0.0))
+    tris = scenes.mesh_triangles(v, n, f)
+    mesh = np.zeros(1, _abi.MESH)
+    mesh["scale"] = 1.0
+    mesh["material"]["color"][:, :3] = 1.0
+    ranges = np.zeros(1, _abi.MESH_RANGE)
+    ranges["numTriangles"] = len(tris)
+    sph = np.zeros(1, _abi.SPHERE)
+    sph["center"][0, :3] = (0.0, 100.0, 0.0)
+    sph["radius"] = 50.0
+    sph["material"]["color"][:, :3] = 1.0
+    cam = np.zeros(1, _abi.CAMERA)
+    cam["position"][0, :3] = (0.0, 100.0, 250.0)
+    cam["yaw"] = 3.14159265
+    cam["fov"] = 60.0
+    cam["aspectRatio"] = 1.0
+    W = H = 64
+    m1, _, d1 = Oracle(tris, mesh, ranges).primary(cam, W, H, threads=4)
+    m2, _, d2 = Oracle(np.zeros(0, _abi.TRIANGLE), np.zeros(0, _abi.MESH), np.zeros(0, _abi.MESH_RANGE), sph).primary(cam, W, H, threads=4)
+    both = (m1 >= 0) & (m2 >= 0)
+    assert both.sum() > 300
+    assert np.abs((m1 >= 0).astype(int) - (m2 >= 0).astype(int)).sum() < 60  # silhouette pixels only
+    assert np.max(np.abs(d1[both] - d2[both])) < 0.5
