@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the render hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus 1 --steps K ...  # the reference's CPU implementation of the path
+
+A *step* is one frame of the workload (default: BASELINE.json configs[3], the ~1 M-triangle mixed
+mesh+sphere scene at 3840x2160, 256 spp -- the configuration the north-star target is quoted on).
+`value` is whole-job Mrays/s with the scene resident in HBM (path segments per second; a segment is
+one closest-hit query, reference src/Trace.cl:494).  `e2e` is the same metric through the C-ABI
+boundary call with HOST buffers: scene upload from pinned memory + LBVH build + render + frame
+read-back, every step.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+F_BOX, F_TRI, F_SPH = 24, 53, 24     # algorithmic flop per test (sphere: DESIGN.md 6)
+B_BOX, B_TRI, B_SPH = 32, 48, 16     # algorithmic bytes per test
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--spp", type=int, default=0)
+    ap.add_argument("--bounces", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def make_workload(args):
+    from ripoff_raytracer_b200 import workloads
+
+    kw = {}
+    for k in ("width", "height", "spp", "bounces"):
+        if getattr(args, k):
+            kw[k] = getattr(args, k)
+    return workloads.WORKLOADS[args.workload](**kw)
+
+
+# ----------------------------------------------------------------------------- clocks ----
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.stop, self.t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.25)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows for k in range(4) if len(r) > 2 + k and r[2 + k] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------- reference arm ----
+def cpu_reference_run(wl, steps, warmup, budget_s=20.0):
+    """The reference's own kernel source (src/Trace.cl compiled for the host, -O3 -ffast-math: the analogue of
+    its -cl-fast-relaxed-math JIT flags) with its own SAH hierarchy, on all host cores, on a bounded sample
+    of the workload: the same scene and camera at reduced resolution / spp."""
+    from oracle.pyoracle import Oracle, Reference
+
+    cores = os.cpu_count() or 1
+    t, m, r, sp = wl.scene.arrays()
+    # the reference kernel has no sphere primitive: a spheres-only workload can only be timed with the port
+    kind = "reference" if Reference.available("fast") and len(t) > 14 else "port"
+    # sample geometry: same aspect, 1/8 linear resolution (>= 64 px wide), spp scaled to the time budget
+    W = max(64, wl.width // 8)
+    H = max(36, wl.height // 8)
+    cam = wl.cam.copy()
+    if kind == "reference":
+        # the reference kernel has no sphere primitive: its arm renders the triangle part of the scene
+        ref = Reference("fast")
+        t0 = time.perf_counter()
+        rt, rm, _ = ref.scene_from_arrays(t, m, r)
+        build_s = time.perf_counter() - t0
+        counter = Oracle(rt, rm, r)                      # strict restatement: counts the segments of the same sample
+        render = lambda spp: ref.render(cam, W, H, spp, wl.bounces, threads=cores)
+    else:
+        t0 = time.perf_counter()
+        counter = Oracle(t, m, r, sp)
+        build_s = time.perf_counter() - t0
+        render = lambda spp: counter.render(cam, W, H, spp, wl.bounces, threads=cores)
+    # calibrate spp for ~budget_s/(steps+warmup) per step
+    t0 = time.perf_counter()
+    render(1)
+    per_spp = max(time.perf_counter() - t0, 1e-4)
+    spp = int(max(1, min(wl.spp, budget_s / max(steps + warmup, 1) / per_spp)))
+    _, _, cst = counter.render(cam, W, H, spp, wl.bounces, threads=cores)
+    rays = cst["rays"]
+    for _ in range(warmup):
+        render(spp)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        render(spp)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {
+        "mrays_s": rays / dt / 1e6, "msamples_s": W * H * spp / dt / 1e6, "ms_per_step": dt * 1e3, "cores": cores,
+        "kind": kind, "build_s": build_s,
+        "sample": f"{wl.name} scene ({len(t)} tris{'' if kind == 'port' else ', triangles only: the reference kernel has no spheres'}) "
+                  f"at {W}x{H}, {spp} spp, {wl.bounces} bounces = {rays} path segments per step; "
+                  + ("reference Trace.cl text compiled for the host (-O3 -ffast-math) with its SAH BVH" if kind == "reference"
+                     else "oracle/rr_oracle.c restatement") + f", {cores} threads",
+    }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = make_workload(args)
+    res = cpu_reference_run(wl, args.steps, max(args.warmup, 1), budget_s=60.0)
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": res["mrays_s"], "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl, args.gpus),
+        "msamples_per_s": res["msamples_s"],
+        "cpu_baseline": {"value": res["mrays_s"], "unit": "Mrays/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
+        "e2e": {"value": res["mrays_s"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(wl, n_gpus):
+    return {"workload": f"{wl.name}: {wl.description}; {wl.width}x{wl.height}, {wl.spp} spp, {wl.bounces} bounces",
+            "triangles": wl.scene.n_triangles, "spheres": wl.scene.n_spheres, "meshes": wl.scene.n_meshes,
+            "width": wl.width, "height": wl.height, "spp": wl.spp, "max_bounces": wl.bounces,
+            "parallelism": f"tile-queue x{n_gpus}" if n_gpus > 1 else "1 GPU, persistent warps over an atomic tile queue",
+            "l2": "scene arrays (nodes+triangles+normals) exceed the 126 MB L2 and a 256 MB buffer is written between steps"}
+
+
+# ------------------------------------------------------------------------------ our arm ----
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import ripoff_raytracer_b200 as rr
+    from ripoff_raytracer_b200 import _abi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the render path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    wl = make_workload(args)
+    W, H, spp, bounces = wl.width, wl.height, wl.spp, wl.bounces
+    tris, meshes, ranges, spheres = wl.scene.arrays()
+
+    # host buffers of the boundary call live in pinned memory (torch owns the allocation)
+    def pinned_copy(a):
+        t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        out = t.numpy()[: a.nbytes].view(a.dtype).reshape(a.shape)
+        out[...] = a
+        return t, out
+
+    keep = []
+    host = {}
+    for name, arr in (("tris", tris), ("meshes", meshes), ("ranges", ranges), ("spheres", spheres)):
+        t, v = pinned_copy(arr)
+        keep.append(t)
+        host[name] = v
+    frame_t = torch.empty(W * H * 4, dtype=torch.uint8, pin_memory=True)
+    frame_host = frame_t.numpy().reshape(H, W, 4)
+
+    r = rr.Renderer((local,))
+    r.upload_arrays(host["tris"], host["meshes"], host["ranges"], host["spheres"])
+
+    # ---- multi-GPU plumbing: rank 0 owns the tile counter and the frame; peers attach over CUDA IPC ----
+    mode = "local"
+    if world > 1:
+        handles = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            q, f = r.queue_export(W, H)
+            handles.copy_(torch.from_numpy(np.concatenate([q, f])))
+        dist.broadcast(handles, 0)
+        ok = torch.ones(1, device="cuda")
+        if rank != 0:
+            h = handles.cpu().numpy()
+            try:
+                r.queue_import(W, H, h[:64], h[64:])
+            except _abi.RRError as e:
+                print(f"[rank {rank}] IPC import failed ({e}); falling back to a static tile partition", file=sys.stderr)
+                ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        mode = "shared" if ok.item() > 0 else "strided"
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def device_step():
+        flush.fill_(1)  # evict L2 between steps
+        if mode == "local":
+            return r.render_device(wl.cam, W, H, spp, bounces)
+        if mode == "shared":
+            if rank == 0:
+                r.queue_reset()
+            barrier()
+            return r.render_shared(wl.cam, W, H, spp, bounces)
+        st = r.render_strided(wl.cam, W, H, spp, bounces, rank, world)
+        return st
+
+    def total(x: float, op=None):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op or dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- per-ray test counts from one instrumented low-spp frame (same scene, same rays per pixel prefix) ----
+    probe_spp = max(1, min(spp, 4))
+    _, _, pst = r.render(wl.cam, W, H, probe_spp, bounces, count_tests=True)
+    traced = max(pst["rays"], 1)
+    n_box, n_tri, n_sph = pst["box_tests"] / traced, pst["tri_tests"] / traced, pst["sphere_tests"] / traced
+    flops_per_ray = n_box * F_BOX + n_tri * F_TRI + n_sph * F_SPH
+    bytes_per_ray = n_box * B_BOX + n_tri * B_TRI + n_sph * B_SPH
+
+    # ---- warm-up, then K timed steps ----
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    rays_total = rays_traced = 0
+    kernel_ms = []
+    with ClockSampler(local) as clocks:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            st = device_step()
+            rays_total += st["rays"] + st["rays_reused"]
+            rays_traced += st["rays"]
+            kernel_ms.append(st["render_ms"])
+        barrier()
+        dt = time.perf_counter() - t0
+    dt = total(dt, dist.ReduceOp.MAX if world > 1 else None)
+    rays_all = total(float(rays_total))
+    traced_all = total(float(rays_traced))
+    kernel_s = float(np.mean(kernel_ms)) / 1e3 if kernel_ms else 0.0
+    kernel_s = total(kernel_s, dist.ReduceOp.MAX if world > 1 else None)
+    samples_all = float(W) * H * spp * args.steps
+    value = rays_all / dt / 1e6
+    clk = clocks.summary()
+
+    # ---- end to end through the boundary call: host scene in, host frame out, every step ----
+    e2e = None
+    if not args.no_e2e:
+        h2d = host["tris"].nbytes + host["meshes"].nbytes + host["spheres"].nbytes + host["ranges"].nbytes + 48
+        d2h = W * H * 4
+        e2e_steps = max(1, min(args.steps, 2))
+        e_rays = 0.0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            r.upload_arrays(host["tris"], host["meshes"], host["ranges"], host["spheres"])  # H2D + LBVH build
+            if mode == "local":
+                _, _, st = r.render(wl.cam, W, H, spp, bounces, out=frame_host)              # render + D2H
+            else:
+                st = device_step_e2e(r, rr, wl, mode, rank, world, barrier, frame_host)
+            e_rays += st["rays"] + st["rays_reused"]
+        barrier()
+        e_dt = total(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+        e_rays = total(e_rays)
+        e2e = {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e_dt / e2e_steps * 1e3, "steps": e2e_steps,
+               "includes": "rr_upload_scene (H2D from pinned memory + LBVH build) + rr_render (kernel + frame D2H)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_render): counted intersection work / live kernel time ----
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+    sm_max = (clk.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+    fp32_peak_tflops = sm_count * 128 * 2 * sm_max * 1e6 / 1e12  # 128 FP32 lanes/SM, FMA = 2 flop
+    per_launch_rays = traced_all / args.steps / world
+    ach_tflops = per_launch_rays * flops_per_ray / kernel_s / 1e12 if kernel_s else 0.0
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    ach_gbs = per_launch_rays * bytes_per_ray / kernel_s / 1e9 if kernel_s else 0.0
+    roofline = {
+        "bound": "fp32", "kernel": "k_render", "achieved": ach_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+        "frac": ach_tflops / fp32_peak_tflops, "traffic": None,
+        "peak_source": f"nominal FP32 FMA peak: {sm_count} SMs x 128 lanes x 2 flop x {sm_max:.0f} MHz (MEASURED_PEAKS.json holds no FP32 figure)",
+        "flops_per_ray": flops_per_ray, "bytes_per_ray": bytes_per_ray, "box_tests_per_ray": n_box, "tri_tests_per_ray": n_tri,
+        "sphere_tests_per_ray": n_sph, "kernel_ms": kernel_s * 1e3,
+        "note": "arithmetic is issued unfused (-fmad=false, numerics contract): the reachable ceiling is half the FMA peak",
+    }
+    roofline_mem = {"bound": "hbm", "kernel": "k_render", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach_gbs / hbm_peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"}
+
+    line = {
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(wl, world),
+        "msamples_per_s": samples_all / dt / 1e6, "frame_time_s": dt / args.steps, "rays_per_sample": rays_all / samples_all,
+        "rays_traced_fraction": traced_all / max(rays_all, 1.0), "tile_queue": mode,
+        "clocks": clk, "gpu_launches": args.steps * world, "roofline": roofline, "roofline_memory": roofline_mem,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            res = cpu_reference_run(wl, 1, 1, budget_s=20.0)
+            line["cpu_baseline"] = {"value": res["mrays_s"], "unit": "Mrays/s", "cores": res["cores"], "kind": res["kind"],
+                                    "sample": res["sample"], "msamples_per_s": res["msamples_s"]}
+        except Exception as e:  # the checker is optional for the measurement itself
+            line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def device_step_e2e(r, rr, wl, mode, rank, world, barrier, frame_host):
+    """One multi-GPU frame ending with the frame in rank 0's host buffer."""
+    W, H = wl.width, wl.height
+    if mode == "shared":
+        if rank == 0:
+            r.queue_reset()
+        barrier()
+        st = r.render_shared(wl.cam, W, H, wl.spp, wl.bounces)
+        barrier()
+        if rank == 0:
+            frame_host[...] = r.read_frame(W, H)
+        return st
+    import torch
+    import torch.distributed as dist
+
+    st = r.render_strided(wl.cam, W, H, wl.spp, wl.bounces, rank, world)
+    fr = r.read_frame(W, H)  # strided fallback: host-side merge through NCCL on an int32 view
+    t = torch.from_numpy(fr.view(np.int32).copy()).cuda()
+    dist.reduce(t, 0, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        frame_host[...] = t.cpu().numpy().view(np.uint8).reshape(H, W, 4)
+    return st
+
+
+if __name__ == "__main__":
+    main()

@@ -143,6 +143,7 @@ class Reference:
             l = C.CDLL(str(REF_DIR / f"libref_{variant}.so"))
             l.ref_scene_default.argtypes = [C.c_char_p]
             l.ref_scene_set.argtypes = [_vp, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t]
+            l.ref_scene_from_arrays.argtypes = [_vp, C.c_size_t, _vp, _vp, C.c_size_t]
             l.ref_count.restype = C.c_size_t
             l.ref_count.argtypes = [C.c_int]
             l.ref_copy.argtypes = [C.c_int, _vp]
@@ -168,6 +169,14 @@ class Reference:
 
     def scene_set(self, tris, meshes, gpunodes):
         self.l.ref_scene_set(_p(tris), len(tris), _p(meshes), len(meshes), _p(gpunodes), len(gpunodes))
+
+    def scene_from_arrays(self, tris, meshes, ranges):
+        """Caller arrays + the reference's own SplitBVH (SAH) hierarchy; returns the (reordered) upload arrays."""
+        tris = np.ascontiguousarray(tris)
+        meshes = np.ascontiguousarray(meshes)
+        ranges = np.ascontiguousarray(ranges)
+        self.l.ref_scene_from_arrays(_p(tris), len(tris), _p(meshes), _p(ranges), len(meshes))
+        return self.arrays()
 
     def arrays(self):
         from ripoff_raytracer_b200._abi import GPU_NODE, MESH, TRIANGLE

@@ -125,6 +125,47 @@ int ref_scene_set(const void* tris, size_t ntris, const void* meshes, size_t nme
   return 0;
 }
 
+// Scene from caller arrays, hierarchy built by the REFERENCE's own SplitBVH
+// (src/readobj.hpp:206-267).  For each mesh the root node is formed exactly as
+// loadMeshFromOBJFile does after parsing (src/readobj.hpp:346-367: childIndex =
+// size+1, bounds grown from the struct defaults, SplitBVH(root, 64)); meshes of
+// <= 2 triangles get the single leaf node addQuad makes (src/readobj.hpp:379-392).
+// ranges: (firstTriangle, numTriangles) pairs, uint64 each.
+int ref_scene_from_arrays(const void* tris, size_t ntris, const void* meshes, const unsigned long long* ranges, size_t nmeshes) {
+  ref_scene_reset();
+  triangleList.resize(ntris);
+  if (ntris) memcpy((void*)triangleList.data(), tris, ntris * 96);
+  meshList.resize(nmeshes);
+  if (nmeshes) memcpy((void*)meshList.data(), meshes, nmeshes * 112);
+  for (size_t m = 0; m < nmeshes; ++m) {
+    size_t first = ranges[2 * m], count = ranges[2 * m + 1];
+    Node c;
+    c.firstTriangleIdx = first;
+    c.numTriangles = count;
+    c.childIndex = count <= 2 ? 0 : nodeList.size() + 1;
+    for (size_t t = 0; t < count; ++t) GrowToInclude(c.bounds, triangleList[first + t]);
+    size_t rootIdx = nodeList.size();
+    nodeList.emplace_back(c);
+    if (count > 2) SplitBVH(rootIdx, 64);
+    meshList[m].nodeIdx = rootIdx;
+  }
+  std::vector<GPUNode> gpuNodes(nodeList.size());
+  for (size_t i = 0; i < nodeList.size(); ++i) {  // src/image.hpp:116-125
+    GPUNode n;
+    n.bounds = nodeList[i].bounds;
+    n.index = nodeList[i].childIndex == 0 ? nodeList[i].firstTriangleIdx : nodeList[i].childIndex;
+    n.numTriangles = nodeList[i].childIndex == 0 ? nodeList[i].numTriangles : 0;
+    gpuNodes[i] = n;
+  }
+  g_tris.resize(triangleList.size());
+  g_meshes.resize(meshList.size());
+  g_nodes.resize(gpuNodes.size());
+  if (!g_tris.empty()) memcpy((void*)g_tris.data(), triangleList.data(), g_tris.size() * 96);
+  if (!g_meshes.empty()) memcpy((void*)g_meshes.data(), meshList.data(), g_meshes.size() * 112);
+  if (!g_nodes.empty()) memcpy((void*)g_nodes.data(), gpuNodes.data(), g_nodes.size() * 48);
+  return 0;
+}
+
 size_t ref_count(int what) { return what == 0 ? g_tris.size() : what == 1 ? g_meshes.size() : g_nodes.size(); }
 
 void ref_copy(int what, void* out) {
