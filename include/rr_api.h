@@ -173,6 +173,10 @@ typedef struct rr_stats {
   uint64_t tiles;        /* tiles this context rendered                     */
   float render_ms;       /* device time of the render kernel(s), CUDA events */
   float build_ms;        /* device time of the last LBVH build              */
+  /* warp-scheduler statistics of the instrumented kernel (count_tests != 0): how often each phase
+   * (0 pixel, 1 shade, 2 mesh setup, 3 node step, 4 leaf test) ran in a warp, and the lanes active in it */
+  uint64_t phase_runs[5];
+  uint64_t phase_lanes[5];
 } rr_stats;
 
 /* Replaces singleThreadedCompute / multiThreadedCompute + renderTile
@@ -191,6 +195,12 @@ int rr_render(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height
 int rr_render_ex(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
                  uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, uint8_t* rgba_out,
                  float* radiance_out, rr_stats* stats_out, int count_tests);
+
+/* Scheduler knobs of the render kernel (performance only; the image does not depend on them).
+ * values[0..4]: vote weight of the phases pixel/shade/setup/node-step/leaf, [5]: the node-step loop keeps
+ * running while at least this many lanes can step, [6]: speculative traversal on/off, [7]: persistent
+ * CTAs per SM (0 = as many as fit).  n < 8 leaves the rest unchanged; values == NULL restores defaults. */
+int rr_set_tuning(rr_ctx* ctx, const uint32_t* values, size_t n);
 
 /* Device-resident variant used for kernel-only timing: renders into the
  * context's own frame buffer on the device and does not copy it back.

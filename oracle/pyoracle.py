@@ -47,6 +47,7 @@ class Oracle:
             l.rro_scene_create.argtypes = [_vp, _u64, _vp, _vp, _u64, _vp, _u64]
             l.rro_scene_destroy.argtypes = [_vp]
             l.rro_scene_set_ref_nodes.argtypes = [_vp, _vp]
+            l.rro_scene_set_brute_force.argtypes = [_vp, C.c_int]
             l.rro_lbvh_size.restype = _u64
             l.rro_lbvh_size.argtypes = [_vp, C.c_int]
             l.rro_lbvh_depth.restype = _u32
@@ -90,6 +91,11 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+    def brute_force(self, on=True):
+        """Closest hit by testing every primitive of a mesh (no hierarchy): the definition of the result."""
+        self.lib().rro_scene_set_brute_force(self.h, 1 if on else 0)
+        return self
 
     def render(self, cam, W, H, spp, bounces, frame_index=0, radiance=False, threads=8):
         rgba = np.zeros((H, W, 4), np.uint8)

@@ -152,7 +152,8 @@ typedef struct {
 
 typedef struct {
   uint64_t first, count;
-  float bmin[3], bmax[3]; /* local-space root box */
+  float bmin[3], bmax[3]; /* local-space root box, delta-inflated */
+  float delta;            /* conservative slack of every box of this segment (box_delta) */
   m33 R, Rinv;
   int cull;
 } rro_meshx;
@@ -167,8 +168,10 @@ typedef struct rro_scene {
   rro_lbvh tb;  /* triangles, one segment per mesh */
   rro_lbvh sb;  /* spheres, one segment */
   float sph_bmin[3], sph_bmax[3];
+  float sph_delta;
   /* optional: the reference's own node list (GPUNode layout) for validation */
   const void* ref_nodes;
+  int brute_force; /* 1: closest hit by testing every primitive (no hierarchy): defines the result */
 } rro_scene;
 
 /* ---- Oracle B: LBVH --------------------------------------------------- */
@@ -237,6 +240,23 @@ static void lbvh_free(rro_lbvh* b) {
 static void box_of_ref(const rro_lbvh* b, int32_t ref, float* out) {
   if (ref < 0) memcpy(out, b->prim_box + 6 * (size_t)b->order[~ref], 24);
   else memcpy(out, b->bounds + 6 * (size_t)ref, 24);
+}
+
+/* Conservative slack added to every box a ray is tested against (same statement as
+ * ripoff_raytracer_b200/csrc/rr_internal.h box_delta): 2^-18 of the largest |coordinate| of the
+ * segment box.  With it the hierarchy only culls what cannot hold the closest hit, so the result
+ * equals the brute-force minimum over all primitives whatever the traversal order. */
+static float box_delta(const float* smin, const float* smax) {
+  float m = 0.0f;
+  for (int k = 0; k < 3; ++k) {
+    float a = fabsf(smin[k]), c = fabsf(smax[k]);
+    if (a > m && a < 3.0e38f) m = a;
+    if (c > m && c < 3.0e38f) m = c;
+  }
+  return m * 3.814697265625e-06f;
+}
+static void inflate_box(float* box6, float d) {
+  for (int k = 0; k < 3; ++k) { box6[k] -= d; box6[3 + k] += d; }
 }
 
 /* Builds the hierarchy of one segment [first, first+n) whose prim_box entries
@@ -352,6 +372,8 @@ rro_scene* rro_scene_create(const rr_triangle* tris, uint64_t n_tris, const rr_m
     x->count = ranges[m].numTriangles;
     if (x->first + x->count > n_tris) { x->count = 0; }
     lbvh_build_segment(&s->tb, x->first, x->count, x->bmin, x->bmax);
+    x->delta = box_delta(x->bmin, x->bmax);
+    for (int a = 0; a < 3; ++a) { x->bmin[a] -= x->delta; x->bmax[a] += x->delta; }
     x->R = make_rotation(meshes[m].pitch, meshes[m].yaw, meshes[m].roll);
     x->Rinv = transpose(x->R);
     int ty = meshes[m].material.type;
@@ -367,6 +389,8 @@ rro_scene* rro_scene_create(const rr_triangle* tris, uint64_t n_tris, const rr_m
     }
   }
   lbvh_build_segment(&s->sb, 0, n_spheres, s->sph_bmin, s->sph_bmax);
+  s->sph_delta = box_delta(s->sph_bmin, s->sph_bmax);
+  for (int a = 0; a < 3; ++a) { s->sph_bmin[a] -= s->sph_delta; s->sph_bmax[a] += s->sph_delta; }
   return s;
 }
 
@@ -381,6 +405,7 @@ void rro_scene_destroy(rro_scene* s) {
  * caller keeps it alive.  When set, triangle meshes are traversed with the
  * reference's own hierarchy and tie rule (validation against libref). */
 void rro_scene_set_ref_nodes(rro_scene* s, const void* gpunodes) { s->ref_nodes = gpunodes; }
+void rro_scene_set_brute_force(rro_scene* s, int on) { s->brute_force = on; }
 
 uint64_t rro_lbvh_size(const rro_scene* s, int which) { return which ? s->sb.n : s->tb.n; }
 uint32_t rro_lbvh_depth(const rro_scene* s, int which) { return which ? s->sb.max_depth : s->tb.max_depth; }
@@ -477,10 +502,12 @@ static void mesh_closest_lbvh(const rro_scene* sc, const rro_meshx* mx, const ra
   best->dst = tmax;
   best->prim = 0x7fffffff;
   float distRoot;
-  c->box_tests++;
-  if (!ray_box(ray, mx->bmin, mx->bmax, &distRoot)) return;
+  if (!sc->brute_force) {
+    c->box_tests++;
+    if (!ray_box(ray, mx->bmin, mx->bmax, &distRoot)) return;
+  }
   const rro_lbvh* b = &sc->tb;
-  if (mx->count <= RRO_DIRECT_MAX) {
+  if (mx->count <= RRO_DIRECT_MAX || sc->brute_force) {
     for (uint64_t k = 0; k < mx->count; ++k) {
       uint32_t prim = b->order[mx->first + k];
       c->tri_tests++;
@@ -497,10 +524,12 @@ static void mesh_closest_lbvh(const rro_scene* sc, const rro_meshx* mx, const ra
     float ba[6], bb[6], dA, dB;
     box_of_ref(b, L, ba);
     box_of_ref(b, R, bb);
+    inflate_box(ba, mx->delta);
+    inflate_box(bb, mx->delta);
     c->box_tests += 2;
-    int hA = ray_box(ray, ba, ba + 3, &dA) && dA < best->dst;
-    int hB = ray_box(ray, bb, bb + 3, &dB) && dB < best->dst;
-    int32_t next;
+    int hA = ray_box(ray, ba, ba + 3, &dA) && dA <= best->dst;
+    int hB = ray_box(ray, bb, bb + 3, &dB) && dB <= best->dst;
+    int32_t next = 0;
     int have = 0;
     if (hA && hB) {
       int32_t far;
@@ -522,7 +551,7 @@ static void mesh_closest_lbvh(const rro_scene* sc, const rro_meshx* mx, const ra
       int found = 0;
       while (sp > 0) {
         --sp;
-        if (stackD[sp] < best->dst) { next = stackN[sp]; found = 1; break; }
+        if (stackD[sp] <= best->dst) { next = stackN[sp]; found = 1; break; }
       }
       if (!found) return;
       have = 1;
@@ -613,10 +642,12 @@ static void spheres_closest(const rro_scene* sc, const ray_t* ray, float tmax, h
   best->prim = 0x7fffffff;
   if (sc->n_spheres == 0) return;
   float distRoot;
-  c->box_tests++;
-  if (!ray_box(ray, sc->sph_bmin, sc->sph_bmax, &distRoot)) return;
+  if (!sc->brute_force) {
+    c->box_tests++;
+    if (!ray_box(ray, sc->sph_bmin, sc->sph_bmax, &distRoot)) return;
+  }
   const rro_lbvh* b = &sc->sb;
-  if (sc->n_spheres <= RRO_DIRECT_MAX) {
+  if (sc->n_spheres <= RRO_DIRECT_MAX || sc->brute_force) {
     for (uint64_t k = 0; k < sc->n_spheres; ++k) {
       uint32_t prim = b->order[k];
       c->sphere_tests++;
@@ -633,10 +664,12 @@ static void spheres_closest(const rro_scene* sc, const ray_t* ray, float tmax, h
     float ba[6], bb[6], dA, dB;
     box_of_ref(b, L, ba);
     box_of_ref(b, R, bb);
+    inflate_box(ba, sc->sph_delta);
+    inflate_box(bb, sc->sph_delta);
     c->box_tests += 2;
-    int hA = ray_box(ray, ba, ba + 3, &dA) && dA < best->dst;
-    int hB = ray_box(ray, bb, bb + 3, &dB) && dB < best->dst;
-    int32_t next;
+    int hA = ray_box(ray, ba, ba + 3, &dA) && dA <= best->dst;
+    int hB = ray_box(ray, bb, bb + 3, &dB) && dB <= best->dst;
+    int32_t next = 0;
     int have = 0;
     if (hA && hB) {
       int32_t far;
@@ -657,7 +690,7 @@ static void spheres_closest(const rro_scene* sc, const ray_t* ray, float tmax, h
       int found = 0;
       while (sp > 0) {
         --sp;
-        if (stackD[sp] < best->dst) { next = stackN[sp]; found = 1; break; }
+        if (stackD[sp] <= best->dst) { next = stackN[sp]; found = 1; break; }
       }
       if (!found) return;
       have = 1;

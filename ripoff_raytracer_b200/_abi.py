@@ -90,10 +90,15 @@ class Stats(C.Structure):
         ("tiles", C.c_uint64),
         ("render_ms", C.c_float),
         ("build_ms", C.c_float),
+        ("phase_runs", C.c_uint64 * 5),
+        ("phase_lanes", C.c_uint64 * 5),
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["phase_runs"] = list(d["phase_runs"])
+        d["phase_lanes"] = list(d["phase_lanes"])
+        return d
 
 
 # every symbol include/rr_api.h declares: name -> (restype, argtypes)
@@ -110,6 +115,7 @@ SYMBOLS = {
     "rr_upload_scene_ref": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, _sz]),
     "rr_render": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, _vp]),
     "rr_render_ex": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, _vp, _vp, C.POINTER(Stats), C.c_int]),
+    "rr_set_tuning": (C.c_int, [_vp, _vp, _sz]),
     "rr_render_device": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, C.POINTER(Stats)]),
     "rr_read_frame": (C.c_int, [_vp, _vp, _sz]),
     "rr_primary_hits": (C.c_int, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),

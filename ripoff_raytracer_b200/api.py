@@ -201,6 +201,14 @@ class Renderer:
                                  C.byref(st), 1 if count_tests else 0), "rr_render_ex")
         return rgba, rad, st.as_dict()
 
+    def set_tuning(self, values=None):
+        """Scheduler knobs of the render kernel (rr_set_tuning); None restores the defaults."""
+        if values is None:
+            check(lib().rr_set_tuning(self.h, None, 0), "rr_set_tuning")
+        else:
+            v = np.ascontiguousarray(values, np.uint32)
+            check(lib().rr_set_tuning(self.h, ptr(v), len(v)), "rr_set_tuning")
+
     def render_plain(self, cam, width, height, spp, bounces, frame_index=0, tile=0, out=None):
         """The boundary call itself: rr_render (host buffers in and out)."""
         cam = np.ascontiguousarray(cam, CAMERA)

@@ -45,9 +45,9 @@ struct Device {
   float* sph_box = nullptr;
   Lbvh tb, sb;
   float4 *tri_geom = nullptr, *tri_nrm = nullptr, *sph_geom = nullptr;
+  float4* nodes = nullptr;  // triangle hierarchies, then the sphere hierarchy
   DMesh* meshes = nullptr;
   DMaterial* materials = nullptr;
-  float sph_bounds[6] = {0, 0, 0, 0, 0, 0};
   float build_ms = 0.0f;
   // frame
   uint8_t* frame = nullptr;
@@ -69,6 +69,7 @@ struct rr_ctx {
   size_t n_tris = 0, n_meshes = 0, n_spheres = 0;
   bool has_scene = false;
   bool peer_ok = false;  // devices 1.. can address device 0's memory
+  rr::Tuning tune;
 };
 
 namespace rr {
@@ -78,7 +79,8 @@ namespace rr {
 __global__ void k_prepare_meshes(const rr_mesh* __restrict__ meshes, const uint32_t* __restrict__ mesh_seg, int n_meshes,
                                  const float* __restrict__ seg_box, const uint32_t* __restrict__ seg_sfirst,
                                  const uint32_t* __restrict__ seg_count, const rr_sphere* __restrict__ spheres,
-                                 int n_spheres, DMesh* __restrict__ out, DMaterial* __restrict__ mats) {
+                                 int n_spheres, const float* __restrict__ sph_seg_box, uint32_t sph_node_base,
+                                 DMesh* __restrict__ out, DMaterial* __restrict__ mats) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_meshes + n_spheres) return;
   const rr_material* src;
@@ -90,28 +92,69 @@ __global__ void k_prepare_meshes(const rr_mesh* __restrict__ meshes, const uint3
     const float cy = cos_c(m.yaw), sy = sin_c(m.yaw);
     const float cz = cos_c(m.roll), sz = sin_c(m.roll);
     // makeRotation, src/Trace.cl:90-100
-    d.R[0] = cy * cz; d.R[1] = cy * sz; d.R[2] = -sy;
-    d.R[3] = cz * sy * sx - cx * sz; d.R[4] = cx * cz + sx * sy * sz; d.R[5] = cy * sx;
-    d.R[6] = sx * sz + cx * cz * sy; d.R[7] = cx * sy * sz - cz * sx; d.R[8] = cx * cy;
-    // transpose_mat, src/Trace.cl:109-116
-    d.Rinv[0] = d.R[0]; d.Rinv[1] = d.R[3]; d.Rinv[2] = d.R[6];
-    d.Rinv[3] = d.R[1]; d.Rinv[4] = d.R[4]; d.Rinv[5] = d.R[7];
-    d.Rinv[6] = d.R[2]; d.Rinv[7] = d.R[5]; d.Rinv[8] = d.R[8];
-    d.pos[0] = m.pos.s[0]; d.pos[1] = m.pos.s[1]; d.pos[2] = m.pos.s[2];
-    d.scale = m.scale;
+    float R[9];
+    R[0] = cy * cz; R[1] = cy * sz; R[2] = -sy;
+    R[3] = cz * sy * sx - cx * sz; R[4] = cx * cz + sx * sy * sz; R[5] = cy * sx;
+    R[6] = sx * sz + cx * cz * sy; R[7] = cx * sy * sz - cz * sx; R[8] = cx * cy;
+    const float px = m.pos.s[0], py = m.pos.s[1], pz = m.pos.s[2];
+    // transpose_mat, src/Trace.cl:109-116 (rows of the inverse), position in .w
+    d.ri0 = make_float4(R[0], R[3], R[6], px);
+    d.ri1 = make_float4(R[1], R[4], R[7], py);
+    d.ri2 = make_float4(R[2], R[5], R[8], pz);
+    const uint32_t sbits = __float_as_uint(m.scale);
+    const uint32_t sexp = (sbits >> 23) & 0xffu;
+    const bool pow2 = m.scale > 0.0f && (sbits & 0x007fffffu) == 0u && sexp > 64u && sexp < 190u;
+    d.r0 = make_float4(R[0], R[1], R[2], m.scale);
+    d.r1 = make_float4(R[3], R[4], R[5], pow2 ? 1.0f / m.scale : 0.0f);
+    d.r2 = make_float4(R[6], R[7], R[8], 0.0f);
     const uint32_t s = mesh_seg[i];
-    for (int k = 0; k < 3; ++k) { d.bmin[k] = seg_box[6 * s + k]; d.bmax[k] = seg_box[6 * s + 3 + k]; }
-    d.sfirst = seg_sfirst[s];
-    d.count = seg_count[s];
+    float sb[6];
+    for (int k = 0; k < 6; ++k) sb[k] = seg_box[6 * s + k];
+    const float delta = box_delta(sb);
+    const uint32_t count = seg_count[s];
     const int t = m.material.type;
-    d.cull = (t != RR_MATERIAL_GLASSY && t != RR_MATERIAL_INVISIBLE && t != RR_MATERIAL_ONESIDED) ? 1 : 0;  // :460-462
-    d.type = t;
-    d.skip = (m.scale <= RR_EPSILON || d.count == 0) ? 1 : 0;  // :448
-    d.material = i;
-    d.pad[0] = d.pad[1] = 0;
+    uint32_t flags = (uint32_t)t << RR_MF_TYPE_SHIFT;
+    if (t != RR_MATERIAL_GLASSY && t != RR_MATERIAL_INVISIBLE && t != RR_MATERIAL_ONESIDED) flags |= RR_MF_CULL;  // :460-462
+    if (m.scale <= RR_EPSILON || count == 0) flags |= RR_MF_SKIP;                                             // :448
+    if (pow2) flags |= RR_MF_POW2;
+    if (m.scale == 1.0f) flags |= RR_MF_UNIT;
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; ++k) { lo[k] = sb[k] - delta; hi[k] = sb[3 + k] + delta; }
+    d.bmin = make_float4(lo[0], lo[1], lo[2], __uint_as_float(seg_sfirst[s]));
+    d.bmax = make_float4(hi[0], hi[1], hi[2], __uint_as_float(count));
+    // world-space box of the (inflated) local root box: LocalToWorldHit of its 8 corners, then a generous slack
+    float wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (!(flags & RR_MF_SKIP)) {
+      for (int c = 0; c < 8; ++c) {
+        const float lx = ((c & 1) ? hi[0] : lo[0]) * m.scale, ly = ((c & 2) ? hi[1] : lo[1]) * m.scale,
+                    lz = ((c & 4) ? hi[2] : lo[2]) * m.scale;
+        const float w[3] = {R[0] * lx + R[1] * ly + R[2] * lz + px, R[3] * lx + R[4] * ly + R[5] * lz + py,
+                            R[6] * lx + R[7] * ly + R[8] * lz + pz};
+        for (int k = 0; k < 3; ++k) { wlo[k] = fminf(wlo[k], w[k]); whi[k] = fmaxf(whi[k], w[k]); }
+      }
+      float mabs = 0.0f;
+      for (int k = 0; k < 3; ++k) mabs = fmaxf(mabs, fmaxf(fabsf(wlo[k]), fabsf(whi[k])));
+      const float e = mabs * 1.220703125e-4f + 1.0e-6f;  // 2^-13 relative
+      for (int k = 0; k < 3; ++k) { wlo[k] -= e; whi[k] += e; }
+    }
+    d.wmin = make_float4(wlo[0], wlo[1], wlo[2], __uint_as_float(flags));
+    d.wmax = make_float4(whi[0], whi[1], whi[2], __int_as_float(i));
     out[i] = d;
   } else {
     src = &spheres[i - n_meshes].material;
+    if (i == n_meshes) {  // the sphere set as a world-space pseudo-mesh
+      DMesh d;
+      d.ri0 = make_float4(1, 0, 0, 0); d.ri1 = make_float4(0, 1, 0, 0); d.ri2 = make_float4(0, 0, 1, 0);
+      d.r0 = make_float4(1, 0, 0, 1); d.r1 = make_float4(0, 1, 0, 1); d.r2 = make_float4(0, 0, 1, 0);
+      float sb[6];
+      for (int k = 0; k < 6; ++k) sb[k] = sph_seg_box[k];
+      const float delta = box_delta(sb);
+      d.bmin = make_float4(sb[0] - delta, sb[1] - delta, sb[2] - delta, __uint_as_float(sph_node_base));
+      d.bmax = make_float4(sb[3] + delta, sb[4] + delta, sb[5] + delta, __uint_as_float((uint32_t)n_spheres));
+      d.wmin = make_float4(d.bmin.x, d.bmin.y, d.bmin.z, __uint_as_float(RR_MF_SPHERES | RR_MF_UNIT | RR_MF_POW2));
+      d.wmax = make_float4(d.bmax.x, d.bmax.y, d.bmax.z, __int_as_float(n_meshes));
+      out[n_meshes] = d;
+    }
   }
   DMaterial mm;
   mm.type = src->type;
@@ -128,8 +171,9 @@ static void free_scene(Device& d) {
   cudaSetDevice(d.ordinal);
   cudaFree(d.tris); cudaFree(d.spheres); cudaFree(d.tri_box); cudaFree(d.sph_box);
   cudaFree(d.tri_geom); cudaFree(d.tri_nrm); cudaFree(d.sph_geom); cudaFree(d.meshes); cudaFree(d.materials);
+  cudaFree(d.nodes);
   d.tris = nullptr; d.spheres = nullptr; d.tri_box = nullptr; d.sph_box = nullptr;
-  d.tri_geom = d.tri_nrm = d.sph_geom = nullptr; d.meshes = nullptr; d.materials = nullptr;
+  d.tri_geom = d.tri_nrm = d.sph_geom = nullptr; d.meshes = nullptr; d.materials = nullptr; d.nodes = nullptr;
   lbvh_free(d.tb);
   lbvh_free(d.sb);
 }
@@ -175,22 +219,25 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   if (n_spheres) RR_CUDA(cudaMemcpyAsync(d.spheres, spheres, n_spheres * sizeof(rr_sphere), cudaMemcpyHostToDevice, st));
   RR_CUDA(cudaEventRecord(d.ev0, st));
   RR_CUDA(launch_tri_boxes(d.tris, n_tris, d.tri_box, st));
-  RR_CUDA(lbvh_build(d.tb, d.tri_box, n_tris, plan.first.data(), plan.count.data(), (uint32_t)plan.first.size(), st));
+  RR_CUDA(lbvh_build(d.tb, d.tri_box, n_tris, plan.first.data(), plan.count.data(), (uint32_t)plan.first.size(), 0, st));
   RR_CUDA(cudaMalloc(&d.tri_geom, std::max<uint64_t>(d.tb.n, 1) * 48));
   RR_CUDA(cudaMalloc(&d.tri_nrm, std::max<uint64_t>(d.tb.n, 1) * 48));
   RR_CUDA(launch_pack_tris(d.tris, d.tb.order, d.tb.n, d.tri_geom, d.tri_nrm, st));
   RR_CUDA(launch_sphere_boxes(d.spheres, n_spheres, d.sph_box, st));
   uint32_t sf = 0, sc = (uint32_t)n_spheres;
-  RR_CUDA(lbvh_build(d.sb, d.sph_box, n_spheres, &sf, &sc, n_spheres ? 1u : 0u, st));
+  RR_CUDA(lbvh_build(d.sb, d.sph_box, n_spheres, &sf, &sc, n_spheres ? 1u : 0u, (int32_t)d.tb.n, st));
   RR_CUDA(cudaMalloc(&d.sph_geom, std::max<size_t>(n_spheres, 1) * 16));
   RR_CUDA(launch_pack_spheres(d.spheres, d.sb.order, d.sb.n, d.sph_geom, st));
-  if (n_spheres) RR_CUDA(cudaMemcpyAsync(d.sph_bounds, d.sb.seg_box, 24, cudaMemcpyDeviceToHost, st));
+  // one node array: triangle hierarchies at [0, tb.n), the sphere hierarchy behind them
+  RR_CUDA(cudaMalloc(&d.nodes, std::max<uint64_t>(d.tb.n + d.sb.n, 1) * 64));
+  if (d.tb.n) RR_CUDA(cudaMemcpyAsync(d.nodes, d.tb.nodes, d.tb.n * 64, cudaMemcpyDeviceToDevice, st));
+  if (d.sb.n) RR_CUDA(cudaMemcpyAsync(d.nodes + 4 * d.tb.n, d.sb.nodes, d.sb.n * 64, cudaMemcpyDeviceToDevice, st));
   // mesh + material tables
   rr_mesh* d_meshes_in = nullptr;
   uint32_t* d_mesh_seg = nullptr;
   RR_CUDA(cudaMalloc(&d_meshes_in, std::max<size_t>(n_meshes, 1) * sizeof(rr_mesh)));
   RR_CUDA(cudaMalloc(&d_mesh_seg, std::max<size_t>(n_meshes, 1) * 4));
-  RR_CUDA(cudaMalloc(&d.meshes, std::max<size_t>(n_meshes, 1) * sizeof(DMesh)));
+  RR_CUDA(cudaMalloc(&d.meshes, (n_meshes + 1) * sizeof(DMesh)));
   RR_CUDA(cudaMalloc(&d.materials, std::max<size_t>(n_meshes + n_spheres, 1) * sizeof(DMaterial)));
   if (n_meshes) {
     RR_CUDA(cudaMemcpyAsync(d_meshes_in, meshes, n_meshes * sizeof(rr_mesh), cudaMemcpyHostToDevice, st));
@@ -199,7 +246,8 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   if (n_meshes + n_spheres) {
     const int n = (int)(n_meshes + n_spheres);
     k_prepare_meshes<<<(n + 127) / 128, 128, 0, st>>>(d_meshes_in, d_mesh_seg, (int)n_meshes, d.tb.seg_box, d.tb.seg_sfirst,
-                                                      d.tb.seg_count, d.spheres, (int)n_spheres, d.meshes, d.materials);
+                                                      d.tb.seg_count, d.spheres, (int)n_spheres, d.sb.seg_box, (uint32_t)d.tb.n, d.meshes,
+                                                      d.materials);
     RR_CUDA(cudaGetLastError());
   }
   RR_CUDA(cudaEventRecord(d.ev1, st));
@@ -207,6 +255,8 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   RR_CUDA(cudaEventElapsedTime(&d.build_ms, d.ev0, d.ev1));
   cudaFree(d_meshes_in);
   cudaFree(d_mesh_seg);
+  cudaFree(d.tb.nodes); d.tb.nodes = nullptr;  // copied into d.nodes
+  cudaFree(d.sb.nodes); d.sb.nodes = nullptr;
   if (d.tb.max_depth > RR_STACK || d.sb.max_depth > RR_STACK)
     return fail(RR_ERR_BVH_DEPTH, "LBVH depth " + std::to_string(std::max(d.tb.max_depth, d.sb.max_depth)) +
                                       " exceeds the traversal stack (" + std::to_string(RR_STACK) + ")");
@@ -238,14 +288,14 @@ static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam
   p.meshes = d.meshes;
   p.n_meshes = (int32_t)ctx->n_meshes;
   p.materials = d.materials;
-  p.tri_nodes = d.tb.nodes;
+  p.nodes = d.nodes;
   p.tri_geom = d.tri_geom;
   p.tri_nrm = d.tri_nrm;
   p.n_spheres = (int32_t)ctx->n_spheres;
-  p.sph_nodes = d.sb.nodes;
+  p.last_mesh = (int32_t)ctx->n_meshes - 1 + (ctx->n_spheres ? 1 : 0);
   p.sph_geom = d.sph_geom;
   p.sph_order = d.sb.order;
-  for (int k = 0; k < 3; ++k) { p.sph_bmin[k] = d.sph_bounds[k]; p.sph_bmax[k] = d.sph_bounds[3 + k]; }
+  p.tune = ctx->tune;
   for (int k = 0; k < 3; ++k) p.cam.pos[k] = cam->position.s[k];
   p.cam.pitch = cam->pitch; p.cam.yaw = cam->yaw; p.cam.roll = cam->roll; p.cam.fov = cam->fov; p.cam.aspect = cam->aspectRatio;
   p.width = W; p.height = H; p.spp = spp; p.max_bounces = bounces; p.frame_index = frame_index;
@@ -280,6 +330,7 @@ static void read_stats(const Counters& c, uint64_t samples, float ms, float buil
   out->tiles = c.tiles;
   out->render_ms = ms;
   out->build_ms = build_ms;
+  for (int k = 0; k < 5; ++k) { out->phase_runs[k] = c.phase_runs[k]; out->phase_lanes[k] = c.phase_lanes[k]; }
 }
 
 // Renders one frame on all devices of the context.  Device 0 owns the queue and
@@ -338,6 +389,7 @@ static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t 
     RR_CUDA(cudaMemcpy(&c, d.counters, sizeof(c), cudaMemcpyDeviceToHost));
     total.rays += c.rays; total.rays_reused += c.rays_reused; total.box_tests += c.box_tests;
     total.tri_tests += c.tri_tests; total.sphere_tests += c.sphere_tests; total.tiles += c.tiles;
+    for (int q = 0; q < 5; ++q) { total.phase_runs[q] += c.phase_runs[q]; total.phase_lanes[q] += c.phase_lanes[q]; }
   }
   read_stats(total, (uint64_t)W * H * spp, ms_max, d0.build_ms, stats_out);
   return RR_OK;
@@ -365,7 +417,7 @@ const char* rr_error_string(int status) {
   }
 }
 const char* rr_last_error(void) { return g_last_error.c_str(); }
-int rr_version(void) { return 100; }
+int rr_version(void) { return 200; }
 
 int rr_device_count(int* out) {
   if (!out) return fail(RR_ERR_INVALID_ARGUMENT, "null output");
@@ -396,6 +448,7 @@ int rr_create(const int* cuda_ordinals, int n, rr_ctx** out) {
   int def = 0;
   if (!cuda_ordinals || n <= 0) { cuda_ordinals = &def; n = 1; }
   rr_ctx* ctx = new rr_ctx();
+  default_tuning(ctx->tune);
   ctx->dev.resize(n);
   for (int k = 0; k < n; ++k) {
     Device& d = ctx->dev[k];
@@ -513,6 +566,17 @@ int rr_render(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height
   return rr_render_ex(ctx, cam, width, height, spp, max_bounces, frame_index, tile_size, rgba_out, nullptr, nullptr, 0);
 }
 
+int rr_set_tuning(rr_ctx* ctx, const uint32_t* values, size_t n) {
+  if (!ctx) return fail(RR_ERR_INVALID_ARGUMENT, "null context");
+  if (!values) { default_tuning(ctx->tune); return RR_OK; }
+  uint32_t* dst[8] = {&ctx->tune.weight[0], &ctx->tune.weight[1], &ctx->tune.weight[2], &ctx->tune.weight[3],
+                      &ctx->tune.weight[4], &ctx->tune.trav_keep, &ctx->tune.speculate, &ctx->tune.ctas_per_sm};
+  for (size_t k = 0; k < n && k < 8; ++k) *dst[k] = values[k];
+  if (ctx->tune.trav_keep == 0) ctx->tune.trav_keep = 1;
+  for (int k = 0; k < 5; ++k) if (ctx->tune.weight[k] == 0) ctx->tune.weight[k] = 1;
+  return RR_OK;
+}
+
 int rr_render_device(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
                      uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, rr_stats* stats_out) {
   return render_frame(ctx, cam, width, height, spp, max_bounces, frame_index, tile_size, false, false, 0, 0, 1, stats_out);
@@ -543,7 +607,9 @@ int rr_primary_hits(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t 
   RenderParams p;
   fill_params(ctx, d, cam, width, height, 1, 1, 0, 0, p);
   p.hit_mesh = dm; p.hit_prim = dp; p.hit_dst = dd;
-  cudaError_t e = launch_primary(p, d.stream);
+  cudaError_t e = cudaMemsetAsync(d.queue, 0, sizeof(unsigned long long), d.stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d.counters, 0, sizeof(Counters), d.stream);
+  if (e == cudaSuccess) e = launch_primary(p, d.sm_count, d.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
   if (e == cudaSuccess && mesh_out) e = cudaMemcpy(mesh_out, dm, n * 4, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && prim_out) e = cudaMemcpy(prim_out, dp, n * 4, cudaMemcpyDeviceToHost);

@@ -36,26 +36,26 @@ struct Lbvh {
   uint32_t* seg_count = nullptr;  // [n_segs]
   uint32_t* seg_sfirst = nullptr; // [n_segs] first slot
   // traversal arrays
-  float4* nodes = nullptr;     // [n*4] per inner node: child boxes + refs
+  float4* nodes = nullptr;     // [n*4] per inner node: delta-inflated child boxes + refs
   uint32_t max_depth = 0;
 };
 
-// Per-mesh record read by the kernel (all floats/ints, 16-byte multiples).
+// Per-mesh record read by the kernel: ten float4 (LDG.128 each).  When the scene has spheres one
+// pseudo-mesh is appended at index n_meshes (world space, identity transform, RR_MF_SPHERES).
 struct DMesh {
-  float Rinv[9];  // rows of transpose(makeRotation)   reference src/Trace.cl:452-454
-  float R[9];     // rows of makeRotation
-  float pos[3];
-  float scale;
-  float bmin[3];  // local-space root box
-  float bmax[3];
-  uint32_t sfirst;  // first slot / inner-node base
-  uint32_t count;   // triangles
-  int32_t cull;     // cullBackface (reference src/Trace.cl:460-462)
-  int32_t type;     // material type
-  int32_t skip;     // scale <= EPSILON (reference src/Trace.cl:448)
-  int32_t material; // index into the material table
-  int32_t pad[2];
+  float4 ri0, ri1, ri2;  // rows of transpose(makeRotation) (reference src/Trace.cl:452-454); .w = pos.x / pos.y / pos.z
+  float4 r0, r1, r2;     // rows of makeRotation; r0.w = scale, r1.w = 1/scale (exact, valid with RR_MF_POW2)
+  float4 bmin;           // local-space root box, delta-inflated; .w = bits(first slot / inner-node base)
+  float4 bmax;           //                                     ; .w = bits(primitive count)
+  float4 wmin;           // world-space box (conservative);       .w = bits(flags)
+  float4 wmax;           //                                     ; .w = bits(material index)
 };
+#define RR_MF_SKIP 1u      // scale <= EPSILON (reference src/Trace.cl:448) or no primitives
+#define RR_MF_CULL 2u      // cullBackface (reference src/Trace.cl:460-462)
+#define RR_MF_POW2 4u      // scale is a power of two: x / scale == x * (1/scale) bit for bit
+#define RR_MF_UNIT 8u      // scale == 1: the division is the identity
+#define RR_MF_SPHERES 16u  // the sphere set (extension)
+#define RR_MF_TYPE_SHIFT 8
 
 struct DMaterial {
   int32_t type;
@@ -75,6 +75,15 @@ struct DCamera {
 
 struct Counters {
   unsigned long long rays, rays_reused, box_tests, tri_tests, sphere_tests, tiles;
+  unsigned long long phase_runs[5], phase_lanes[5];  // scheduler statistics (instrumented kernel only)
+};
+
+// Warp scheduler knobs of k_render.  Phases: 0 pixel, 1 shade, 2 setup, 3 traverse, 4 leaf.
+struct Tuning {
+  uint32_t weight[5];   // a phase runs when weight * ready lanes is the largest
+  uint32_t trav_keep;   // the traversal loop keeps stepping while at least this many lanes can step
+  uint32_t speculate;   // 1: a lane with a postponed leaf keeps traversing
+  uint32_t ctas_per_sm; // persistent CTAs per SM (0 = default)
 };
 
 // Everything a render kernel needs (passed by value).
@@ -83,15 +92,15 @@ struct RenderParams {
   const DMesh* meshes;
   int32_t n_meshes;
   const DMaterial* materials;
-  const float4* tri_nodes;   // 4 x float4 per inner node
+  const float4* nodes;       // 4 x float4 per inner node: triangle hierarchies, then the sphere hierarchy
   const float4* tri_geom;    // 3 x float4 per slot: (A, primId) (B-A) (C-A)
   const float4* tri_nrm;     // 3 x float4 per slot: nA nB nC
   // spheres (one segment, world space)
   int32_t n_spheres;
-  const float4* sph_nodes;
+  int32_t last_mesh;         // n_meshes - 1, or n_meshes when the sphere pseudo-mesh exists
   const float4* sph_geom;    // (center, radius) per slot
   const uint32_t* sph_order; // slot -> sphere index
-  float sph_bmin[3], sph_bmax[3];
+  Tuning tune;
   // frame
   DCamera cam;
   uint32_t width, height, spp, max_bounces;
@@ -110,8 +119,20 @@ struct RenderParams {
 // ---- builder (rr_lbvh.cu) -------------------------------------------------
 // boxes: prim boxes [n_total*6] on the device, segments on the HOST (first,count per segment,
 // sorted by first, non-overlapping).  Builds everything in `out` on `stream`.
+// ref_offset is added to the inner-node references of the packed traversal nodes (the sphere
+// hierarchy is stored behind the triangle hierarchies in one array).
 cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, const uint32_t* h_seg_first,
-                       const uint32_t* h_seg_count, uint32_t n_segs, cudaStream_t stream);
+                       const uint32_t* h_seg_count, uint32_t n_segs, int32_t ref_offset, cudaStream_t stream);
+// Conservative slack added to every box a ray is tested against: 2^-18 of the largest |coordinate|
+// of the segment box (about 60 ulp), so that the closest hit does not depend on the traversal order.
+__host__ __device__ inline float box_delta(const float* seg_box6) {
+  float m = 0.0f;
+  for (int k = 0; k < 6; ++k) {
+    float a = seg_box6[k] < 0.0f ? -seg_box6[k] : seg_box6[k];
+    if (a > m && a < 3.0e38f) m = a;
+  }
+  return m * 3.814697265625e-06f;
+}
 void lbvh_free(Lbvh& b);
 
 cudaError_t launch_tri_boxes(const rr_triangle* d_tris, uint64_t n, float* d_box, cudaStream_t s);
@@ -123,7 +144,8 @@ cudaError_t launch_pack_spheres(const rr_sphere* d_sph, const uint32_t* d_order,
 
 // ---- render (rr_render.cu) --------------------------------------------------
 cudaError_t launch_render(const RenderParams& p, bool count_tests, int sm_count, cudaStream_t s);
-cudaError_t launch_primary(const RenderParams& p, cudaStream_t s);
+cudaError_t launch_primary(const RenderParams& p, int sm_count, cudaStream_t s);
+void default_tuning(Tuning& t);
 cudaError_t launch_math_probe(int fn, const float* x, const float* y, float* out, uint64_t n, cudaStream_t s);
 cudaError_t launch_rng_probe(uint32_t pixel, int32_t frame, uint32_t* out_u32, float* out_f32, cudaStream_t s);
 

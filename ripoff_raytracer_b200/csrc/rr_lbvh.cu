@@ -401,11 +401,14 @@ __global__ void k_refit(uint64_t n, const uint32_t* __restrict__ order, const fl
 
 // Traversal node: boxes of both children + child refs, 64 bytes.
 //   q0 = (A.min.xyz, A.max.x) q1 = (A.max.yz, B.min.xy) q2 = (B.min.z, B.max.xyz) q3 = (refA, refB, -, -)
+// The boxes are inflated by the segment's box_delta() so that culling is conservative (the closest
+// hit then does not depend on the order in which a traversal visits the nodes); inner references
+// get ref_offset added (position of this hierarchy inside the combined node array).
 __global__ void k_pack_nodes(uint64_t n, const uint32_t* __restrict__ order, const float* __restrict__ prim_box,
                              const int32_t* __restrict__ left, const int32_t* __restrict__ right,
-                             const int32_t* __restrict__ parent, const int32_t* __restrict__ leaf_parent,
                              const float* __restrict__ bounds, const unsigned int* __restrict__ flags,
-                             float4* __restrict__ nodes) {
+                             const uint32_t* __restrict__ seg_sfirst, int n_segs, const float* __restrict__ seg_box,
+                             int32_t ref_offset, float4* __restrict__ nodes) {
   uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n) return;
   float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
@@ -414,6 +417,15 @@ __global__ void k_pack_nodes(uint64_t n, const uint32_t* __restrict__ order, con
     int32_t L = left[g], R = right[g];
     load_ref_box(L, order, prim_box, bounds, a);
     load_ref_box(R, order, prim_box, bounds, c);
+    const int s = seg_search(seg_sfirst, n_segs, (uint32_t)g);
+    float sb[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sb[k] = __ldg(seg_box + 6 * s + k);
+    const float d = box_delta(sb);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { a[k] -= d; c[k] -= d; a[3 + k] += d; c[3 + k] += d; }
+    if (L >= 0) L += ref_offset;
+    if (R >= 0) R += ref_offset;
     q0 = make_float4(a[0], a[1], a[2], a[3]);
     q1 = make_float4(a[4], a[5], c[0], c[1]);
     q2 = make_float4(c[2], c[3], c[4], c[5]);
@@ -484,7 +496,7 @@ static cudaError_t dalloc(T** p, uint64_t count) {
 }
 
 cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, const uint32_t* h_seg_first,
-                       const uint32_t* h_seg_count, uint32_t n_segs, cudaStream_t st) {
+                       const uint32_t* h_seg_count, uint32_t n_segs, int32_t ref_offset, cudaStream_t st) {
   lbvh_free(out);
   out.n_segs = n_segs;
   uint64_t n = 0;
@@ -575,8 +587,8 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
                                                out.parent, leaf_parent);
     k_refit<<<grid_for(n, 128), 128, 0, st>>>(n, out.order, d_prim_box, out.left, out.right, out.parent, leaf_parent,
                                               out.bounds, flags, d_depth);
-    k_pack_nodes<<<grid_for(n, 128), 128, 0, st>>>(n, out.order, d_prim_box, out.left, out.right, out.parent, leaf_parent,
-                                                   out.bounds, flags, out.nodes);
+    k_pack_nodes<<<grid_for(n, 128), 128, 0, st>>>(n, out.order, d_prim_box, out.left, out.right, out.bounds, flags,
+                                                   out.seg_sfirst, (int)n_segs, out.seg_box, ref_offset, out.nodes);
     RR_TRY(cudaGetLastError());
   }
   RR_TRY(cudaMemcpyAsync(&out.max_depth, d_depth, 4, cudaMemcpyDeviceToHost, st));

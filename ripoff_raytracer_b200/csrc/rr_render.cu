@@ -1,20 +1,31 @@
-// rr_render.cu -- the per-pixel path-tracing kernels (sm_100a).
+// rr_render.cu -- the per-pixel path-tracing kernel (sm_100a).
 //
 // B200-native replacement of the reference's `raytrace` OpenCL kernel
 // (src/Trace.cl:623-653) and everything it calls.  Each device function names
-// the reference lines whose arithmetic it reproduces; the arithmetic is kept in
-// the reference's operation order and this file is compiled with -fmad=false
-// so the result is bit-identical to the CPU oracle.
+// the reference lines whose arithmetic it reproduces.  Everything that decides
+// a RESULT (triangle test, instance transforms, shading, RNG, tonemap) is kept
+// in the reference's operation order and this file is compiled with
+// -fmad=false, so those results are bit-identical to the CPU oracle
+// (DESIGN.md section 3).  Ray/box tests only CULL: they run in FMA form with an
+// approximate reciprocal against delta-inflated boxes (rr_internal.h box_delta),
+// which keeps them conservative, so the closest hit is the same whatever order
+// the hierarchy is walked in.
 //
-// Structure:
+// Structure -- a warp-synchronous state machine:
 //   * persistent warps pop 8x4-pixel tiles from one 64-bit atomic counter (the
 //     reference's mutex-guarded std::queue, src/image.hpp:286-314); a lane that
-//     finishes its pixel takes the next pixel of the warp's tile at once;
+//     finishes its pixel takes the next pixel of the warp's tile;
 //   * per pixel the spp samples run serially in the lane because the RNG state
 //     is carried across samples (src/Trace.cl:632,639-642);
-//   * closest hit = loop over meshes in mesh-local space (src/Trace.cl:444-482)
-//     with our LBVH instead of the reference's SAH tree: one 64-byte node fetch
-//     (4 x LDG.128) brings both child boxes and both child references.
+//   * every lane is in one of five phases (pixel, shade, mesh setup, node step,
+//     leaf test); each round the warp votes and runs the phase with the most
+//     ready lanes, so the hot node-step loop executes with most lanes active
+//     instead of each lane walking its own ray while 31 others wait;
+//   * a node step is one 64-byte fetch (4 x LDG.128: both child boxes and both
+//     child references) and two slab tests; a lane may postpone one leaf and
+//     keep walking (speculative traversal);
+//   * the per-path colour state lives in shared memory so that the traversal
+//     fits 64 registers and 32 warps stay resident per SM.
 #include <math.h>
 
 #include "rr_internal.h"
@@ -88,234 +99,39 @@ __device__ __forceinline__ V3 random_direction(uint32_t& state) {
   return v;
 }
 
+
 // ---- intersection ------------------------------------------------------------
-struct Ray {
-  V3 o, d, inv;
-};
-
-// src/Trace.cl:259-274
-__device__ __forceinline__ bool ray_box(const Ray& r, float minx, float miny, float minz, float maxx, float maxy,
-                                        float maxz, float& dist) {
-  float t0x = (minx - r.o.x) * r.inv.x, t0y = (miny - r.o.y) * r.inv.y, t0z = (minz - r.o.z) * r.inv.z;
-  float t1x = (maxx - r.o.x) * r.inv.x, t1y = (maxy - r.o.y) * r.inv.y, t1z = (maxz - r.o.z) * r.inv.z;
-  float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
-  float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-  dist = tmin;
-  return tmax >= fmaxf(tmin, 0.0f);
+// Culling slab test (replaces src/Trace.cl:259-274 for traversal decisions): t = b*inv - o*inv in one
+// FFMA (finite reciprocal, see rcp_approx).
+// 1/x for the slab tests only.  |x| is clamped to 1e-18 so that the reciprocal stays finite: with an
+// infinite reciprocal b*inv - o*inv is inf - inf = NaN on one plane only and the slab would reject
+// rays that run inside it.
+__device__ __forceinline__ float rcp_approx(float x) {
+  const float xs = fabsf(x) < 1.0e-18f ? copysignf(1.0e-18f, x) : x;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(xs));
+  return r;
+}
+__device__ __forceinline__ bool box_cull(float lox, float loy, float loz, float hix, float hiy, float hiz, const V3& inv,
+                                         const V3& noi, float tbest, float& tn) {
+  const float t0x = __fmaf_rn(lox, inv.x, noi.x), t1x = __fmaf_rn(hix, inv.x, noi.x);
+  const float t0y = __fmaf_rn(loy, inv.y, noi.y), t1y = __fmaf_rn(hiy, inv.y, noi.y);
+  const float t0z = __fmaf_rn(loz, inv.z, noi.z), t1z = __fmaf_rn(hiz, inv.z, noi.z);
+  tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+  const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+  return tf >= fmaxf(tn, 0.0f) && tn <= tbest;
 }
 
-struct Hit {  // closest hit inside one mesh (local space) or the sphere set
-  float t;
-  int32_t prim;  // uploaded index; INT_MAX while empty
-  V3 n;
-  bool back;
-  bool did;
-};
+constexpr int32_t REF_END = (int32_t)0x80000000;  // traversal finished / "pop the stack"
+constexpr int32_t NO_PRIM = 0x7fffffff;
 
-// src/Trace.cl:276-317 with the distance test hoisted before the normal (same
-// accept set) and a total order (t, prim) instead of first-found-wins.
-__device__ __forceinline__ void ray_triangle(const Ray& ray, const float4* __restrict__ geom,
-                                             const float4* __restrict__ nrm, uint32_t slot, bool cull, Hit& best) {
-  const float4 g0 = __ldg(geom + 3 * (size_t)slot), g1 = __ldg(geom + 3 * (size_t)slot + 1),
-               g2 = __ldg(geom + 3 * (size_t)slot + 2);
-  const V3 A = xyz(g0), edge1 = xyz(g1), edge2 = xyz(g2);
-  const V3 h = cross(ray.d, edge2);
-  const float a = dot(edge1, h);
-  if (fabsf(a) < RR_EPSILON) return;
-  const float f = 1.0f / a;
-  const V3 s = ray.o - A;
-  const float u = f * dot(s, h);
-  if (u < 0.0f || u > 1.0f) return;
-  const V3 q = cross(s, edge1);
-  const float v = f * dot(ray.d, q);
-  if (v < 0.0f || u + v > 1.0f) return;
-  const float t = f * dot(edge2, q);
-  if (t <= RR_EPSILON) return;
-  const int32_t prim = (int32_t)__float_as_uint(g0.w);
-  if (!(t < best.t || (t == best.t && best.did && prim < best.prim))) return;
-  const float4 n0 = __ldg(nrm + 3 * (size_t)slot), n1 = __ldg(nrm + 3 * (size_t)slot + 1),
-               n2 = __ldg(nrm + 3 * (size_t)slot + 2);
-  V3 n = normalize(xyz(n0) * (1.0f - u - v) + xyz(n1) * u + xyz(n2) * v);
-  bool back = false;
-  if (dot(ray.d, n) > RR_EPSILON) {
-    if (cull) return;
-    back = true;
-    n = -n;
-  }
-  best.did = true;
-  best.t = t;
-  best.prim = prim;
-  best.n = n;
-  best.back = back;
-}
-
-// EXTENSION (the reference kernel has no sphere primitive): semantics defined by oracle/rr_oracle.c ray_sphere.
-__device__ __forceinline__ void ray_sphere(const Ray& ray, float4 cr, int32_t prim, int32_t mtype, Hit& best) {
-  const V3 c = xyz(cr);
-  const float r = cr.w;
-  const V3 oc = ray.o - c;
-  const float b = dot(oc, ray.d);
-  const float cc = dot(oc, oc) - r * r;
-  const float disc = b * b - cc;
-  if (!(disc >= 0.0f)) return;
-  const float sq = sqrtf(disc);
-  float t = -b - sq;
-  bool back = false;
-  if (t <= RR_EPSILON) { t = -b + sq; back = true; }
-  if (t <= RR_EPSILON) return;
-  if (!(t < best.t || (t == best.t && best.did && prim < best.prim))) return;
-  const bool cull = (mtype != RR_MATERIAL_GLASSY && mtype != RR_MATERIAL_INVISIBLE && mtype != RR_MATERIAL_ONESIDED);
-  if (back && cull) return;
-  const V3 hp = ray.o + ray.d * t;
-  V3 n = (hp - c) / r;
-  if (back) n = -n;
-  best.did = true; best.t = t; best.prim = prim; best.n = n; best.back = back;
-}
-
-struct TraversalCounters {
-  unsigned box, tri, sph;
-};
-
-// LBVH traversal of one segment; replaces src/Trace.cl:319-397.  PRIM = 0 triangles, 1 spheres.
-template <int PRIM, bool COUNT>
-__device__ __forceinline__ void traverse(const RenderParams& p, const Ray& ray, const float4* __restrict__ nodes,
-                                         uint32_t sfirst, uint32_t count, bool cull, Hit& best, TraversalCounters& tc) {
-  auto leaf = [&](uint32_t slot) {
-    if (PRIM == 0) {
-      if (COUNT) tc.tri++;
-      ray_triangle(ray, p.tri_geom, p.tri_nrm, slot, cull, best);
-    } else {
-      if (COUNT) tc.sph++;
-      const uint32_t prim = __ldg(p.sph_order + slot);
-      const int32_t mtype = __ldg(&p.materials[p.n_meshes + prim].type);
-      ray_sphere(ray, __ldg(p.sph_geom + slot), (int32_t)prim, mtype, best);
-    }
-  };
-  if (count <= RR_DIRECT_MAX) {
-    for (uint32_t k = 0; k < count; ++k) leaf(sfirst + k);
-    return;
-  }
-  int32_t stackN[RR_STACK];
-  float stackD[RR_STACK];
-  int sp = 0;
-  int32_t cur = (int32_t)sfirst;
-  for (;;) {
-    const float4* nd = nodes + 4 * (size_t)cur;
-    const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
-    const int32_t L = __float_as_int(q3.x), R = __float_as_int(q3.y);
-    float dA, dB;
-    if (COUNT) tc.box += 2;
-    const bool hA = ray_box(ray, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, dA) && dA < best.t;
-    const bool hB = ray_box(ray, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, dB) && dB < best.t;
-    int32_t next = 0;
-    bool have = false;
-    if (hA && hB) {
-      int32_t far;
-      float dfar;
-      if (dA < dB) { next = L; far = R; dfar = dB; } else { next = R; far = L; dfar = dA; }
-      if (sp < RR_STACK) { stackN[sp] = far; stackD[sp] = dfar; sp++; }
-      have = true;
-    } else if (hA) { next = L; have = true; }
-    else if (hB) { next = R; have = true; }
-    for (;;) {
-      if (have) {
-        if (next >= 0) { cur = next; break; }
-        leaf((uint32_t)~next);
-        have = false;
-      }
-      bool found = false;
-      while (sp > 0) {
-        --sp;
-        if (stackD[sp] < best.t) { next = stackN[sp]; found = true; break; }
-      }
-      if (!found) return;
-      have = true;
-    }
-  }
-}
-
-struct SceneHit {
+struct SceneHit {  // HitInfo of src/Trace.cl:67-74 as the shade phase sees it
   bool did;
   float dst;
   V3 point, normal;
   bool back;
-  int32_t mesh;      // mesh index, n_meshes for a sphere
-  int32_t prim;      // uploaded primitive index
   int32_t material;  // index into the material table
 };
-
-// src/Trace.cl:434-485 (+ the sphere extension after the mesh loop).
-template <bool COUNT>
-__device__ __forceinline__ void scene_closest(const RenderParams& p, V3 origin, V3 dir, SceneHit& out, TraversalCounters& tc) {
-  out.did = false;
-  out.dst = INFINITY;
-  out.mesh = -1;
-  out.prim = -1;
-  out.material = 0;
-  for (int m = 0; m < p.n_meshes; ++m) {
-    const DMesh* M = p.meshes + m;
-    if (__ldg(&M->skip)) continue;
-    const float scale = __ldg(&M->scale);
-    const V3 pos = ld3(M->pos);
-    const V3 i0 = ld3(M->Rinv), i1 = ld3(M->Rinv + 3), i2 = ld3(M->Rinv + 6);
-    // WorldToLocalRay, src/Trace.cl:118-137
-    const V3 rel = origin - pos;
-    V3 lo = mk(dot(i0, rel), dot(i1, rel), dot(i2, rel));
-    V3 ld = mk(dot(i0, dir), dot(i1, dir), dot(i2, dir));
-    if (fabsf(scale) > RR_EPSILON) {
-      lo = lo / scale;
-      ld = ld / scale;
-    }
-    ld = normalize(ld);
-    Ray lr;
-    lr.o = lo;
-    lr.d = ld;
-    lr.inv = mk(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
-    Hit lh;
-    lh.did = false; lh.t = INFINITY; lh.prim = 0x7fffffff; lh.back = false; lh.n = mk(0, 0, 0);
-    float dRoot;
-    if (COUNT) tc.box++;
-    if (!ray_box(lr, __ldg(M->bmin), __ldg(M->bmin + 1), __ldg(M->bmin + 2), __ldg(M->bmax), __ldg(M->bmax + 1),
-                 __ldg(M->bmax + 2), dRoot))
-      continue;
-    const bool cull = __ldg(&M->cull) != 0;
-    traverse<0, COUNT>(p, lr, p.tri_nodes, __ldg(&M->sfirst), __ldg(&M->count), cull, lh, tc);
-    if (!lh.did) continue;
-    const int32_t type = __ldg(&M->type);
-    if (type == RR_MATERIAL_ONESIDED && lh.back) continue;
-    // LocalToWorldHit, src/Trace.cl:139-156
-    const V3 r0 = ld3(M->R), r1 = ld3(M->R + 3), r2 = ld3(M->R + 6);
-    const V3 lp = (lr.o + lr.d * lh.t) * scale;
-    const V3 wp = mk(dot(r0, lp), dot(r1, lp), dot(r2, lp)) + pos;
-    const V3 wn = normalize(mk(dot(r0, lh.n), dot(r1, lh.n), dot(r2, lh.n)));
-    const float wd = length(wp - origin);
-    if (wd < out.dst) {
-      out.did = true; out.dst = wd; out.point = wp; out.normal = wn; out.back = lh.back;
-      out.mesh = m; out.prim = lh.prim; out.material = __ldg(&M->material);
-    }
-  }
-  if (p.n_spheres > 0) {
-    Ray wr;
-    wr.o = origin;
-    wr.d = dir;
-    wr.inv = mk(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
-    float dRoot;
-    if (COUNT) tc.box++;
-    if (ray_box(wr, p.sph_bmin[0], p.sph_bmin[1], p.sph_bmin[2], p.sph_bmax[0], p.sph_bmax[1], p.sph_bmax[2], dRoot)) {
-      Hit sh;
-      sh.did = false; sh.t = INFINITY; sh.prim = 0x7fffffff; sh.back = false; sh.n = mk(0, 0, 0);
-      traverse<1, COUNT>(p, wr, p.sph_nodes, 0u, (uint32_t)p.n_spheres, false, sh, tc);
-      if (sh.did) {
-        const int32_t mat = p.n_meshes + sh.prim;
-        const int32_t type = __ldg(&p.materials[mat].type);
-        if (!(type == RR_MATERIAL_ONESIDED && sh.back) && sh.t < out.dst) {
-          out.did = true; out.dst = sh.t; out.point = origin + dir * sh.t; out.normal = sh.n; out.back = sh.back;
-          out.mesh = p.n_meshes; out.prim = sh.prim; out.material = mat;
-        }
-      }
-    }
-  }
-}
 
 // ---- shading -------------------------------------------------------------------
 __device__ __forceinline__ V3 lerp3(V3 a, V3 b, float t) { return a * (1.0f - t) + b * t; }               // :84
@@ -430,11 +246,11 @@ __device__ __forceinline__ uint32_t tonemap_rgba(V3 c) {
   return R | (G << 8) | (B << 16) | (255u << 24);
 }
 
+
 // ---- tile queue ----------------------------------------------------------------
 // Tiles are numbered row-major.  With a shared counter (possibly in a peer
 // GPU's memory, hence the system-scope atomic) every warp of every GPU pops the
-// next tile; with a static partition (queue == nullptr is not used: the local
-// counter is scaled by tile_stride) rank r renders tiles r, r+world, ...
+// next tile; with a static partition rank r renders tiles r, r+world, ...
 __device__ __forceinline__ bool pop_tile(const RenderParams& p, uint32_t& tile) {
   unsigned long long t = 0;
   if ((threadIdx.x & 31) == 0) t = atomicAdd_system(p.queue, 1ull);
@@ -444,86 +260,398 @@ __device__ __forceinline__ bool pop_tile(const RenderParams& p, uint32_t& tile) 
   return t < (unsigned long long)p.tiles_x * p.tiles_y;
 }
 
-constexpr int RENDER_THREADS = 256;
+constexpr int NT = 128;  // threads per CTA (warps are independent: no block-level barrier in the loop)
+enum { ST_IDLE = 0, ST_PIXEL = 1, ST_SHADE = 2, ST_SETUP = 3, ST_TRAV = 4 };
+enum { PH_PIXEL = 0, PH_SHADE = 1, PH_SETUP = 2, PH_TRAV = 3, PH_LEAF = 4 };
+// per-thread words kept in shared memory (word k of thread t at smem[k * NT + t]: conflict-free)
+enum { S_THR = 0, S_INC = 3, S_ACC = 6, S_BP = 9, S_BN = 12, S_LN = 15, S_WINV = 18, S_PD = 21, S_WORDS = 24 };
 
-template <bool COUNT>
-__global__ void __launch_bounds__(RENDER_THREADS, 2) k_render(const RenderParams p) {
+template <bool COUNT, bool PRIMARY>
+__global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
+  __shared__ float smem[S_WORDS * NT];
+#define SM(k) smem[(k) * NT + threadIdx.x]
+#define SM_ST3(k, v) do { SM(k) = (v).x; SM((k) + 1) = (v).y; SM((k) + 2) = (v).z; } while (0)
+#define SM_LD3(k) mk(SM(k), SM((k) + 1), SM((k) + 2))
   const unsigned lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
-  TraversalCounters tc = {0u, 0u, 0u};
-  unsigned long long n_rays = 0, n_tiles = 0;
   const V3 cam_pos = mk(p.cam.pos[0], p.cam.pos[1], p.cam.pos[2]);
+  // traversal stack (local memory; interleaved per lane by the hardware)
+  int32_t stackN[RR_STACK];
+  float stackD[RR_STACK];
   // warp-uniform tile state
   bool queue_empty = false;
-  uint32_t tile_x0 = 0, tile_y0 = 0, tile_w = 0, tile_h = 0, tile_next = 0, tile_pixels = 0;
+  uint32_t tile_x0 = 0, tile_y0 = 0, tile_w = 1, tile_next = 0, tile_pixels = 0;
   // lane state
+  int state = ST_PIXEL;
   int32_t pix = -1;
   uint32_t rng = 0, sample = 0, bounce = 0, passes = 0;
-  V3 pd = mk(0, 0, 1), origin = cam_pos, dir = pd, throughput = mk(1, 1, 1), incoming = mk(0, 0, 0), accum = mk(0, 0, 0);
+  V3 origin = cam_pos, dir = mk(0, 0, 1);
+  float best_dst = INFINITY;
+  int32_t best_mat = 0, best_mesh = -1, best_prim = -1;
+  bool best_back = false;
+  int m = -1;
+  uint32_t mflags = 0;
+  V3 lo = origin, ld = dir, linv = dir, lnoi = dir;
+  float lt = INFINITY;
+  int32_t lprim = NO_PRIM;
+  bool lback = false;
+  int32_t cur = REF_END;
+  int sp = 0;
+  uint32_t pend_slot = 0, pend_cnt = 0;
+  // statistics
+  unsigned long long n_rays = 0, n_tiles = 0;
+  unsigned c_box = 0, c_tri = 0, c_sph = 0;
+  unsigned ph_runs[5] = {0, 0, 0, 0, 0}, ph_lanes[5] = {0, 0, 0, 0, 0};
+
+  const uint32_t wP = p.tune.weight[PH_PIXEL], wH = p.tune.weight[PH_SHADE], wS = p.tune.weight[PH_SETUP],
+                 wT = p.tune.weight[PH_TRAV], wL = p.tune.weight[PH_LEAF];
+  const uint32_t trav_keep = p.tune.trav_keep;
+  const bool speculate = p.tune.speculate != 0;
+
+  // A new ray starts: reset the closest hit and the mesh cursor (src/Trace.cl:437-444).
+  auto begin_ray = [&]() {
+    best_dst = INFINITY; best_mat = 0; best_mesh = -1; best_prim = -1; best_back = false;
+    m = -1;
+    lprim = NO_PRIM;
+    SM(S_WINV) = rcp_approx(dir.x); SM(S_WINV + 1) = rcp_approx(dir.y); SM(S_WINV + 2) = rcp_approx(dir.z);
+    n_rays++;
+    state = ST_SETUP;
+  };
+  auto begin_path = [&]() {  // src/Trace.cl:488-491
+    bounce = 0; passes = 0;
+    origin = cam_pos;
+    dir = SM_LD3(S_PD);
+    SM(S_THR) = 1.0f; SM(S_THR + 1) = 1.0f; SM(S_THR + 2) = 1.0f;
+    SM(S_INC) = 0.0f; SM(S_INC + 1) = 0.0f; SM(S_INC + 2) = 0.0f;
+  };
+  // Pops the stack / postpones leaves until `cur` is an inner node, a leaf the lane must wait for, or REF_END.
+  auto resolve = [&](int32_t next) {
+    for (;;) {
+      if (next == REF_END) {
+        bool found = false;
+        while (sp > 0) {
+          --sp;
+          if (stackD[sp] <= lt) { next = stackN[sp]; found = true; break; }
+        }
+        if (!found) { cur = REF_END; break; }
+      }
+      if (next >= 0) { cur = next; break; }
+      if (pend_cnt == 0) { pend_slot = (uint32_t)~next; pend_cnt = 1; next = REF_END; continue; }
+      cur = next;  // a second leaf while one is postponed: wait for the leaf phase
+      break;
+    }
+    if (cur == REF_END && pend_cnt == 0) state = ST_SETUP;
+  };
 
   for (;;) {
-    // ---- hand a pixel to every idle lane ----
-    bool need = pix < 0;
-    while (__any_sync(full, need)) {
-      if (tile_next >= tile_pixels) {
-        if (queue_empty) break;
-        uint32_t tile;
-        if (!pop_tile(p, tile)) { queue_empty = true; break; }
-        n_tiles++;
-        tile_x0 = (tile % p.tiles_x) * p.tile_w;
-        tile_y0 = (tile / p.tiles_x) * p.tile_h;
-        tile_w = min(p.tile_w, p.width - tile_x0);
-        tile_h = min(p.tile_h, p.height - tile_y0);
-        tile_pixels = tile_w * tile_h;
-        tile_next = 0;
-      }
-      const unsigned m = __ballot_sync(full, need);
-      const unsigned rank = __popc(m & ((1u << lane) - 1u));
-      const uint32_t k = tile_next + rank;
-      if (need && k < tile_pixels) {
-        const uint32_t x = tile_x0 + k % tile_w, y = tile_y0 + k / tile_w;
-        pix = (int32_t)(y * p.width + x);
-        rng = make_seed((uint32_t)pix, p.frame_index, 0u);  // src/Trace.cl:631-632
-        pd = primary_dir(p.cam, x, y, p.width, p.height);   // once per pixel, :634-636
-        accum = mk(0, 0, 0);
-        sample = 0; bounce = 0; passes = 0;
-        origin = cam_pos; dir = pd; throughput = mk(1, 1, 1); incoming = mk(0, 0, 0);
-        need = false;
-      }
-      tile_next += __popc(m);
+    // ---- vote: which phase has the most ready lanes ----
+    const bool inT = state == ST_TRAV;
+    const unsigned bT = __ballot_sync(full, inT && cur >= 0 && (speculate || pend_cnt == 0));
+    const unsigned bL = __ballot_sync(full, inT && pend_cnt > 0);
+    const unsigned bS = __ballot_sync(full, state == ST_SETUP);
+    const unsigned bH = __ballot_sync(full, state == ST_SHADE);
+    const unsigned bP = queue_empty && tile_next >= tile_pixels ? 0u : __ballot_sync(full, state == ST_PIXEL);
+    if (!(bT | bL | bS | bH | bP)) break;
+    const uint32_t sT = __popc(bT) * wT, sL = __popc(bL) * wL, sS = __popc(bS) * wS, sH = __popc(bH) * wH,
+                   sP = __popc(bP) * wP;
+    int phase = PH_TRAV;
+    uint32_t best = sT;
+    if (sL > best) { best = sL; phase = PH_LEAF; }
+    if (sS > best) { best = sS; phase = PH_SETUP; }
+    if (sH > best) { best = sH; phase = PH_SHADE; }
+    if (sP > best) { best = sP; phase = PH_PIXEL; }
+    if (COUNT) {
+      const unsigned bb = phase == PH_TRAV ? bT : phase == PH_LEAF ? bL : phase == PH_SETUP ? bS : phase == PH_SHADE ? bH : bP;
+      if (phase != PH_TRAV) { ph_runs[phase]++; ph_lanes[phase] += __popc(bb); }
     }
-    if (__all_sync(full, pix < 0)) break;
 
-    if (pix >= 0) {
-      bool alive = bounce < p.max_bounces && sample < p.spp;
-      if (alive) {
-        SceneHit hit;
-        n_rays++;
-        scene_closest<COUNT>(p, origin, dir, hit, tc);
-        alive = shade(p, hit, origin, dir, throughput, incoming, bounce, passes, rng);
-        alive = alive && bounce < p.max_bounces;
-      }
-      if (!alive) {  // path finished: src/Trace.cl:639-642
-        if (sample < p.spp) {
-          accum = accum + incoming;
-          sample++;
+    if (phase == PH_TRAV) {
+      // ================= node steps =================
+      unsigned active = bT;
+      do {
+        if (COUNT) { ph_runs[PH_TRAV]++; ph_lanes[PH_TRAV] += __popc(active); }
+        if (state == ST_TRAV && cur >= 0 && (speculate || pend_cnt == 0)) {
+          const float4* nd = p.nodes + 4 * (size_t)cur;
+          const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
+          if (COUNT) c_box += 2;
+          float tA, tB;
+          const bool hA = box_cull(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, linv, lnoi, lt, tA);
+          const bool hB = box_cull(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, linv, lnoi, lt, tB);
+          const int32_t L = __float_as_int(q3.x), R = __float_as_int(q3.y);
+          int32_t next = REF_END;
+          if (hA && hB) {
+            const bool aNear = tA < tB;
+            next = aNear ? L : R;
+            if (sp < RR_STACK) { stackN[sp] = aNear ? R : L; stackD[sp] = aNear ? tB : tA; sp++; }
+          } else if (hA) next = L;
+          else if (hB) next = R;
+          resolve(next);
         }
-        if (sample >= p.spp) {
-          const V3 c = accum / (float)p.spp;
-          reinterpret_cast<uint32_t*>(p.frame)[pix] = tonemap_rgba(c);
-          if (p.radiance) {
-            p.radiance[3 * (size_t)pix] = c.x;
-            p.radiance[3 * (size_t)pix + 1] = c.y;
-            p.radiance[3 * (size_t)pix + 2] = c.z;
+        active = __ballot_sync(full, state == ST_TRAV && cur >= 0 && (speculate || pend_cnt == 0));
+      } while ((uint32_t)__popc(active) >= trav_keep);
+    } else if (phase == PH_LEAF) {
+      // ================= leaf tests =================
+      if (state == ST_TRAV && pend_cnt > 0) {
+        const uint32_t slot = pend_slot;
+        pend_slot++;
+        pend_cnt--;
+        if (mflags & RR_MF_SPHERES) {
+          // EXTENSION (the reference kernel has no sphere primitive): semantics of oracle/rr_oracle.c ray_sphere
+          if (COUNT) c_sph++;
+          const float4 cr = __ldg(p.sph_geom + slot);
+          const int32_t prim = (int32_t)__ldg(p.sph_order + slot);
+          const V3 c = xyz(cr);
+          const float r = cr.w;
+          const V3 oc = lo - c;
+          const float b = dot(oc, ld);
+          const float cc = dot(oc, oc) - r * r;
+          const float disc = b * b - cc;
+          if (disc >= 0.0f) {
+            const float sq = sqrtf(disc);
+            float t = -b - sq;
+            bool back = false;
+            if (t <= RR_EPSILON) { t = -b + sq; back = true; }
+            if (t > RR_EPSILON && (t < lt || (t == lt && lprim != NO_PRIM && prim < lprim))) {
+              const int32_t mtype = __ldg(&p.materials[p.n_meshes + prim].type);
+              const bool cull = (mtype != RR_MATERIAL_GLASSY && mtype != RR_MATERIAL_INVISIBLE && mtype != RR_MATERIAL_ONESIDED);
+              if (!(back && cull)) {
+                const V3 hp = lo + ld * t;
+                V3 n = (hp - c) / r;
+                if (back) n = -n;
+                lt = t; lprim = prim; lback = back;
+                SM_ST3(S_LN, n);
+              }
+            }
           }
-          pix = -1;
         } else {
-          bounce = 0; passes = 0;
-          origin = cam_pos; dir = pd; throughput = mk(1, 1, 1); incoming = mk(0, 0, 0);
+          // src/Trace.cl:276-317 with the distance test hoisted before the normal (same accept set) and a
+          // total order (t, prim) instead of first-found-wins
+          if (COUNT) c_tri++;
+          const float4* gp = p.tri_geom + 3 * (size_t)slot;
+          const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
+          const V3 A = xyz(g0), edge1 = xyz(g1), edge2 = xyz(g2);
+          const V3 h = cross(ld, edge2);
+          const float a = dot(edge1, h);
+          if (!(fabsf(a) < RR_EPSILON)) {
+            const float f = 1.0f / a;
+            const V3 s = lo - A;
+            const float u = f * dot(s, h);
+            if (!(u < 0.0f || u > 1.0f)) {
+              const V3 q = cross(s, edge1);
+              const float v = f * dot(ld, q);
+              if (!(v < 0.0f || u + v > 1.0f)) {
+                const float t = f * dot(edge2, q);
+                const int32_t prim = (int32_t)__float_as_uint(g0.w);
+                if (t > RR_EPSILON && (t < lt || (t == lt && lprim != NO_PRIM && prim < lprim))) {
+                  const float4* np = p.tri_nrm + 3 * (size_t)slot;
+                  const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+                  V3 n = normalize(xyz(n0) * (1.0f - u - v) + xyz(n1) * u + xyz(n2) * v);
+                  bool back = false;
+                  bool ok = true;
+                  if (dot(ld, n) > RR_EPSILON) {
+                    if (mflags & RR_MF_CULL) ok = false;
+                    back = true;
+                    n = -n;
+                  }
+                  if (ok) {
+                    lt = t; lprim = prim; lback = back;
+                    SM_ST3(S_LN, n);
+                  }
+                }
+              }
+            }
+          }
+        }
+        if (pend_cnt == 0) {
+          if (cur < 0 && cur != REF_END) {  // the leaf this lane was waiting on becomes the postponed one
+            pend_slot = (uint32_t)~cur;
+            pend_cnt = 1;
+            resolve(REF_END);
+          } else if (cur == REF_END) {
+            state = ST_SETUP;
+          }
         }
       }
+    } else if (phase == PH_SETUP) {
+      // ================= finish the current mesh, find and enter the next (src/Trace.cl:444-482) =================
+      if (state == ST_SETUP) {
+        if (lprim != NO_PRIM) {
+          if (mflags & RR_MF_SPHERES) {
+            const int32_t mat = p.n_meshes + lprim;
+            const int32_t type = __ldg(&p.materials[mat].type);
+            if (!(type == RR_MATERIAL_ONESIDED && lback) && lt < best_dst) {
+              best_dst = lt; best_mat = mat; best_back = lback; best_mesh = p.n_meshes; best_prim = lprim;
+              const V3 wp = origin + dir * lt;
+              SM_ST3(S_BP, wp);
+              SM(S_BN) = SM(S_LN); SM(S_BN + 1) = SM(S_LN + 1); SM(S_BN + 2) = SM(S_LN + 2);
+            }
+          } else {
+            const int32_t type = (int32_t)(mflags >> RR_MF_TYPE_SHIFT);
+            if (!(type == RR_MATERIAL_ONESIDED && lback)) {
+              // LocalToWorldHit, src/Trace.cl:139-156
+              const DMesh* M = p.meshes + m;
+              const float4 r0 = __ldg(&M->r0), r1 = __ldg(&M->r1), r2 = __ldg(&M->r2);
+              const V3 pos = mk(__ldg(&M->ri0.w), __ldg(&M->ri1.w), __ldg(&M->ri2.w));
+              const V3 lp = (lo + ld * lt) * r0.w;
+              const V3 wp = mk(dot(xyz(r0), lp), dot(xyz(r1), lp), dot(xyz(r2), lp)) + pos;
+              const V3 ln = SM_LD3(S_LN);
+              const V3 wn = normalize(mk(dot(xyz(r0), ln), dot(xyz(r1), ln), dot(xyz(r2), ln)));
+              const float wd = length(wp - origin);
+              if (wd < best_dst) {
+                best_dst = wd; best_mat = m; best_back = lback; best_mesh = m; best_prim = lprim;
+                SM_ST3(S_BP, wp);
+                SM_ST3(S_BN, wn);
+              }
+            }
+          }
+          lprim = NO_PRIM;
+        }
+        // next mesh whose world box the ray enters before the closest hit so far
+        const V3 winv = SM_LD3(S_WINV);
+        const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
+        int mm = m;
+        for (;;) {
+          ++mm;
+          if (mm > p.last_mesh) break;
+          const DMesh* M = p.meshes + mm;
+          const float4 wlo = __ldg(&M->wmin), whi = __ldg(&M->wmax);
+          if (__float_as_uint(wlo.w) & RR_MF_SKIP) continue;
+          if (COUNT) c_box++;
+          float tn;
+          if (box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, best_dst, tn)) break;
+        }
+        m = mm;
+        if (m > p.last_mesh) {
+          state = ST_SHADE;
+        } else {
+          const DMesh* M = p.meshes + m;
+          mflags = __float_as_uint(__ldg(&M->wmin.w));
+          if (mflags & RR_MF_SPHERES) {
+            lo = origin; ld = dir; linv = winv; lnoi = wnoi;
+          } else {
+            // WorldToLocalRay, src/Trace.cl:118-137
+            const float4 i0 = __ldg(&M->ri0), i1 = __ldg(&M->ri1), i2 = __ldg(&M->ri2);
+            const V3 rel = origin - mk(i0.w, i1.w, i2.w);
+            lo = mk(dot(xyz(i0), rel), dot(xyz(i1), rel), dot(xyz(i2), rel));
+            ld = mk(dot(xyz(i0), dir), dot(xyz(i1), dir), dot(xyz(i2), dir));
+            if (!(mflags & RR_MF_UNIT)) {
+              const float scale = __ldg(&M->r0.w);
+              if (mflags & RR_MF_POW2) {  // x / 2^k == x * 2^-k exactly
+                const float is = __ldg(&M->r1.w);
+                lo = lo * is; ld = ld * is;
+              } else if (fabsf(scale) > RR_EPSILON) {
+                lo = lo / scale; ld = ld / scale;
+              }
+            }
+            ld = normalize(ld);
+            linv = mk(rcp_approx(ld.x), rcp_approx(ld.y), rcp_approx(ld.z));
+            lnoi = mk(-(lo.x * linv.x), -(lo.y * linv.y), -(lo.z * linv.z));
+          }
+          const float4 blo = __ldg(&M->bmin), bhi = __ldg(&M->bmax);
+          float tn;
+          if (COUNT) c_box++;
+          if (box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, linv, lnoi, INFINITY, tn)) {
+            const uint32_t first = __float_as_uint(blo.w), count = __float_as_uint(bhi.w);
+            lt = INFINITY; lprim = NO_PRIM; lback = false;
+            sp = 0;
+            if (count <= RR_DIRECT_MAX) {  // no hierarchy: test the primitives one by one in the leaf phase
+              pend_slot = (mflags & RR_MF_SPHERES) ? 0u : first;
+              pend_cnt = count;
+              cur = REF_END;
+            } else {
+              pend_cnt = 0;
+              cur = (int32_t)first;  // root node
+            }
+            state = ST_TRAV;
+          }
+          // else: stay in ST_SETUP and look for the next mesh in the next setup round
+        }
+      }
+    } else if (phase == PH_SHADE) {
+      // ================= one bounce of Trace() (src/Trace.cl:497-591) and the sample loop (:639-642) =================
+      if (state == ST_SHADE) {
+        if (PRIMARY) {
+          if (p.hit_mesh) p.hit_mesh[pix] = best_dst < INFINITY ? best_mesh : -1;
+          if (p.hit_prim) p.hit_prim[pix] = best_dst < INFINITY ? best_prim : -1;
+          if (p.hit_dst) p.hit_dst[pix] = best_dst < INFINITY ? best_dst : 0.0f;
+          state = ST_PIXEL;
+        } else {
+          SceneHit hit;
+          hit.did = best_dst < INFINITY;
+          hit.dst = best_dst;
+          hit.point = SM_LD3(S_BP);
+          hit.normal = SM_LD3(S_BN);
+          hit.back = best_back;
+          hit.material = best_mat;
+          V3 throughput = SM_LD3(S_THR), incoming = SM_LD3(S_INC);
+          bool alive = shade(p, hit, origin, dir, throughput, incoming, bounce, passes, rng);
+          alive = alive && bounce < p.max_bounces;
+          if (alive) {
+            SM_ST3(S_THR, throughput);
+            SM_ST3(S_INC, incoming);
+          } else {  // path finished: src/Trace.cl:639-642
+            const V3 accum = SM_LD3(S_ACC) + incoming;
+            sample++;
+            if (sample >= p.spp) {
+              const V3 c = accum / (float)p.spp;
+              reinterpret_cast<uint32_t*>(p.frame)[pix] = tonemap_rgba(c);
+              if (p.radiance) {
+                p.radiance[3 * (size_t)pix] = c.x;
+                p.radiance[3 * (size_t)pix + 1] = c.y;
+                p.radiance[3 * (size_t)pix + 2] = c.z;
+              }
+              state = ST_PIXEL;
+            } else {
+              SM_ST3(S_ACC, accum);
+              begin_path();
+            }
+          }
+          if (state != ST_PIXEL) begin_ray();
+        }
+      }
+    } else {
+      // ================= hand a pixel to every lane that needs one =================
+      bool need = state == ST_PIXEL;
+      while (__any_sync(full, need)) {
+        if (tile_next >= tile_pixels) {
+          if (queue_empty) break;
+          uint32_t tile;
+          if (!pop_tile(p, tile)) { queue_empty = true; break; }
+          n_tiles++;
+          tile_x0 = (tile % p.tiles_x) * p.tile_w;
+          tile_y0 = (tile / p.tiles_x) * p.tile_h;
+          tile_w = min(p.tile_w, p.width - tile_x0);
+          tile_pixels = tile_w * min(p.tile_h, p.height - tile_y0);
+          tile_next = 0;
+        }
+        const unsigned mb = __ballot_sync(full, need);
+        const unsigned rank = __popc(mb & ((1u << lane) - 1u));
+        const uint32_t k = tile_next + rank;
+        if (need && k < tile_pixels) {
+          const uint32_t x = tile_x0 + k % tile_w, y = tile_y0 + k / tile_w;
+          pix = (int32_t)(y * p.width + x);
+          if (!PRIMARY && p.max_bounces == 0) {  // no segment is ever traced: the pixel is black
+            reinterpret_cast<uint32_t*>(p.frame)[pix] = tonemap_rgba(mk(0, 0, 0));
+            if (p.radiance) { p.radiance[3 * (size_t)pix] = 0.0f; p.radiance[3 * (size_t)pix + 1] = 0.0f; p.radiance[3 * (size_t)pix + 2] = 0.0f; }
+          } else {
+            rng = make_seed((uint32_t)pix, p.frame_index, 0u);          // src/Trace.cl:631-632
+            const V3 pd = primary_dir(p.cam, x, y, p.width, p.height);  // once per pixel, :634-636
+            SM_ST3(S_PD, pd);
+            SM(S_ACC) = 0.0f; SM(S_ACC + 1) = 0.0f; SM(S_ACC + 2) = 0.0f;
+            sample = 0;
+            begin_path();
+            begin_ray();
+            need = false;
+          }
+        }
+        tile_next += __popc(mb);
+      }
+      if (need) state = ST_IDLE;  // the queue is empty
     }
   }
+#undef SM
+#undef SM_ST3
+#undef SM_LD3
   // counters: one atomic per warp
   unsigned long long r = n_rays;
 #pragma unroll
@@ -533,7 +661,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 2) k_render(const RenderParams
     atomicAdd(&p.counters->tiles, n_tiles);
   }
   if (COUNT) {
-    unsigned long long b = tc.box, t = tc.tri, s = tc.sph;
+    unsigned long long b = c_box, t = c_tri, s = c_sph;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       b += __shfl_xor_sync(full, b, off);
@@ -544,35 +672,46 @@ __global__ void __launch_bounds__(RENDER_THREADS, 2) k_render(const RenderParams
       atomicAdd(&p.counters->box_tests, b);
       atomicAdd(&p.counters->tri_tests, t);
       atomicAdd(&p.counters->sphere_tests, s);
+      for (int k = 0; k < 5; ++k) {
+        atomicAdd(&p.counters->phase_runs[k], (unsigned long long)ph_runs[k]);
+        atomicAdd(&p.counters->phase_lanes[k], (unsigned long long)ph_lanes[k]);
+      }
     }
   }
 }
 
-// Primary-ray closest hit per pixel (MakeRay + CalculateRayCollisionWithTriangle).
-__global__ void __launch_bounds__(256) k_primary(const RenderParams p) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.width * p.height) return;
-  const uint32_t x = i % p.width, y = i / p.width;
-  const V3 d = primary_dir(p.cam, x, y, p.width, p.height);
-  SceneHit hit;
-  TraversalCounters tc = {0u, 0u, 0u};
-  scene_closest<false>(p, mk(p.cam.pos[0], p.cam.pos[1], p.cam.pos[2]), d, hit, tc);
-  if (p.hit_mesh) p.hit_mesh[i] = hit.did ? hit.mesh : -1;
-  if (p.hit_prim) p.hit_prim[i] = hit.did ? hit.prim : -1;
-  if (p.hit_dst) p.hit_dst[i] = hit.did ? hit.dst : 0.0f;
+void default_tuning(Tuning& t) {
+  for (int k = 0; k < 5; ++k) t.weight[k] = 4;
+  t.trav_keep = 12;
+  t.speculate = 1;
+  t.ctas_per_sm = 0;
+}
+
+static int resident_ctas(const void* fn, const RenderParams& p) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, NT, 0) != cudaSuccess || n < 1) n = 1;
+  if (p.tune.ctas_per_sm && (int)p.tune.ctas_per_sm < n) n = (int)p.tune.ctas_per_sm;
+  return n;
 }
 
 cudaError_t launch_render(const RenderParams& p, bool count_tests, int sm_count, cudaStream_t s) {
-  const int grid = sm_count * 2;  // persistent: launch_bounds(256, 2) -> two resident CTAs per SM
-  if (count_tests) k_render<true><<<grid, RENDER_THREADS, 0, s>>>(p);
-  else k_render<false><<<grid, RENDER_THREADS, 0, s>>>(p);
+  // persistent: as many CTAs as are resident at once, each warp loops until the tile queue is empty
+  if (count_tests) {
+    const int grid = sm_count * resident_ctas((const void*)k_render<true, false>, p);
+    k_render<true, false><<<grid, NT, 0, s>>>(p);
+  } else {
+    const int grid = sm_count * resident_ctas((const void*)k_render<false, false>, p);
+    k_render<false, false><<<grid, NT, 0, s>>>(p);
+  }
   return cudaGetLastError();
 }
 
-cudaError_t launch_primary(const RenderParams& p, cudaStream_t s) {
-  const uint64_t n = (uint64_t)p.width * p.height;
-  if (!n) return cudaSuccess;
-  k_primary<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
+// Primary-ray closest hit per pixel (MakeRay + CalculateRayCollisionWithTriangle): the same kernel, stopped
+// at the first shade phase.
+cudaError_t launch_primary(const RenderParams& p, int sm_count, cudaStream_t s) {
+  if (!p.width || !p.height) return cudaSuccess;
+  const int grid = sm_count * resident_ctas((const void*)k_render<false, true>, p);
+  k_render<false, true><<<grid, NT, 0, s>>>(p);
   return cudaGetLastError();
 }
 

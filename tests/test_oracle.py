@@ -172,3 +172,25 @@ def test_spheres_extension_sanity():
     assert both.sum() > 300
     assert np.abs((m1 >= 0).astype(int) - (m2 >= 0).astype(int)).sum() < 60  # silhouette pixels only
     assert np.max(np.abs(d1[both] - d2[both])) < 0.5
+
+
+def test_hierarchy_only_culls_brute_force_defines_the_result(golden_wide, knight_obj):
+    """The closest hit is DEFINED by the primitive tests (brute-force minimum in the order (t, index));
+    walking the delta-inflated LBVH must give exactly that, primary hits and multi-bounce radiance alike."""
+    import ripoff_raytracer_b200 as rr
+
+    cases = []
+    g = golden_wide
+    cases.append((g["tris"], g["meshes"], g["ranges"], None, g["cam"], int(g["W"]), int(g["H"])))
+    s = rr.default_scene(knight_obj)
+    t, m, r, sp = s.arrays()
+    cases.append((t, m, r, sp, rr.default_camera(96, 96), 96, 96))
+    for t, m, r, sp, cam, W, H in cases:
+        walk = Oracle(t, m, r, sp)
+        brute = Oracle(t, m, r, sp).brute_force()
+        for a, b in zip(walk.primary(cam, W, H), brute.primary(cam, W, H)):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        wi, wr, wst = walk.render(cam, W, H, 2, 12, radiance=True)
+        bi, br, bst = brute.render(cam, W, H, 2, 12, radiance=True)
+        assert np.array_equal(wi, bi) and np.array_equal(wr.view(np.uint32), br.view(np.uint32))
+        assert wst["rays"] == bst["rays"] and wst["tri_tests"] < bst["tri_tests"]
