@@ -80,7 +80,8 @@ __global__ void k_prepare_meshes(const rr_mesh* __restrict__ meshes, const uint3
                                  const float* __restrict__ seg_box, const uint32_t* __restrict__ seg_sfirst,
                                  const uint32_t* __restrict__ seg_count, const rr_sphere* __restrict__ spheres,
                                  int n_spheres, const float* __restrict__ sph_seg_box, uint32_t sph_node_base,
-                                 DMesh* __restrict__ out, DMaterial* __restrict__ mats) {
+                                 const uint32_t* __restrict__ mesh_pos, DMesh* __restrict__ out,
+                                 DMaterial* __restrict__ mats) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_meshes + n_spheres) return;
   const rr_material* src;
@@ -139,7 +140,7 @@ __global__ void k_prepare_meshes(const rr_mesh* __restrict__ meshes, const uint3
     }
     d.wmin = make_float4(wlo[0], wlo[1], wlo[2], __uint_as_float(flags));
     d.wmax = make_float4(whi[0], whi[1], whi[2], __int_as_float(i));
-    out[i] = d;
+    out[mesh_pos[i]] = d;  // the kernel visits the meshes in mesh_pos order (largest first)
   } else {
     src = &spheres[i - n_meshes].material;
     if (i == n_meshes) {  // the sphere set as a world-space pseudo-mesh
@@ -153,7 +154,7 @@ __global__ void k_prepare_meshes(const rr_mesh* __restrict__ meshes, const uint3
       d.bmax = make_float4(sb[3] + delta, sb[4] + delta, sb[5] + delta, __uint_as_float((uint32_t)n_spheres));
       d.wmin = make_float4(d.bmin.x, d.bmin.y, d.bmin.z, __uint_as_float(RR_MF_SPHERES | RR_MF_UNIT | RR_MF_POW2));
       d.wmax = make_float4(d.bmax.x, d.bmax.y, d.bmax.z, __int_as_float(n_meshes));
-      out[n_meshes] = d;
+      out[mesh_pos[n_meshes]] = d;
     }
   }
   DMaterial mm;
@@ -234,7 +235,19 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   if (d.sb.n) RR_CUDA(cudaMemcpyAsync(d.nodes + 4 * d.tb.n, d.sb.nodes, d.sb.n * 64, cudaMemcpyDeviceToDevice, st));
   // mesh + material tables
   rr_mesh* d_meshes_in = nullptr;
-  uint32_t* d_mesh_seg = nullptr;
+  uint32_t *d_mesh_seg = nullptr, *d_mesh_pos = nullptr;
+  // visiting order of the meshes: most primitives first (a hit there prunes the small ones by their world box);
+  // equal world distances are resolved by the original index in the kernel, so the order does not change results
+  std::vector<uint32_t> mesh_pos(n_meshes + 1, 0);
+  {
+    std::vector<std::pair<uint64_t, uint32_t>> byCount;
+    for (size_t i = 0; i < n_meshes; ++i) byCount.push_back({plan.count[plan.mesh_seg[i]], (uint32_t)i});
+    if (n_spheres) byCount.push_back({n_spheres, (uint32_t)n_meshes});
+    std::stable_sort(byCount.begin(), byCount.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+    for (size_t k = 0; k < byCount.size(); ++k) mesh_pos[byCount[k].second] = (uint32_t)k;
+  }
+  RR_CUDA(cudaMalloc(&d_mesh_pos, (n_meshes + 1) * 4));
+  RR_CUDA(cudaMemcpyAsync(d_mesh_pos, mesh_pos.data(), (n_meshes + 1) * 4, cudaMemcpyHostToDevice, st));
   RR_CUDA(cudaMalloc(&d_meshes_in, std::max<size_t>(n_meshes, 1) * sizeof(rr_mesh)));
   RR_CUDA(cudaMalloc(&d_mesh_seg, std::max<size_t>(n_meshes, 1) * 4));
   RR_CUDA(cudaMalloc(&d.meshes, (n_meshes + 1) * sizeof(DMesh)));
@@ -246,8 +259,8 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   if (n_meshes + n_spheres) {
     const int n = (int)(n_meshes + n_spheres);
     k_prepare_meshes<<<(n + 127) / 128, 128, 0, st>>>(d_meshes_in, d_mesh_seg, (int)n_meshes, d.tb.seg_box, d.tb.seg_sfirst,
-                                                      d.tb.seg_count, d.spheres, (int)n_spheres, d.sb.seg_box, (uint32_t)d.tb.n, d.meshes,
-                                                      d.materials);
+                                                      d.tb.seg_count, d.spheres, (int)n_spheres, d.sb.seg_box, (uint32_t)d.tb.n, d_mesh_pos,
+                                                      d.meshes, d.materials);
     RR_CUDA(cudaGetLastError());
   }
   RR_CUDA(cudaEventRecord(d.ev1, st));
@@ -255,6 +268,7 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   RR_CUDA(cudaEventElapsedTime(&d.build_ms, d.ev0, d.ev1));
   cudaFree(d_meshes_in);
   cudaFree(d_mesh_seg);
+  cudaFree(d_mesh_pos);
   cudaFree(d.tb.nodes); d.tb.nodes = nullptr;  // copied into d.nodes
   cudaFree(d.sb.nodes); d.sb.nodes = nullptr;
   if (d.tb.max_depth > RR_STACK || d.sb.max_depth > RR_STACK)

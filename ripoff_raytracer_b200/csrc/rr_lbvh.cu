@@ -424,8 +424,9 @@ __global__ void k_pack_nodes(uint64_t n, const uint32_t* __restrict__ order, con
     const float d = box_delta(sb);
 #pragma unroll
     for (int k = 0; k < 3; ++k) { a[k] -= d; c[k] -= d; a[3 + k] += d; c[3 + k] += d; }
-    if (L >= 0) L += ref_offset;
-    if (R >= 0) R += ref_offset;
+    // inner: index in the combined node array; leaf: -(slot + 2)  (so that -1 is free for "pop", rr_render.cu)
+    L = L >= 0 ? L + ref_offset : L - 1;
+    R = R >= 0 ? R + ref_offset : R - 1;
     q0 = make_float4(a[0], a[1], a[2], a[3]);
     q1 = make_float4(a[4], a[5], c[0], c[1]);
     q2 = make_float4(c[2], c[3], c[4], c[5]);

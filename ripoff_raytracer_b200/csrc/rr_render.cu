@@ -122,7 +122,6 @@ __device__ __forceinline__ bool box_cull(float lox, float loy, float loz, float 
   return tf >= fmaxf(tn, 0.0f) && tn <= tbest;
 }
 
-constexpr int32_t REF_END = (int32_t)0x80000000;  // traversal finished / "pop the stack"
 constexpr int32_t NO_PRIM = 0x7fffffff;
 
 struct SceneHit {  // HitInfo of src/Trace.cl:67-74 as the shade phase sees it
@@ -265,6 +264,11 @@ enum { ST_IDLE = 0, ST_PIXEL = 1, ST_SHADE = 2, ST_SETUP = 3, ST_TRAV = 4 };
 enum { PH_PIXEL = 0, PH_SHADE = 1, PH_SETUP = 2, PH_TRAV = 3, PH_LEAF = 4 };
 // per-thread words kept in shared memory (word k of thread t at smem[k * NT + t]: conflict-free)
 enum { S_THR = 0, S_INC = 3, S_ACC = 6, S_BP = 9, S_BN = 12, S_LN = 15, S_WINV = 18, S_PD = 21, S_WORDS = 24 };
+// Node references.  In the packed nodes a leaf is -(slot + 2), so that "inner node or pop" is cur >= -1.
+constexpr int32_t REF_POP = -1;                   // take the next entry of the stack
+constexpr int32_t REF_END = (int32_t)0x80000000;  // traversal of this mesh finished
+__device__ __forceinline__ bool ref_is_leaf(int32_t r) { return r < REF_POP && r != REF_END; }
+__device__ __forceinline__ uint32_t ref_slot(int32_t r) { return (uint32_t)(-r) - 2u; }
 
 template <bool COUNT, bool PRIMARY>
 __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
@@ -287,9 +291,11 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
   uint32_t rng = 0, sample = 0, bounce = 0, passes = 0;
   V3 origin = cam_pos, dir = mk(0, 0, 1);
   float best_dst = INFINITY;
-  int32_t best_mat = 0, best_mesh = -1, best_prim = -1;
+  int32_t best_mat = 0, best_mesh = 0x7fffffff, best_prim = -1;
   bool best_back = false;
-  int m = -1;
+  uint32_t cand = 0;     // candidate meshes of the current 32-mesh chunk (bit k = mesh cand_base + k) not yet visited
+  int32_t cand_base = 0;
+  int m = 0;
   uint32_t mflags = 0;
   V3 lo = origin, ld = dir, linv = dir, lnoi = dir;
   float lt = INFINITY;
@@ -308,12 +314,30 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
   const uint32_t trav_keep = p.tune.trav_keep;
   const bool speculate = p.tune.speculate != 0;
 
-  // A new ray starts: reset the closest hit and the mesh cursor (src/Trace.cl:437-444).
+  // World-box tests of the meshes [base, base + 32): bit k set = the ray enters mesh base + k's box before `tmax`.
+  // Every lane walks the whole chunk, so the loop is convergent.
+  auto scan_meshes = [&](int32_t base, const V3& winv, const V3& wnoi, float tmax) -> uint32_t {
+    uint32_t mask = 0;
+    const int32_t end = min(base + 32, p.last_mesh + 1);
+    for (int32_t k = base; k < end; ++k) {
+      const DMesh* M = p.meshes + k;
+      const float4 wlo = __ldg(&M->wmin), whi = __ldg(&M->wmax);
+      float tn;
+      const bool hit = box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, tmax, tn);
+      if (hit && !(__float_as_uint(wlo.w) & RR_MF_SKIP)) mask |= 1u << (k - base);
+    }
+    if (COUNT) c_box += (unsigned)(end - base);
+    return mask;
+  };
+  // A new ray starts: reset the closest hit (src/Trace.cl:437-444) and collect the candidate meshes.
   auto begin_ray = [&]() {
-    best_dst = INFINITY; best_mat = 0; best_mesh = -1; best_prim = -1; best_back = false;
-    m = -1;
+    best_dst = INFINITY; best_mat = 0; best_mesh = 0x7fffffff; best_prim = -1; best_back = false;
     lprim = NO_PRIM;
-    SM(S_WINV) = rcp_approx(dir.x); SM(S_WINV + 1) = rcp_approx(dir.y); SM(S_WINV + 2) = rcp_approx(dir.z);
+    const V3 winv = mk(rcp_approx(dir.x), rcp_approx(dir.y), rcp_approx(dir.z));
+    SM_ST3(S_WINV, winv);
+    const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
+    cand_base = 0;
+    cand = scan_meshes(0, winv, wnoi, INFINITY);
     n_rays++;
     state = ST_SETUP;
   };
@@ -324,71 +348,179 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
     SM(S_THR) = 1.0f; SM(S_THR + 1) = 1.0f; SM(S_THR + 2) = 1.0f;
     SM(S_INC) = 0.0f; SM(S_INC + 1) = 0.0f; SM(S_INC + 2) = 0.0f;
   };
-  // Pops the stack / postpones leaves until `cur` is an inner node, a leaf the lane must wait for, or REF_END.
-  auto resolve = [&](int32_t next) {
-    for (;;) {
-      if (next == REF_END) {
-        bool found = false;
-        while (sp > 0) {
-          --sp;
-          if (stackD[sp] <= lt) { next = stackN[sp]; found = true; break; }
-        }
-        if (!found) { cur = REF_END; break; }
+  // The mesh just traversed has a closest hit (local space): LocalToWorldHit and the keep-min of
+  // src/Trace.cl:465-481.  Meshes are visited in our own order, so equal distances are resolved by the
+  // original mesh index, which is what the reference's in-order strict `<` does.
+  auto finish_mesh = [&]() {
+    if (lprim == NO_PRIM) return;
+    const DMesh* M = p.meshes + m;
+    const int32_t mesh_index = __float_as_int(__ldg(&M->wmax.w));
+    if (mflags & RR_MF_SPHERES) {
+      const int32_t mat = mesh_index + lprim;
+      const int32_t type = __ldg(&p.materials[mat].type);
+      if (!(type == RR_MATERIAL_ONESIDED && lback) && (lt < best_dst || (lt == best_dst && mesh_index < best_mesh))) {
+        best_dst = lt; best_mat = mat; best_back = lback; best_mesh = mesh_index; best_prim = lprim;
+        const V3 wp = origin + dir * lt;
+        SM_ST3(S_BP, wp);
+        SM(S_BN) = SM(S_LN); SM(S_BN + 1) = SM(S_LN + 1); SM(S_BN + 2) = SM(S_LN + 2);
       }
-      if (next >= 0) { cur = next; break; }
-      if (pend_cnt == 0) { pend_slot = (uint32_t)~next; pend_cnt = 1; next = REF_END; continue; }
-      cur = next;  // a second leaf while one is postponed: wait for the leaf phase
-      break;
+    } else {
+      const int32_t type = (int32_t)(mflags >> RR_MF_TYPE_SHIFT);
+      if (!(type == RR_MATERIAL_ONESIDED && lback)) {
+        // LocalToWorldHit, src/Trace.cl:139-156
+        const float4 r0 = __ldg(&M->r0), r1 = __ldg(&M->r1), r2 = __ldg(&M->r2);
+        const V3 pos = mk(__ldg(&M->ri0.w), __ldg(&M->ri1.w), __ldg(&M->ri2.w));
+        const V3 lp = (lo + ld * lt) * r0.w;
+        const V3 wp = mk(dot(xyz(r0), lp), dot(xyz(r1), lp), dot(xyz(r2), lp)) + pos;
+        const V3 ln = SM_LD3(S_LN);
+        const V3 wn = normalize(mk(dot(xyz(r0), ln), dot(xyz(r1), ln), dot(xyz(r2), ln)));
+        const float wd = length(wp - origin);
+        if (wd < best_dst || (wd == best_dst && mesh_index < best_mesh)) {
+          best_dst = wd; best_mat = mesh_index; best_back = lback; best_mesh = mesh_index; best_prim = lprim;
+          SM_ST3(S_BP, wp);
+          SM_ST3(S_BN, wn);
+        }
+      }
     }
-    if (cur == REF_END && pend_cnt == 0) state = ST_SETUP;
+    lprim = NO_PRIM;
   };
+  // Enters the next candidate mesh (src/Trace.cl:444-463): world box against the closest hit so far,
+  // WorldToLocalRay, root box; ST_TRAV when a traversal starts, ST_SHADE when no candidate is left.
+  auto enter_next_mesh = [&](const V3& winv, const V3& wnoi) {
+    for (;;) {
+      if (cand == 0) {
+        if (cand_base + 32 > p.last_mesh) { state = ST_SHADE; return; }
+        cand_base += 32;
+        cand = scan_meshes(cand_base, winv, wnoi, best_dst);
+        continue;
+      }
+      const int k = __ffs((int)cand) - 1;
+      cand &= cand - 1u;
+      m = cand_base + k;
+      const DMesh* M = p.meshes + m;
+      float tn;
+      if (best_dst < INFINITY) {  // a hit exists: the box may now lie behind it
+        const float4 wlo = __ldg(&M->wmin), whi = __ldg(&M->wmax);
+        if (COUNT) c_box++;
+        if (!box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, best_dst, tn)) continue;
+      }
+      mflags = __float_as_uint(__ldg(&M->wmin.w));
+      if (mflags & RR_MF_SPHERES) {
+        lo = origin; ld = dir; linv = winv; lnoi = wnoi;
+      } else {
+        // WorldToLocalRay, src/Trace.cl:118-137
+        const float4 i0 = __ldg(&M->ri0), i1 = __ldg(&M->ri1), i2 = __ldg(&M->ri2);
+        const V3 rel = origin - mk(i0.w, i1.w, i2.w);
+        lo = mk(dot(xyz(i0), rel), dot(xyz(i1), rel), dot(xyz(i2), rel));
+        ld = mk(dot(xyz(i0), dir), dot(xyz(i1), dir), dot(xyz(i2), dir));
+        if (!(mflags & RR_MF_UNIT)) {
+          const float scale = __ldg(&M->r0.w);
+          if (mflags & RR_MF_POW2) {  // x / 2^k == x * 2^-k exactly
+            const float is = __ldg(&M->r1.w);
+            lo = lo * is; ld = ld * is;
+          } else if (fabsf(scale) > RR_EPSILON) {
+            lo = lo / scale; ld = ld / scale;
+          }
+        }
+        ld = normalize(ld);
+        linv = mk(rcp_approx(ld.x), rcp_approx(ld.y), rcp_approx(ld.z));
+        lnoi = mk(-(lo.x * linv.x), -(lo.y * linv.y), -(lo.z * linv.z));
+      }
+      const float4 blo = __ldg(&M->bmin), bhi = __ldg(&M->bmax);
+      if (COUNT) c_box++;
+      if (!box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, linv, lnoi, INFINITY, tn)) continue;
+      const uint32_t first = __float_as_uint(blo.w), count = __float_as_uint(bhi.w);
+      lt = INFINITY; lprim = NO_PRIM; lback = false;
+      sp = 0;
+      if (count <= RR_DIRECT_MAX) {  // no hierarchy: the primitives are tested one by one in the leaf phase
+        pend_slot = (mflags & RR_MF_SPHERES) ? 0u : first;
+        pend_cnt = count;
+        cur = REF_END;
+      } else {
+        pend_cnt = 0;
+        cur = (int32_t)first;  // root node
+      }
+      state = ST_TRAV;
+      return;
+    }
+  };
+  // after the last node / leaf of a mesh: more candidates -> setup phase, none -> shade phase (which
+  // finishes the mesh itself)
+  auto leave_mesh = [&]() { state = (cand != 0 || cand_base + 32 <= p.last_mesh) ? ST_SETUP : ST_SHADE; };
 
   for (;;) {
-    // ---- vote: which phase has the most ready lanes ----
-    const bool inT = state == ST_TRAV;
-    const unsigned bT = __ballot_sync(full, inT && cur >= 0 && (speculate || pend_cnt == 0));
-    const unsigned bL = __ballot_sync(full, inT && pend_cnt > 0);
-    const unsigned bS = __ballot_sync(full, state == ST_SETUP);
-    const unsigned bH = __ballot_sync(full, state == ST_SHADE);
-    const unsigned bP = queue_empty && tile_next >= tile_pixels ? 0u : __ballot_sync(full, state == ST_PIXEL);
-    if (!(bT | bL | bS | bH | bP)) break;
-    const uint32_t sT = __popc(bT) * wT, sL = __popc(bL) * wL, sS = __popc(bS) * wS, sH = __popc(bH) * wH,
-                   sP = __popc(bP) * wP;
+    // ---- vote: one REDUX over 6-bit fields counts the ready lanes of every phase ----
+    const bool more_pixels = !(queue_empty && tile_next >= tile_pixels);
+    uint32_t key = 0;
+    if (state == ST_TRAV) {
+      key = ((cur >= REF_POP && (speculate || pend_cnt == 0)) ? 1u << (6 * PH_TRAV) : 0u) | (pend_cnt ? 1u << (6 * PH_LEAF) : 0u);
+    } else if (state == ST_SETUP) key = 1u << (6 * PH_SETUP);
+    else if (state == ST_SHADE) key = 1u << (6 * PH_SHADE);
+    else if (state == ST_PIXEL && more_pixels) key = 1u << (6 * PH_PIXEL);
+    const uint32_t counts = __reduce_add_sync(full, key);
+    if (counts == 0) break;
+    const uint32_t nP = counts & 63u, nH = (counts >> 6) & 63u, nS = (counts >> 12) & 63u, nT = (counts >> 18) & 63u,
+                   nL = (counts >> 24) & 63u;
     int phase = PH_TRAV;
-    uint32_t best = sT;
-    if (sL > best) { best = sL; phase = PH_LEAF; }
-    if (sS > best) { best = sS; phase = PH_SETUP; }
-    if (sH > best) { best = sH; phase = PH_SHADE; }
-    if (sP > best) { best = sP; phase = PH_PIXEL; }
-    if (COUNT) {
-      const unsigned bb = phase == PH_TRAV ? bT : phase == PH_LEAF ? bL : phase == PH_SETUP ? bS : phase == PH_SHADE ? bH : bP;
-      if (phase != PH_TRAV) { ph_runs[phase]++; ph_lanes[phase] += __popc(bb); }
+    uint32_t best = nT * wT;
+    if (nL * wL > best) { best = nL * wL; phase = PH_LEAF; }
+    if (nS * wS > best) { best = nS * wS; phase = PH_SETUP; }
+    if (nH * wH > best) { best = nH * wH; phase = PH_SHADE; }
+    if (nP * wP > best) { best = nP * wP; phase = PH_PIXEL; }
+    if (COUNT && phase != PH_TRAV) {
+      ph_runs[phase]++;
+      ph_lanes[phase] += phase == PH_LEAF ? nL : phase == PH_SETUP ? nS : phase == PH_SHADE ? nH : nP;
     }
 
     if (phase == PH_TRAV) {
       // ================= node steps =================
-      unsigned active = bT;
+      uint32_t active = nT;
       do {
-        if (COUNT) { ph_runs[PH_TRAV]++; ph_lanes[PH_TRAV] += __popc(active); }
-        if (state == ST_TRAV && cur >= 0 && (speculate || pend_cnt == 0)) {
-          const float4* nd = p.nodes + 4 * (size_t)cur;
-          const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
-          if (COUNT) c_box += 2;
-          float tA, tB;
-          const bool hA = box_cull(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, linv, lnoi, lt, tA);
-          const bool hB = box_cull(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, linv, lnoi, lt, tB);
-          const int32_t L = __float_as_int(q3.x), R = __float_as_int(q3.y);
-          int32_t next = REF_END;
-          if (hA && hB) {
-            const bool aNear = tA < tB;
-            next = aNear ? L : R;
-            if (sp < RR_STACK) { stackN[sp] = aNear ? R : L; stackD[sp] = aNear ? tB : tA; sp++; }
-          } else if (hA) next = L;
-          else if (hB) next = R;
-          resolve(next);
+        if (COUNT) { ph_runs[PH_TRAV]++; ph_lanes[PH_TRAV] += active; }
+        if (state == ST_TRAV && cur >= REF_POP && (speculate || pend_cnt == 0)) {
+          if (cur == REF_POP) {  // one stack entry per step, in lock-step with the other lanes
+            if (sp > 0) {
+              --sp;
+              const float d = stackD[sp];
+              const int32_t n = stackN[sp];
+              cur = d <= lt ? n : REF_POP;
+              if (ref_is_leaf(cur) && pend_cnt == 0) { pend_slot = ref_slot(cur); pend_cnt = 1; cur = REF_POP; }
+            } else {
+              cur = REF_END;
+            }
+          }
+          if (cur >= 0) {
+            const float4* nd = p.nodes + 4 * (size_t)cur;
+            const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
+            if (COUNT) c_box += 2;
+            float tA, tB;
+            const bool hA = box_cull(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, linv, lnoi, lt, tA);
+            const bool hB = box_cull(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, linv, lnoi, lt, tB);
+            const int32_t L = __float_as_int(q3.x), R = __float_as_int(q3.y);
+            int32_t next = REF_POP;
+            if (hA && hB) {
+              const bool aNear = tA < tB;
+              const int32_t nearRef = aNear ? L : R, farRef = aNear ? R : L;
+              if (pend_cnt == 0 && nearRef < REF_POP) {  // the near child is a leaf: postpone it, go on with the far one
+                if (farRef < REF_POP) {  // two leaves: adjacent slots, L first
+                  pend_slot = ref_slot(L); pend_cnt = 2;
+                } else {
+                  pend_slot = ref_slot(nearRef); pend_cnt = 1;
+                  next = farRef;
+                }
+              } else {
+                if (sp < RR_STACK) { stackN[sp] = farRef; stackD[sp] = aNear ? tB : tA; sp++; }
+                next = nearRef;
+              }
+            } else if (hA) next = L;
+            else if (hB) next = R;
+            if (next < REF_POP && pend_cnt == 0) { pend_slot = ref_slot(next); pend_cnt = 1; next = REF_POP; }
+            cur = next;
+          }
+          if (cur == REF_END && pend_cnt == 0) leave_mesh();
         }
-        active = __ballot_sync(full, state == ST_TRAV && cur >= 0 && (speculate || pend_cnt == 0));
-      } while ((uint32_t)__popc(active) >= trav_keep);
+        active = __popc(__ballot_sync(full, state == ST_TRAV && cur >= REF_POP && (speculate || pend_cnt == 0)));
+      } while (active >= trav_keep);
     } else if (phase == PH_LEAF) {
       // ================= leaf tests =================
       if (state == ST_TRAV && pend_cnt > 0) {
@@ -463,113 +595,27 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
           }
         }
         if (pend_cnt == 0) {
-          if (cur < 0 && cur != REF_END) {  // the leaf this lane was waiting on becomes the postponed one
-            pend_slot = (uint32_t)~cur;
+          if (ref_is_leaf(cur)) {  // the leaf this lane was waiting on becomes the postponed one
+            pend_slot = ref_slot(cur);
             pend_cnt = 1;
-            resolve(REF_END);
+            cur = REF_POP;
           } else if (cur == REF_END) {
-            state = ST_SETUP;
+            leave_mesh();
           }
         }
       }
     } else if (phase == PH_SETUP) {
-      // ================= finish the current mesh, find and enter the next (src/Trace.cl:444-482) =================
+      // ================= finish the current mesh, enter the next candidate (src/Trace.cl:444-482) =================
       if (state == ST_SETUP) {
-        if (lprim != NO_PRIM) {
-          if (mflags & RR_MF_SPHERES) {
-            const int32_t mat = p.n_meshes + lprim;
-            const int32_t type = __ldg(&p.materials[mat].type);
-            if (!(type == RR_MATERIAL_ONESIDED && lback) && lt < best_dst) {
-              best_dst = lt; best_mat = mat; best_back = lback; best_mesh = p.n_meshes; best_prim = lprim;
-              const V3 wp = origin + dir * lt;
-              SM_ST3(S_BP, wp);
-              SM(S_BN) = SM(S_LN); SM(S_BN + 1) = SM(S_LN + 1); SM(S_BN + 2) = SM(S_LN + 2);
-            }
-          } else {
-            const int32_t type = (int32_t)(mflags >> RR_MF_TYPE_SHIFT);
-            if (!(type == RR_MATERIAL_ONESIDED && lback)) {
-              // LocalToWorldHit, src/Trace.cl:139-156
-              const DMesh* M = p.meshes + m;
-              const float4 r0 = __ldg(&M->r0), r1 = __ldg(&M->r1), r2 = __ldg(&M->r2);
-              const V3 pos = mk(__ldg(&M->ri0.w), __ldg(&M->ri1.w), __ldg(&M->ri2.w));
-              const V3 lp = (lo + ld * lt) * r0.w;
-              const V3 wp = mk(dot(xyz(r0), lp), dot(xyz(r1), lp), dot(xyz(r2), lp)) + pos;
-              const V3 ln = SM_LD3(S_LN);
-              const V3 wn = normalize(mk(dot(xyz(r0), ln), dot(xyz(r1), ln), dot(xyz(r2), ln)));
-              const float wd = length(wp - origin);
-              if (wd < best_dst) {
-                best_dst = wd; best_mat = m; best_back = lback; best_mesh = m; best_prim = lprim;
-                SM_ST3(S_BP, wp);
-                SM_ST3(S_BN, wn);
-              }
-            }
-          }
-          lprim = NO_PRIM;
-        }
-        // next mesh whose world box the ray enters before the closest hit so far
+        finish_mesh();
         const V3 winv = SM_LD3(S_WINV);
         const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
-        int mm = m;
-        for (;;) {
-          ++mm;
-          if (mm > p.last_mesh) break;
-          const DMesh* M = p.meshes + mm;
-          const float4 wlo = __ldg(&M->wmin), whi = __ldg(&M->wmax);
-          if (__float_as_uint(wlo.w) & RR_MF_SKIP) continue;
-          if (COUNT) c_box++;
-          float tn;
-          if (box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, best_dst, tn)) break;
-        }
-        m = mm;
-        if (m > p.last_mesh) {
-          state = ST_SHADE;
-        } else {
-          const DMesh* M = p.meshes + m;
-          mflags = __float_as_uint(__ldg(&M->wmin.w));
-          if (mflags & RR_MF_SPHERES) {
-            lo = origin; ld = dir; linv = winv; lnoi = wnoi;
-          } else {
-            // WorldToLocalRay, src/Trace.cl:118-137
-            const float4 i0 = __ldg(&M->ri0), i1 = __ldg(&M->ri1), i2 = __ldg(&M->ri2);
-            const V3 rel = origin - mk(i0.w, i1.w, i2.w);
-            lo = mk(dot(xyz(i0), rel), dot(xyz(i1), rel), dot(xyz(i2), rel));
-            ld = mk(dot(xyz(i0), dir), dot(xyz(i1), dir), dot(xyz(i2), dir));
-            if (!(mflags & RR_MF_UNIT)) {
-              const float scale = __ldg(&M->r0.w);
-              if (mflags & RR_MF_POW2) {  // x / 2^k == x * 2^-k exactly
-                const float is = __ldg(&M->r1.w);
-                lo = lo * is; ld = ld * is;
-              } else if (fabsf(scale) > RR_EPSILON) {
-                lo = lo / scale; ld = ld / scale;
-              }
-            }
-            ld = normalize(ld);
-            linv = mk(rcp_approx(ld.x), rcp_approx(ld.y), rcp_approx(ld.z));
-            lnoi = mk(-(lo.x * linv.x), -(lo.y * linv.y), -(lo.z * linv.z));
-          }
-          const float4 blo = __ldg(&M->bmin), bhi = __ldg(&M->bmax);
-          float tn;
-          if (COUNT) c_box++;
-          if (box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, linv, lnoi, INFINITY, tn)) {
-            const uint32_t first = __float_as_uint(blo.w), count = __float_as_uint(bhi.w);
-            lt = INFINITY; lprim = NO_PRIM; lback = false;
-            sp = 0;
-            if (count <= RR_DIRECT_MAX) {  // no hierarchy: test the primitives one by one in the leaf phase
-              pend_slot = (mflags & RR_MF_SPHERES) ? 0u : first;
-              pend_cnt = count;
-              cur = REF_END;
-            } else {
-              pend_cnt = 0;
-              cur = (int32_t)first;  // root node
-            }
-            state = ST_TRAV;
-          }
-          // else: stay in ST_SETUP and look for the next mesh in the next setup round
-        }
+        enter_next_mesh(winv, wnoi);
       }
     } else if (phase == PH_SHADE) {
       // ================= one bounce of Trace() (src/Trace.cl:497-591) and the sample loop (:639-642) =================
       if (state == ST_SHADE) {
+        finish_mesh();
         if (PRIMARY) {
           if (p.hit_mesh) p.hit_mesh[pix] = best_dst < INFINITY ? best_mesh : -1;
           if (p.hit_prim) p.hit_prim[pix] = best_dst < INFINITY ? best_prim : -1;
@@ -606,7 +652,12 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
               begin_path();
             }
           }
-          if (state != ST_PIXEL) begin_ray();
+          if (state != ST_PIXEL) {  // next segment: candidates, then straight into its first mesh
+            begin_ray();
+            const V3 winv = SM_LD3(S_WINV);
+            const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
+            enter_next_mesh(winv, wnoi);
+          }
         }
       }
     } else {
@@ -640,7 +691,7 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
             SM(S_ACC) = 0.0f; SM(S_ACC + 1) = 0.0f; SM(S_ACC + 2) = 0.0f;
             sample = 0;
             begin_path();
-            begin_ray();
+            begin_ray();  // -> ST_SETUP
             need = false;
           }
         }
