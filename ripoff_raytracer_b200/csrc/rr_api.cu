@@ -54,6 +54,9 @@ struct Device {
   size_t frame_bytes = 0;
   float* radiance = nullptr;
   size_t radiance_bytes = 0;
+  uint2* stack = nullptr;               // traversal stacks of the render kernel (scratch)
+  uint32_t* cold = nullptr;             // cold slot words of the render kernel (scratch)
+  uint32_t stack_warps = 0;
   unsigned long long* queue = nullptr;  // local tile counter
   Counters* counters = nullptr;
   // shared (multi-process) attachments
@@ -319,6 +322,9 @@ static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam
   p.tiles_y = (H + p.tile_h - 1) / p.tile_h;
   p.tile_begin = 0;
   p.tile_stride = 1;
+  p.stack = d.stack;
+  p.cold = d.cold;
+  p.stack_warps = d.stack_warps;
   p.queue = d.queue;
   p.frame = d.frame;
   p.radiance = nullptr;
@@ -476,6 +482,11 @@ int rr_create(const int* cuda_ordinals, int n, rr_ctx** out) {
     if (e == cudaSuccess) e = cudaEventCreate(&d.ev1);
     if (e == cudaSuccess) e = cudaMalloc(&d.queue, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&d.counters, sizeof(Counters));
+    if (e == cudaSuccess) {
+      d.stack_warps = (uint32_t)(prop.multiProcessorCount * render_max_warps_per_sm());
+      e = cudaMalloc(&d.stack, (size_t)d.stack_warps * render_stack_bytes_per_warp());
+      if (e == cudaSuccess) e = cudaMalloc(&d.cold, (size_t)d.stack_warps * render_cold_bytes_per_warp());
+    }
     if (e != cudaSuccess) { rr_destroy(ctx); return cuda_fail(e, "rr_create"); }
     d.sm_count = prop.multiProcessorCount;
   }
@@ -505,7 +516,7 @@ void rr_destroy(rr_ctx* ctx) {
       if (d.shared_queue) cudaIpcCloseMemHandle(d.shared_queue);
       if (d.shared_frame) cudaIpcCloseMemHandle(d.shared_frame);
     }
-    cudaFree(d.frame); cudaFree(d.radiance); cudaFree(d.queue); cudaFree(d.counters);
+    cudaFree(d.frame); cudaFree(d.radiance); cudaFree(d.queue); cudaFree(d.counters); cudaFree(d.stack); cudaFree(d.cold);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
     if (d.stream) cudaStreamDestroy(d.stream);

@@ -13,6 +13,14 @@
 #define RR_DIRECT_MAX 4               // segments this small are tested without a hierarchy
 #define RR_TILE_W 8                   // default work tile: 8 x 4 pixels = one warp
 #define RR_TILE_H 4
+#ifndef RR_POOL
+#define RR_POOL 64        // path slots per warp of the render kernel (rr_render.cu)
+#endif
+#ifndef RR_MIN_CTAS
+#define RR_MIN_CTAS 6     // resident 128-thread CTAs per SM the render kernel is compiled for
+#endif
+#define RR_POOL_WORDS 31  // 32-bit words of one slot in shared memory
+#define RR_COLD_WORDS 22  // ... and in the per-warp global scratch
 
 namespace rr {
 
@@ -107,6 +115,9 @@ struct RenderParams {
   int32_t frame_index;
   uint32_t tile_w, tile_h, tiles_x, tiles_y;
   uint32_t tile_begin, tile_stride;  // static partition: this rank renders tile_begin + k*tile_stride ...
+  uint2* stack;                      // traversal stacks, RR_STACK * RR_POOL entries per warp (scratch)
+  uint32_t* cold;                    // cold slot words, RR_COLD_WORDS * RR_POOL per warp (scratch)
+  uint32_t stack_warps;              // warps the scratch was sized for
   unsigned long long* queue;         // tile counter (may live in a peer GPU's memory)
   uint8_t* frame;                    // RGBA8 (may live in a peer GPU's memory)
   float* radiance;                   // optional, local
@@ -146,6 +157,9 @@ cudaError_t launch_pack_spheres(const rr_sphere* d_sph, const uint32_t* d_order,
 cudaError_t launch_render(const RenderParams& p, bool count_tests, int sm_count, cudaStream_t s);
 cudaError_t launch_primary(const RenderParams& p, int sm_count, cudaStream_t s);
 void default_tuning(Tuning& t);
+size_t render_stack_bytes_per_warp();
+size_t render_cold_bytes_per_warp();
+int render_max_warps_per_sm();
 cudaError_t launch_math_probe(int fn, const float* x, const float* y, float* out, uint64_t n, cudaStream_t s);
 cudaError_t launch_rng_probe(uint32_t pixel, int32_t frame, uint32_t* out_u32, float* out_f32, cudaStream_t s);
 

@@ -259,11 +259,34 @@ __device__ __forceinline__ bool pop_tile(const RenderParams& p, uint32_t& tile) 
   return t < (unsigned long long)p.tiles_x * p.tiles_y;
 }
 
-constexpr int NT = 128;  // threads per CTA (warps are independent: no block-level barrier in the loop)
-enum { ST_IDLE = 0, ST_PIXEL = 1, ST_SHADE = 2, ST_SETUP = 3, ST_TRAV = 4 };
+constexpr int NT = 128;          // threads per CTA (warps are independent: no block-level barrier in the loop)
+constexpr int WARPS = NT / 32;
+constexpr int POOL = RR_POOL;    // path slots per warp (rr_internal.h)
+constexpr int ROUNDS = POOL / 32;
 enum { PH_PIXEL = 0, PH_SHADE = 1, PH_SETUP = 2, PH_TRAV = 3, PH_LEAF = 4 };
-// per-thread words kept in shared memory (word k of thread t at smem[k * NT + t]: conflict-free)
-enum { S_THR = 0, S_INC = 3, S_ACC = 6, S_BP = 9, S_BN = 12, S_LN = 15, S_WINV = 18, S_PD = 21, S_WORDS = 24 };
+// Vote key of a slot: one byte per phase, so that ONE warp reduction (REDUX) over the keys counts the
+// ready slots of every phase.  A slot that needs a pixel has key 0 and W_PIX == PIX_NEED.
+constexpr uint32_t K_T = 1u, K_L = 1u << 8, K_S = 1u << 16, K_H = 1u << 24;
+constexpr int32_t PIX_NEED = -1, PIX_IDLE = -2;
+// Words of one slot.  Hot words live in shared memory (word w of slot s at pool[w * POOL + s]); the words only
+// the shade / pixel phases touch live in a per-warp global scratch with the same layout (cold[w * POOL + s]).
+enum {
+  W_KEY = 0, W_PIX,
+  W_OX, W_OY, W_OZ, W_DX, W_DY, W_DZ,           // world ray
+  W_BDST, W_BMAT, W_BMESH,                      // closest hit so far: distance, material | back << 31, mesh
+  W_CAND, W_M, W_MFLAGS,                        // candidate meshes of the chunk, current mesh (-1: new ray), flags | lback << 31
+  W_LOX, W_LOY, W_LOZ, W_LDX, W_LDY, W_LDZ, W_LIX, W_LIY, W_LIZ,  // mesh-local ray and its reciprocal direction
+  W_LT, W_LPRIM, W_LNX, W_LNY, W_LNZ,           // closest hit inside the current mesh
+  W_CUR, W_SPC, W_PSLOT,                        // traversal: node ref, stack pointer | postponed count << 8, postponed slot
+  NW
+};
+enum {
+  C_RNG = 0, C_SAMPLE, C_BOUNCE,                // bounce | passes << 16
+  C_BPRIM, C_BPX, C_BPY, C_BPZ, C_BNX, C_BNY, C_BNZ,  // primitive, point and normal of the closest hit
+  C_THR, C_THR1, C_THR2, C_INC, C_INC1, C_INC2, C_ACC, C_ACC1, C_ACC2, C_PD, C_PD1, C_PD2,
+  NC
+};
+static_assert(NW == RR_POOL_WORDS && NC == RR_COLD_WORDS, "rr_internal.h RR_POOL_WORDS / RR_COLD_WORDS");
 // Node references.  In the packed nodes a leaf is -(slot + 2), so that "inner node or pop" is cur >= -1.
 constexpr int32_t REF_POP = -1;                   // take the next entry of the stack
 constexpr int32_t REF_END = (int32_t)0x80000000;  // traversal of this mesh finished
@@ -271,39 +294,32 @@ __device__ __forceinline__ bool ref_is_leaf(int32_t r) { return r < REF_POP && r
 __device__ __forceinline__ uint32_t ref_slot(int32_t r) { return (uint32_t)(-r) - 2u; }
 
 template <bool COUNT, bool PRIMARY>
-__global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
-  __shared__ float smem[S_WORDS * NT];
-#define SM(k) smem[(k) * NT + threadIdx.x]
-#define SM_ST3(k, v) do { SM(k) = (v).x; SM((k) + 1) = (v).y; SM((k) + 2) = (v).z; } while (0)
-#define SM_LD3(k) mk(SM(k), SM((k) + 1), SM((k) + 2))
+__global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p) {
+  extern __shared__ uint32_t pool_all[];
   const unsigned lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
   const unsigned full = 0xffffffffu;
+  const unsigned lanes_below = (1u << lane) - 1u;
+  uint32_t* const pool = pool_all + warp * (NW * POOL + 32);
+  uint32_t* const sel = pool + NW * POOL;  // slot picked for each lane in the current phase
+  uint2* const stack = p.stack + (size_t)(blockIdx.x * WARPS + warp) * (RR_STACK * POOL);  // [depth][slot]
+  uint32_t* const cold = p.cold + (size_t)(blockIdx.x * WARPS + warp) * (NC * POOL);
+#define CW(w, s) cold[(w) * POOL + (s)]
+#define CF(w, s) __uint_as_float(cold[(w) * POOL + (s)])
+#define CSF(w, s, v) cold[(w) * POOL + (s)] = __float_as_uint(v)
+#define CLD3(w, s) mk(CF(w, s), CF((w) + 1, s), CF((w) + 2, s))
+#define CST3(w, s, v) do { CSF(w, s, (v).x); CSF((w) + 1, s, (v).y); CSF((w) + 2, s, (v).z); } while (0)
+#define PW(w, s) pool[(w) * POOL + (s)]
+#define PF(w, s) __uint_as_float(pool[(w) * POOL + (s)])
+#define PSF(w, s, v) pool[(w) * POOL + (s)] = __float_as_uint(v)
+#define PLD3(w, s) mk(PF(w, s), PF((w) + 1, s), PF((w) + 2, s))
+#define PST3(w, s, v) do { PSF(w, s, (v).x); PSF((w) + 1, s, (v).y); PSF((w) + 2, s, (v).z); } while (0)
   const V3 cam_pos = mk(p.cam.pos[0], p.cam.pos[1], p.cam.pos[2]);
-  // traversal stack (local memory; interleaved per lane by the hardware)
-  int32_t stackN[RR_STACK];
-  float stackD[RR_STACK];
-  // warp-uniform tile state
+  // warp-uniform state
   bool queue_empty = false;
   uint32_t tile_x0 = 0, tile_y0 = 0, tile_w = 1, tile_next = 0, tile_pixels = 0;
-  // lane state
-  int state = ST_PIXEL;
-  int32_t pix = -1;
-  uint32_t rng = 0, sample = 0, bounce = 0, passes = 0;
-  V3 origin = cam_pos, dir = mk(0, 0, 1);
-  float best_dst = INFINITY;
-  int32_t best_mat = 0, best_mesh = 0x7fffffff, best_prim = -1;
-  bool best_back = false;
-  uint32_t cand = 0;     // candidate meshes of the current 32-mesh chunk (bit k = mesh cand_base + k) not yet visited
-  int32_t cand_base = 0;
-  int m = 0;
-  uint32_t mflags = 0;
-  V3 lo = origin, ld = dir, linv = dir, lnoi = dir;
-  float lt = INFINITY;
-  int32_t lprim = NO_PRIM;
-  bool lback = false;
-  int32_t cur = REF_END;
-  int sp = 0;
-  uint32_t pend_slot = 0, pend_cnt = 0;
+  uint32_t n_need = POOL;  // slots waiting for a pixel
+  uint32_t round = 0;
   // statistics
   unsigned long long n_rays = 0, n_tiles = 0;
   unsigned c_box = 0, c_tri = 0, c_sph = 0;
@@ -313,6 +329,55 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
                  wT = p.tune.weight[PH_TRAV], wL = p.tune.weight[PH_LEAF];
   const uint32_t trav_keep = p.tune.trav_keep;
   const bool speculate = p.tune.speculate != 0;
+
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    PW(W_KEY, lane + 32 * r) = 0u;
+    PW(W_PIX, lane + 32 * r) = (uint32_t)PIX_NEED;
+  }
+  __syncwarp();
+
+  // ---- per-slot working set of a phase (loaded from / stored to the pool by the phase) ----
+  int s = -1;  // the slot this lane works on
+  int32_t pix = 0;
+  uint32_t rng = 0, sample = 0, bounce = 0, passes = 0;
+  V3 origin = cam_pos, dir = mk(0, 0, 1);
+  float best_dst = INFINITY;
+  int32_t best_mat = 0, best_mesh = 0x7fffffff, best_prim = -1;
+  bool best_back = false;
+  uint32_t cand = 0;  // candidate meshes of the current 32-mesh chunk (bit k = mesh (m & ~31) + k) not yet visited
+  int m = 0;
+  uint32_t mflags = 0;
+  V3 lo = origin, ld = dir, linv = dir, lnoi = dir;
+  float lt = INFINITY;
+  int32_t lprim = NO_PRIM;
+  bool lback = false;
+  int32_t cur = REF_END;
+  int sp = 0;
+  uint32_t pend_slot = 0, pend_cnt = 0;
+
+  // Up to 32 slots with `ready` set are handed to the lanes (lane j gets the j-th ready slot); returns how many.
+  auto select = [&](const bool (&ready)[ROUNDS]) -> int {
+    __syncwarp();
+    int base = 0;
+#pragma unroll
+    for (int q = 0; q < ROUNDS; ++q) {
+      const int r = (q + (int)(round % ROUNDS)) % ROUNDS;  // rotate which part of the pool is served first
+      const unsigned b = __ballot_sync(full, ready[r]);
+      const int rank = base + __popc(b & lanes_below);
+      if (ready[r] && rank < 32) sel[rank] = lane + 32 * r;
+      base += __popc(b);
+    }
+    __syncwarp();
+    const int n = min(base, 32);
+    s = (int)lane < n ? (int)sel[lane] : -1;
+    return n;
+  };
+  auto trav_key = [&]() -> uint32_t {
+    if (cur == REF_END && pend_cnt == 0)  // mesh done: more candidates -> setup, none -> shade (which finishes the mesh itself)
+      return (cand != 0 || (m & ~31) + 32 <= p.last_mesh) ? K_S : K_H;
+    return ((cur >= REF_POP && (speculate || pend_cnt == 0)) ? K_T : 0u) | (pend_cnt ? K_L : 0u);
+  };
 
   // World-box tests of the meshes [base, base + 32): bit k set = the ray enters mesh base + k's box before `tmax`.
   // Every lane walks the whole chunk, so the loop is convergent.
@@ -326,27 +391,17 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
       const bool hit = box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, tmax, tn);
       if (hit && !(__float_as_uint(wlo.w) & RR_MF_SKIP)) mask |= 1u << (k - base);
     }
-    if (COUNT) c_box += (unsigned)(end - base);
+    if (COUNT) c_box += (unsigned)max(end - base, 0);
     return mask;
   };
   // A new ray starts: reset the closest hit (src/Trace.cl:437-444) and collect the candidate meshes.
-  auto begin_ray = [&]() {
+  auto begin_ray = [&](const V3& winv, const V3& wnoi) {
     best_dst = INFINITY; best_mat = 0; best_mesh = 0x7fffffff; best_prim = -1; best_back = false;
     lprim = NO_PRIM;
-    const V3 winv = mk(rcp_approx(dir.x), rcp_approx(dir.y), rcp_approx(dir.z));
-    SM_ST3(S_WINV, winv);
-    const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
-    cand_base = 0;
+    m = 0;
     cand = scan_meshes(0, winv, wnoi, INFINITY);
+    cur = REF_END; sp = 0; pend_cnt = 0; pend_slot = 0;
     n_rays++;
-    state = ST_SETUP;
-  };
-  auto begin_path = [&]() {  // src/Trace.cl:488-491
-    bounce = 0; passes = 0;
-    origin = cam_pos;
-    dir = SM_LD3(S_PD);
-    SM(S_THR) = 1.0f; SM(S_THR + 1) = 1.0f; SM(S_THR + 2) = 1.0f;
-    SM(S_INC) = 0.0f; SM(S_INC + 1) = 0.0f; SM(S_INC + 2) = 0.0f;
   };
   // The mesh just traversed has a closest hit (local space): LocalToWorldHit and the keep-min of
   // src/Trace.cl:465-481.  Meshes are visited in our own order, so equal distances are resolved by the
@@ -361,42 +416,43 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
       if (!(type == RR_MATERIAL_ONESIDED && lback) && (lt < best_dst || (lt == best_dst && mesh_index < best_mesh))) {
         best_dst = lt; best_mat = mat; best_back = lback; best_mesh = mesh_index; best_prim = lprim;
         const V3 wp = origin + dir * lt;
-        SM_ST3(S_BP, wp);
-        SM(S_BN) = SM(S_LN); SM(S_BN + 1) = SM(S_LN + 1); SM(S_BN + 2) = SM(S_LN + 2);
+        CST3(C_BPX, s, wp);
+        CW(C_BNX, s) = PW(W_LNX, s); CW(C_BNY, s) = PW(W_LNY, s); CW(C_BNZ, s) = PW(W_LNZ, s);
       }
     } else {
-      const int32_t type = (int32_t)(mflags >> RR_MF_TYPE_SHIFT);
+      const int32_t type = (int32_t)((mflags >> RR_MF_TYPE_SHIFT) & 0xffu);
       if (!(type == RR_MATERIAL_ONESIDED && lback)) {
         // LocalToWorldHit, src/Trace.cl:139-156
         const float4 r0 = __ldg(&M->r0), r1 = __ldg(&M->r1), r2 = __ldg(&M->r2);
         const V3 pos = mk(__ldg(&M->ri0.w), __ldg(&M->ri1.w), __ldg(&M->ri2.w));
         const V3 lp = (lo + ld * lt) * r0.w;
         const V3 wp = mk(dot(xyz(r0), lp), dot(xyz(r1), lp), dot(xyz(r2), lp)) + pos;
-        const V3 ln = SM_LD3(S_LN);
+        const V3 ln = PLD3(W_LNX, s);
         const V3 wn = normalize(mk(dot(xyz(r0), ln), dot(xyz(r1), ln), dot(xyz(r2), ln)));
         const float wd = length(wp - origin);
         if (wd < best_dst || (wd == best_dst && mesh_index < best_mesh)) {
           best_dst = wd; best_mat = mesh_index; best_back = lback; best_mesh = mesh_index; best_prim = lprim;
-          SM_ST3(S_BP, wp);
-          SM_ST3(S_BN, wn);
+          CST3(C_BPX, s, wp);
+          CST3(C_BNX, s, wn);
         }
       }
     }
     lprim = NO_PRIM;
   };
   // Enters the next candidate mesh (src/Trace.cl:444-463): world box against the closest hit so far,
-  // WorldToLocalRay, root box; ST_TRAV when a traversal starts, ST_SHADE when no candidate is left.
-  auto enter_next_mesh = [&](const V3& winv, const V3& wnoi) {
+  // WorldToLocalRay, root box.  Returns the slot's new key (traversal started, or K_H: no candidate left).
+  auto enter_next_mesh = [&](const V3& winv, const V3& wnoi) -> uint32_t {
     for (;;) {
       if (cand == 0) {
-        if (cand_base + 32 > p.last_mesh) { state = ST_SHADE; return; }
-        cand_base += 32;
-        cand = scan_meshes(cand_base, winv, wnoi, best_dst);
+        const int32_t base = (m & ~31) + 32;
+        if (base > p.last_mesh) return K_H;
+        m = base;
+        cand = scan_meshes(base, winv, wnoi, best_dst);
         continue;
       }
       const int k = __ffs((int)cand) - 1;
       cand &= cand - 1u;
-      m = cand_base + k;
+      m = (m & ~31) + k;
       const DMesh* M = p.meshes + m;
       float tn;
       if (best_dst < INFINITY) {  // a hit exists: the box may now lie behind it
@@ -440,55 +496,117 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
         pend_cnt = 0;
         cur = (int32_t)first;  // root node
       }
-      state = ST_TRAV;
-      return;
+      return trav_key();
     }
   };
-  // after the last node / leaf of a mesh: more candidates -> setup phase, none -> shade phase (which
-  // finishes the mesh itself)
-  auto leave_mesh = [&]() { state = (cand != 0 || cand_base + 32 <= p.last_mesh) ? ST_SETUP : ST_SHADE; };
+  // what setup and shade write back after finish_mesh / enter_next_mesh
+  auto store_ray_state = [&](uint32_t key) {
+    PSF(W_BDST, s, best_dst);
+    PW(W_BMAT, s) = (uint32_t)best_mat | (best_back ? 0x80000000u : 0u);
+    PW(W_BMESH, s) = (uint32_t)best_mesh;
+    if (PRIMARY) CW(C_BPRIM, s) = (uint32_t)best_prim;
+    PW(W_CAND, s) = cand;
+    PW(W_M, s) = (uint32_t)m;
+    PW(W_MFLAGS, s) = (mflags & 0x7fffffffu) | (lback ? 0x80000000u : 0u);
+    PST3(W_LOX, s, lo);
+    PST3(W_LDX, s, ld);
+    PST3(W_LIX, s, linv);
+    PSF(W_LT, s, lt);
+    PW(W_LPRIM, s) = (uint32_t)lprim;
+    PW(W_CUR, s) = (uint32_t)cur;
+    PW(W_SPC, s) = (uint32_t)sp | (pend_cnt << 8);
+    PW(W_PSLOT, s) = pend_slot;
+    PW(W_KEY, s) = key;
+  };
+  auto load_ray_state = [&]() {
+    best_dst = PF(W_BDST, s);
+    const uint32_t bm = PW(W_BMAT, s);
+    best_mat = (int32_t)(bm & 0x7fffffffu);
+    best_back = (bm >> 31) != 0u;
+    best_mesh = (int32_t)PW(W_BMESH, s);
+    if (PRIMARY) best_prim = (int32_t)CW(C_BPRIM, s);
+    cand = PW(W_CAND, s);
+    const uint32_t mf = PW(W_MFLAGS, s);
+    mflags = mf & 0x7fffffffu;
+    lback = (mf >> 31) != 0u;
+    lo = PLD3(W_LOX, s);
+    ld = PLD3(W_LDX, s);
+    lt = PF(W_LT, s);
+    lprim = (int32_t)PW(W_LPRIM, s);
+  };
+  // shade / pixel hand the new ray to the setup phase: W_M = -1 marks "collect the candidates first"
+  auto store_new_ray = [&]() {
+    PST3(W_OX, s, origin);
+    PST3(W_DX, s, dir);
+    PW(W_M, s) = 0xffffffffu;
+    PW(W_KEY, s) = K_S;
+  };
 
   for (;;) {
-    // ---- vote: one REDUX over 6-bit fields counts the ready lanes of every phase ----
+    // ---- vote: one REDUX over the byte-packed keys counts the ready slots of every phase ----
+    __syncwarp();  // the slots written by the previous phase are visible to every lane
+    uint32_t ksum = 0;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) ksum += PW(W_KEY, lane + 32 * r);
+    const uint32_t counts = __reduce_add_sync(full, ksum);
     const bool more_pixels = !(queue_empty && tile_next >= tile_pixels);
-    uint32_t key = 0;
-    if (state == ST_TRAV) {
-      key = ((cur >= REF_POP && (speculate || pend_cnt == 0)) ? 1u << (6 * PH_TRAV) : 0u) | (pend_cnt ? 1u << (6 * PH_LEAF) : 0u);
-    } else if (state == ST_SETUP) key = 1u << (6 * PH_SETUP);
-    else if (state == ST_SHADE) key = 1u << (6 * PH_SHADE);
-    else if (state == ST_PIXEL && more_pixels) key = 1u << (6 * PH_PIXEL);
-    const uint32_t counts = __reduce_add_sync(full, key);
-    if (counts == 0) break;
-    const uint32_t nP = counts & 63u, nH = (counts >> 6) & 63u, nS = (counts >> 12) & 63u, nT = (counts >> 18) & 63u,
-                   nL = (counts >> 24) & 63u;
+    const uint32_t nP = more_pixels ? n_need : 0u;
+    if (counts == 0 && nP == 0) break;
+    const uint32_t nT = min(counts & 0xffu, 32u), nL = min((counts >> 8) & 0xffu, 32u), nS = min((counts >> 16) & 0xffu, 32u),
+                   nH = min(counts >> 24, 32u);
     int phase = PH_TRAV;
     uint32_t best = nT * wT;
     if (nL * wL > best) { best = nL * wL; phase = PH_LEAF; }
     if (nS * wS > best) { best = nS * wS; phase = PH_SETUP; }
     if (nH * wH > best) { best = nH * wH; phase = PH_SHADE; }
-    if (nP * wP > best) { best = nP * wP; phase = PH_PIXEL; }
-    if (COUNT && phase != PH_TRAV) {
-      ph_runs[phase]++;
-      ph_lanes[phase] += phase == PH_LEAF ? nL : phase == PH_SETUP ? nS : phase == PH_SHADE ? nH : nP;
-    }
+    if (min(nP, 32u) * wP > best) { best = min(nP, 32u) * wP; phase = PH_PIXEL; }
+    round++;
 
     if (phase == PH_TRAV) {
       // ================= node steps =================
-      uint32_t active = nT;
-      do {
-        if (COUNT) { ph_runs[PH_TRAV]++; ph_lanes[PH_TRAV] += active; }
-        if (state == ST_TRAV && cur >= REF_POP && (speculate || pend_cnt == 0)) {
-          if (cur == REF_POP) {  // one stack entry per step, in lock-step with the other lanes
-            if (sp > 0) {
+      bool ready[ROUNDS];
+#pragma unroll
+      for (int r = 0; r < ROUNDS; ++r) ready[r] = (PW(W_KEY, lane + 32 * r) & K_T) != 0u;
+      select(ready);
+      const bool mine = s >= 0;
+      if (mine) {
+        cur = (int32_t)PW(W_CUR, s);
+        const uint32_t spc = PW(W_SPC, s);
+        sp = (int)(spc & 0xffu);
+        pend_cnt = spc >> 8;
+        pend_slot = PW(W_PSLOT, s);
+        lt = PF(W_LT, s);
+        lo = PLD3(W_LOX, s);
+        linv = PLD3(W_LIX, s);
+        lnoi = mk(-(lo.x * linv.x), -(lo.y * linv.y), -(lo.z * linv.z));
+      } else {
+        cur = REF_END; sp = 0; pend_cnt = 0;
+      }
+      uint2* const stk = stack + (mine ? s : 0);
+      // Pops the stack / postpones leaves until `cur` is an inner node, a leaf the slot must wait for, or REF_END.
+      auto resolve = [&](int32_t next) {
+        for (;;) {
+          if (next == REF_POP) {
+            bool found = false;
+            while (sp > 0) {
               --sp;
-              const float d = stackD[sp];
-              const int32_t n = stackN[sp];
-              cur = d <= lt ? n : REF_POP;
-              if (ref_is_leaf(cur) && pend_cnt == 0) { pend_slot = ref_slot(cur); pend_cnt = 1; cur = REF_POP; }
-            } else {
-              cur = REF_END;
+              const uint2 e = stk[sp * POOL];
+              if (__uint_as_float(e.y) <= lt) { next = (int32_t)e.x; found = true; break; }
             }
+            if (!found) { cur = REF_END; break; }
           }
+          if (next >= 0) { cur = next; break; }
+          if (pend_cnt == 0) { pend_slot = ref_slot(next); pend_cnt = 1; next = REF_POP; continue; }
+          cur = next;  // a second leaf while one is postponed: wait for the leaf phase
+          break;
+        }
+      };
+      uint32_t active;
+      do {
+        const bool step = mine && cur >= REF_POP && (speculate || pend_cnt == 0);
+        if (COUNT) { ph_runs[PH_TRAV]++; ph_lanes[PH_TRAV] += __popc(__ballot_sync(full, step)); }
+        if (step) {
+          if (cur == REF_POP) resolve(REF_POP);
           if (cur >= 0) {
             const float4* nd = p.nodes + 4 * (size_t)cur;
             const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
@@ -509,24 +627,49 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
                   next = farRef;
                 }
               } else {
-                if (sp < RR_STACK) { stackN[sp] = farRef; stackD[sp] = aNear ? tB : tA; sp++; }
+                if (sp < RR_STACK) { stk[sp * POOL] = make_uint2((uint32_t)farRef, __float_as_uint(aNear ? tB : tA)); sp++; }
                 next = nearRef;
               }
             } else if (hA) next = L;
             else if (hB) next = R;
-            if (next < REF_POP && pend_cnt == 0) { pend_slot = ref_slot(next); pend_cnt = 1; next = REF_POP; }
-            cur = next;
+            resolve(next);
           }
-          if (cur == REF_END && pend_cnt == 0) leave_mesh();
         }
-        active = __popc(__ballot_sync(full, state == ST_TRAV && cur >= REF_POP && (speculate || pend_cnt == 0)));
+        active = __popc(__ballot_sync(full, mine && cur >= REF_POP && (speculate || pend_cnt == 0)));
       } while (active >= trav_keep);
+      if (mine) {
+        PW(W_CUR, s) = (uint32_t)cur;
+        PW(W_SPC, s) = (uint32_t)sp | (pend_cnt << 8);
+        PW(W_PSLOT, s) = pend_slot;
+        cand = PW(W_CAND, s);
+        m = (int)PW(W_M, s);
+        PW(W_KEY, s) = trav_key();
+      }
     } else if (phase == PH_LEAF) {
       // ================= leaf tests =================
-      if (state == ST_TRAV && pend_cnt > 0) {
+      bool ready[ROUNDS];
+#pragma unroll
+      for (int r = 0; r < ROUNDS; ++r) ready[r] = (PW(W_KEY, lane + 32 * r) & K_L) != 0u;
+      const int n = select(ready);
+      if (COUNT) { ph_runs[PH_LEAF]++; ph_lanes[PH_LEAF] += n; }
+      if (s >= 0) {
+        cur = (int32_t)PW(W_CUR, s);
+        const uint32_t spc = PW(W_SPC, s);
+        sp = (int)(spc & 0xffu);
+        pend_cnt = spc >> 8;
+        pend_slot = PW(W_PSLOT, s);
+        lt = PF(W_LT, s);
+        lprim = (int32_t)PW(W_LPRIM, s);
+        lo = PLD3(W_LOX, s);
+        ld = PLD3(W_LDX, s);
+        const uint32_t mf = PW(W_MFLAGS, s);
+        mflags = mf & 0x7fffffffu;
+        lback = (mf >> 31) != 0u;
         const uint32_t slot = pend_slot;
         pend_slot++;
         pend_cnt--;
+        bool accepted = false;
+        V3 n3 = mk(0, 0, 0);
         if (mflags & RR_MF_SPHERES) {
           // EXTENSION (the reference kernel has no sphere primitive): semantics of oracle/rr_oracle.c ray_sphere
           if (COUNT) c_sph++;
@@ -548,10 +691,10 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
               const bool cull = (mtype != RR_MATERIAL_GLASSY && mtype != RR_MATERIAL_INVISIBLE && mtype != RR_MATERIAL_ONESIDED);
               if (!(back && cull)) {
                 const V3 hp = lo + ld * t;
-                V3 n = (hp - c) / r;
-                if (back) n = -n;
+                n3 = (hp - c) / r;
+                if (back) n3 = -n3;
                 lt = t; lprim = prim; lback = back;
-                SM_ST3(S_LN, n);
+                accepted = true;
               }
             }
           }
@@ -566,10 +709,10 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
           const float a = dot(edge1, h);
           if (!(fabsf(a) < RR_EPSILON)) {
             const float f = 1.0f / a;
-            const V3 s = lo - A;
-            const float u = f * dot(s, h);
+            const V3 sv = lo - A;
+            const float u = f * dot(sv, h);
             if (!(u < 0.0f || u > 1.0f)) {
-              const V3 q = cross(s, edge1);
+              const V3 q = cross(sv, edge1);
               const float v = f * dot(ld, q);
               if (!(v < 0.0f || u + v > 1.0f)) {
                 const float t = f * dot(edge2, q);
@@ -577,66 +720,104 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
                 if (t > RR_EPSILON && (t < lt || (t == lt && lprim != NO_PRIM && prim < lprim))) {
                   const float4* np = p.tri_nrm + 3 * (size_t)slot;
                   const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
-                  V3 n = normalize(xyz(n0) * (1.0f - u - v) + xyz(n1) * u + xyz(n2) * v);
+                  n3 = normalize(xyz(n0) * (1.0f - u - v) + xyz(n1) * u + xyz(n2) * v);
                   bool back = false;
                   bool ok = true;
-                  if (dot(ld, n) > RR_EPSILON) {
+                  if (dot(ld, n3) > RR_EPSILON) {
                     if (mflags & RR_MF_CULL) ok = false;
                     back = true;
-                    n = -n;
+                    n3 = -n3;
                   }
                   if (ok) {
                     lt = t; lprim = prim; lback = back;
-                    SM_ST3(S_LN, n);
+                    accepted = true;
                   }
                 }
               }
             }
           }
         }
-        if (pend_cnt == 0) {
-          if (ref_is_leaf(cur)) {  // the leaf this lane was waiting on becomes the postponed one
-            pend_slot = ref_slot(cur);
-            pend_cnt = 1;
-            cur = REF_POP;
-          } else if (cur == REF_END) {
-            leave_mesh();
-          }
+        if (accepted) {
+          PSF(W_LT, s, lt);
+          PW(W_LPRIM, s) = (uint32_t)lprim;
+          PW(W_MFLAGS, s) = mflags | (lback ? 0x80000000u : 0u);
+          PST3(W_LNX, s, n3);
         }
+        if (pend_cnt == 0 && ref_is_leaf(cur)) {  // the leaf this slot was waiting on becomes the postponed one
+          pend_slot = ref_slot(cur);
+          pend_cnt = 1;
+          cur = REF_POP;
+          PW(W_CUR, s) = (uint32_t)cur;
+        }
+        PW(W_SPC, s) = (uint32_t)sp | (pend_cnt << 8);
+        PW(W_PSLOT, s) = pend_slot;
+        cand = PW(W_CAND, s);
+        m = (int)PW(W_M, s);
+        PW(W_KEY, s) = trav_key();
       }
     } else if (phase == PH_SETUP) {
       // ================= finish the current mesh, enter the next candidate (src/Trace.cl:444-482) =================
-      if (state == ST_SETUP) {
-        finish_mesh();
-        const V3 winv = SM_LD3(S_WINV);
+      bool ready[ROUNDS];
+#pragma unroll
+      for (int r = 0; r < ROUNDS; ++r) ready[r] = (PW(W_KEY, lane + 32 * r) & K_S) != 0u;
+      const int n = select(ready);
+      if (COUNT) { ph_runs[PH_SETUP]++; ph_lanes[PH_SETUP] += n; }
+      if (s >= 0) {
+        origin = PLD3(W_OX, s);
+        dir = PLD3(W_DX, s);
+        m = (int)PW(W_M, s);
+        const V3 winv = mk(rcp_approx(dir.x), rcp_approx(dir.y), rcp_approx(dir.z));
         const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
-        enter_next_mesh(winv, wnoi);
+        if (m < 0) {
+          begin_ray(winv, wnoi);
+        } else {
+          load_ray_state();
+          finish_mesh();
+        }
+        const uint32_t key = enter_next_mesh(winv, wnoi);
+        store_ray_state(key);
       }
     } else if (phase == PH_SHADE) {
       // ================= one bounce of Trace() (src/Trace.cl:497-591) and the sample loop (:639-642) =================
-      if (state == ST_SHADE) {
+      bool ready[ROUNDS];
+#pragma unroll
+      for (int r = 0; r < ROUNDS; ++r) ready[r] = (PW(W_KEY, lane + 32 * r) & K_H) != 0u;
+      const int n = select(ready);
+      if (COUNT) { ph_runs[PH_SHADE]++; ph_lanes[PH_SHADE] += n; }
+      bool pixel_done = false;
+      if (s >= 0) {
+        origin = PLD3(W_OX, s);
+        dir = PLD3(W_DX, s);
+        m = (int)PW(W_M, s);
+        load_ray_state();
         finish_mesh();
+        pix = (int32_t)PW(W_PIX, s);
         if (PRIMARY) {
           if (p.hit_mesh) p.hit_mesh[pix] = best_dst < INFINITY ? best_mesh : -1;
           if (p.hit_prim) p.hit_prim[pix] = best_dst < INFINITY ? best_prim : -1;
           if (p.hit_dst) p.hit_dst[pix] = best_dst < INFINITY ? best_dst : 0.0f;
-          state = ST_PIXEL;
+          pixel_done = true;
         } else {
+          rng = CW(C_RNG, s);
+          sample = CW(C_SAMPLE, s);
+          const uint32_t bw = CW(C_BOUNCE, s);
+          bounce = bw & 0xffffu;
+          passes = bw >> 16;
           SceneHit hit;
           hit.did = best_dst < INFINITY;
           hit.dst = best_dst;
-          hit.point = SM_LD3(S_BP);
-          hit.normal = SM_LD3(S_BN);
+          hit.point = CLD3(C_BPX, s);
+          hit.normal = CLD3(C_BNX, s);
           hit.back = best_back;
           hit.material = best_mat;
-          V3 throughput = SM_LD3(S_THR), incoming = SM_LD3(S_INC);
+          V3 throughput = CLD3(C_THR, s), incoming = CLD3(C_INC, s);
           bool alive = shade(p, hit, origin, dir, throughput, incoming, bounce, passes, rng);
           alive = alive && bounce < p.max_bounces;
           if (alive) {
-            SM_ST3(S_THR, throughput);
-            SM_ST3(S_INC, incoming);
+            CST3(C_THR, s, throughput);
+            CST3(C_INC, s, incoming);
           } else {  // path finished: src/Trace.cl:639-642
-            const V3 accum = SM_LD3(S_ACC) + incoming;
+            const V3 accum = CLD3(C_ACC, s) + incoming;
             sample++;
             if (sample >= p.spp) {
               const V3 c = accum / (float)p.spp;
@@ -646,23 +827,36 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
                 p.radiance[3 * (size_t)pix + 1] = c.y;
                 p.radiance[3 * (size_t)pix + 2] = c.z;
               }
-              state = ST_PIXEL;
+              pixel_done = true;
             } else {
-              SM_ST3(S_ACC, accum);
-              begin_path();
+              CST3(C_ACC, s, accum);
+              bounce = 0; passes = 0;  // next sample of this pixel: src/Trace.cl:488-491
+              origin = cam_pos;
+              dir = CLD3(C_PD, s);
+              CSF(C_THR, s, 1.0f); CSF(C_THR1, s, 1.0f); CSF(C_THR2, s, 1.0f);
+              CSF(C_INC, s, 0.0f); CSF(C_INC1, s, 0.0f); CSF(C_INC2, s, 0.0f);
             }
           }
-          if (state != ST_PIXEL) {  // next segment: candidates, then straight into its first mesh
-            begin_ray();
-            const V3 winv = SM_LD3(S_WINV);
-            const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
-            enter_next_mesh(winv, wnoi);
-          }
+        }
+        if (pixel_done) {
+          PW(W_KEY, s) = 0u;
+          PW(W_PIX, s) = (uint32_t)PIX_NEED;
+        } else {  // next segment: the setup phase collects its candidate meshes
+          CW(C_RNG, s) = rng;
+          CW(C_SAMPLE, s) = sample;
+          CW(C_BOUNCE, s) = bounce | (passes << 16);
+          store_new_ray();
         }
       }
+      n_need += __popc(__ballot_sync(full, pixel_done));
     } else {
-      // ================= hand a pixel to every lane that needs one =================
-      bool need = state == ST_PIXEL;
+      // ================= hand a pixel to every slot that needs one =================
+      bool ready[ROUNDS];
+#pragma unroll
+      for (int r = 0; r < ROUNDS; ++r) ready[r] = (int32_t)PW(W_PIX, lane + 32 * r) == PIX_NEED;
+      const int n = select(ready);
+      if (COUNT) { ph_runs[PH_PIXEL]++; ph_lanes[PH_PIXEL] += n; }
+      bool need = s >= 0;
       while (__any_sync(full, need)) {
         if (tile_next >= tile_pixels) {
           if (queue_empty) break;
@@ -676,7 +870,7 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
           tile_next = 0;
         }
         const unsigned mb = __ballot_sync(full, need);
-        const unsigned rank = __popc(mb & ((1u << lane) - 1u));
+        const unsigned rank = __popc(mb & lanes_below);
         const uint32_t k = tile_next + rank;
         if (need && k < tile_pixels) {
           const uint32_t x = tile_x0 + k % tile_w, y = tile_y0 + k / tile_w;
@@ -685,24 +879,38 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
             reinterpret_cast<uint32_t*>(p.frame)[pix] = tonemap_rgba(mk(0, 0, 0));
             if (p.radiance) { p.radiance[3 * (size_t)pix] = 0.0f; p.radiance[3 * (size_t)pix + 1] = 0.0f; p.radiance[3 * (size_t)pix + 2] = 0.0f; }
           } else {
-            rng = make_seed((uint32_t)pix, p.frame_index, 0u);          // src/Trace.cl:631-632
-            const V3 pd = primary_dir(p.cam, x, y, p.width, p.height);  // once per pixel, :634-636
-            SM_ST3(S_PD, pd);
-            SM(S_ACC) = 0.0f; SM(S_ACC + 1) = 0.0f; SM(S_ACC + 2) = 0.0f;
-            sample = 0;
-            begin_path();
-            begin_ray();  // -> ST_SETUP
+            PW(W_PIX, s) = (uint32_t)pix;
+            CW(C_RNG, s) = make_seed((uint32_t)pix, p.frame_index, 0u);  // src/Trace.cl:631-632
+            const V3 pd = primary_dir(p.cam, x, y, p.width, p.height);   // once per pixel, :634-636
+            CST3(C_PD, s, pd);
+            CSF(C_ACC, s, 0.0f); CSF(C_ACC1, s, 0.0f); CSF(C_ACC2, s, 0.0f);
+            CW(C_SAMPLE, s) = 0u;
+            CW(C_BOUNCE, s) = 0u;
+            CSF(C_THR, s, 1.0f); CSF(C_THR1, s, 1.0f); CSF(C_THR2, s, 1.0f);
+            CSF(C_INC, s, 0.0f); CSF(C_INC1, s, 0.0f); CSF(C_INC2, s, 0.0f);
+            origin = cam_pos;
+            dir = pd;
+            store_new_ray();
             need = false;
           }
         }
         tile_next += __popc(mb);
       }
-      if (need) state = ST_IDLE;  // the queue is empty
+      const bool got = s >= 0 && !need;
+      n_need -= __popc(__ballot_sync(full, got));
+      if (need) PW(W_PIX, s) = (uint32_t)PIX_IDLE;  // the queue is empty
     }
   }
-#undef SM
-#undef SM_ST3
-#undef SM_LD3
+#undef CW
+#undef CF
+#undef CSF
+#undef CLD3
+#undef CST3
+#undef PW
+#undef PF
+#undef PSF
+#undef PLD3
+#undef PST3
   // counters: one atomic per warp
   unsigned long long r = n_rays;
 #pragma unroll
@@ -712,17 +920,17 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
     atomicAdd(&p.counters->tiles, n_tiles);
   }
   if (COUNT) {
-    unsigned long long b = c_box, t = c_tri, s = c_sph;
+    unsigned long long b = c_box, t = c_tri, sq = c_sph;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       b += __shfl_xor_sync(full, b, off);
       t += __shfl_xor_sync(full, t, off);
-      s += __shfl_xor_sync(full, s, off);
+      sq += __shfl_xor_sync(full, sq, off);
     }
     if (lane == 0) {
       atomicAdd(&p.counters->box_tests, b);
       atomicAdd(&p.counters->tri_tests, t);
-      atomicAdd(&p.counters->sphere_tests, s);
+      atomicAdd(&p.counters->sphere_tests, sq);
       for (int k = 0; k < 5; ++k) {
         atomicAdd(&p.counters->phase_runs[k], (unsigned long long)ph_runs[k]);
         atomicAdd(&p.counters->phase_lanes[k], (unsigned long long)ph_lanes[k]);
@@ -733,38 +941,44 @@ __global__ void __launch_bounds__(NT, 8) k_render(const RenderParams p) {
 
 void default_tuning(Tuning& t) {
   for (int k = 0; k < 5; ++k) t.weight[k] = 4;
-  t.trav_keep = 12;
+  t.trav_keep = 22;
   t.speculate = 1;
   t.ctas_per_sm = 0;
 }
 
-static int resident_ctas(const void* fn, const RenderParams& p) {
+constexpr size_t RENDER_SMEM = (size_t)WARPS * (NW * POOL + 32) * sizeof(uint32_t);
+
+template <class K>
+static cudaError_t launch_persistent(K kernel, const RenderParams& p, int sm_count, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RENDER_SMEM);
+  if (e != cudaSuccess) return e;
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, NT, 0) != cudaSuccess || n < 1) n = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, NT, RENDER_SMEM);
+  if (e != cudaSuccess) return e;
+  if (n < 1) n = 1;
   if (p.tune.ctas_per_sm && (int)p.tune.ctas_per_sm < n) n = (int)p.tune.ctas_per_sm;
-  return n;
+  int grid = sm_count * n;
+  if (grid > (int)p.stack_warps / WARPS) grid = (int)p.stack_warps / WARPS;  // scratch stacks were sized for this many warps
+  // persistent: as many CTAs as are resident at once, each warp loops until the tile queue is empty
+  kernel<<<grid, NT, RENDER_SMEM, s>>>(p);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_render(const RenderParams& p, bool count_tests, int sm_count, cudaStream_t s) {
-  // persistent: as many CTAs as are resident at once, each warp loops until the tile queue is empty
-  if (count_tests) {
-    const int grid = sm_count * resident_ctas((const void*)k_render<true, false>, p);
-    k_render<true, false><<<grid, NT, 0, s>>>(p);
-  } else {
-    const int grid = sm_count * resident_ctas((const void*)k_render<false, false>, p);
-    k_render<false, false><<<grid, NT, 0, s>>>(p);
-  }
-  return cudaGetLastError();
+  if (count_tests) return launch_persistent(k_render<true, false>, p, sm_count, s);
+  return launch_persistent(k_render<false, false>, p, sm_count, s);
 }
 
 // Primary-ray closest hit per pixel (MakeRay + CalculateRayCollisionWithTriangle): the same kernel, stopped
 // at the first shade phase.
 cudaError_t launch_primary(const RenderParams& p, int sm_count, cudaStream_t s) {
   if (!p.width || !p.height) return cudaSuccess;
-  const int grid = sm_count * resident_ctas((const void*)k_render<false, true>, p);
-  k_render<false, true><<<grid, NT, 0, s>>>(p);
-  return cudaGetLastError();
+  return launch_persistent(k_render<false, true>, p, sm_count, s);
 }
+
+size_t render_stack_bytes_per_warp() { return (size_t)RR_STACK * POOL * sizeof(uint2); }
+size_t render_cold_bytes_per_warp() { return (size_t)NC * POOL * sizeof(uint32_t); }
+int render_max_warps_per_sm() { return 64; }
 
 // ---- probes for the bit-level parity tests (tests/test_math_parity.py) ---------
 __global__ void k_math_probe(int fn, const float* x, const float* y, float* out, uint64_t n) {

@@ -53,27 +53,18 @@ def run(tune, label):
 
 
 #        wP wH wS wT wL keep spec ctas
-base = [4, 4, 4, 4, 4, 12, 1, 0]
+base = [4, 4, 4, 4, 4, 22, 1, 0]
 run(base, "base")
 if a.grid == "default":
-    for keep in (1, 4, 8, 16, 20, 24):
+    for keep in (1, 8, 16, 20, 24, 28, 32):
         t = list(base); t[5] = keep
         run(t, f"keep={keep}")
-    for spec in (0,):
-        t = list(base); t[6] = spec
-        run(t, "spec=0")
-    for ctas in (2, 4, 6):
+    t = list(base); t[6] = 0
+    run(t, "spec=0")
+    for ctas in (1, 2, 3):
         t = list(base); t[7] = ctas
         run(t, f"ctas={ctas}")
-    for wT in (2, 3, 6, 8):
-        t = list(base); t[3] = wT
-        run(t, f"wT={wT}")
-    for wL in (2, 3, 6, 8):
-        t = list(base); t[4] = wL
-        run(t, f"wL={wL}")
-    for wS in (2, 6, 8):
-        t = list(base); t[2] = wS
-        run(t, f"wS={wS}")
-    for wH in (2, 6, 8):
-        t = list(base); t[1] = wH
-        run(t, f"wH={wH}")
+    for i, name in ((3, "wT"), (4, "wL"), (2, "wS"), (1, "wH")):
+        for w in (2, 8):
+            t = list(base); t[i] = w
+            run(t, f"{name}={w}")
