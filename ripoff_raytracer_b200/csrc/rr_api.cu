@@ -233,9 +233,10 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   RR_CUDA(cudaMalloc(&d.sph_geom, std::max<size_t>(n_spheres, 1) * 16));
   RR_CUDA(launch_pack_spheres(d.spheres, d.sb.order, d.sb.n, d.sph_geom, st));
   // one node array: triangle hierarchies at [0, tb.n), the sphere hierarchy behind them
-  RR_CUDA(cudaMalloc(&d.nodes, std::max<uint64_t>(d.tb.n + d.sb.n, 1) * 64));
-  if (d.tb.n) RR_CUDA(cudaMemcpyAsync(d.nodes, d.tb.nodes, d.tb.n * 64, cudaMemcpyDeviceToDevice, st));
-  if (d.sb.n) RR_CUDA(cudaMemcpyAsync(d.nodes + 4 * d.tb.n, d.sb.nodes, d.sb.n * 64, cudaMemcpyDeviceToDevice, st));
+  const size_t node_bytes = RR_NODE_QUADS * sizeof(float4);
+  RR_CUDA(cudaMalloc(&d.nodes, std::max<uint64_t>(d.tb.n + d.sb.n, 1) * node_bytes));
+  if (d.tb.n) RR_CUDA(cudaMemcpyAsync(d.nodes, d.tb.nodes, d.tb.n * node_bytes, cudaMemcpyDeviceToDevice, st));
+  if (d.sb.n) RR_CUDA(cudaMemcpyAsync(d.nodes + RR_NODE_QUADS * d.tb.n, d.sb.nodes, d.sb.n * node_bytes, cudaMemcpyDeviceToDevice, st));
   // mesh + material tables
   rr_mesh* d_meshes_in = nullptr;
   uint32_t *d_mesh_seg = nullptr, *d_mesh_pos = nullptr;

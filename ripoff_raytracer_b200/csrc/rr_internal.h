@@ -13,6 +13,7 @@
 #define RR_DIRECT_MAX 4               // segments this small are tested without a hierarchy
 #define RR_TILE_W 8                   // default work tile: 8 x 4 pixels = one warp
 #define RR_TILE_H 4
+#define RR_NODE_QUADS 8   // float4 per traversal node (4-wide node, 128 bytes)
 #ifndef RR_POOL
 #define RR_POOL 64        // path slots per warp of the render kernel (rr_render.cu)
 #endif
@@ -44,7 +45,7 @@ struct Lbvh {
   uint32_t* seg_count = nullptr;  // [n_segs]
   uint32_t* seg_sfirst = nullptr; // [n_segs] first slot
   // traversal arrays
-  float4* nodes = nullptr;     // [n*4] per inner node: delta-inflated child boxes + refs
+  float4* nodes = nullptr;     // [n*RR_NODE_QUADS] 4-wide traversal nodes: delta-inflated child boxes + refs
   uint32_t max_depth = 0;
 };
 
@@ -100,7 +101,7 @@ struct RenderParams {
   const DMesh* meshes;
   int32_t n_meshes;
   const DMaterial* materials;
-  const float4* nodes;       // 4 x float4 per inner node: triangle hierarchies, then the sphere hierarchy
+  const float4* nodes;       // RR_NODE_QUADS float4 per node: triangle hierarchies, then the sphere hierarchy
   const float4* tri_geom;    // 3 x float4 per slot: (A, primId) (B-A) (C-A)
   const float4* tri_nrm;     // 3 x float4 per slot: nA nB nC
   // spheres (one segment, world space)

@@ -399,43 +399,69 @@ __global__ void k_refit(uint64_t n, const uint32_t* __restrict__ order, const fl
   if (depth > 1) atomicMax(max_depth, depth);
 }
 
-// Traversal node: boxes of both children + child refs, 64 bytes.
-//   q0 = (A.min.xyz, A.max.x) q1 = (A.max.yz, B.min.xy) q2 = (B.min.z, B.max.xyz) q3 = (refA, refB, -, -)
-// The boxes are inflated by the segment's box_delta() so that culling is conservative (the closest
-// hit then does not depend on the order in which a traversal visits the nodes); inner references
-// get ref_offset added (position of this hierarchy inside the combined node array).
+// Traversal node: a 4-wide node, 128 bytes = one cache line, made of a binary LBVH node and its grandchildren
+// (a child that is a leaf stays a child).  Only binary nodes at EVEN depth below their segment root become
+// wide nodes; they keep their binary index, the odd ones in between are never fetched.
+//   q0..q2 = min.x[4] min.y[4] min.z[4]   q3..q5 = max.x[4] max.y[4] max.z[4]   q6 = ref[4]   q7 = (#children, -, -, -)
+// Unused child slots hold a NaN box: every comparison of the slab test fails, no ray enters it (an inverted
+// box would not do: the test orders the two planes of a slab itself).  The boxes are inflated by
+// the segment's box_delta() so that culling is conservative (the closest hit then does not depend on the order
+// in which a traversal visits the nodes).  ref: inner = index in the combined node array (ref_offset added),
+// leaf = -(slot + 2) (so that -1 is free for "pop", rr_render.cu).
 __global__ void k_pack_nodes(uint64_t n, const uint32_t* __restrict__ order, const float* __restrict__ prim_box,
                              const int32_t* __restrict__ left, const int32_t* __restrict__ right,
-                             const float* __restrict__ bounds, const unsigned int* __restrict__ flags,
-                             const uint32_t* __restrict__ seg_sfirst, int n_segs, const float* __restrict__ seg_box,
-                             int32_t ref_offset, float4* __restrict__ nodes) {
+                             const int32_t* __restrict__ parent, const float* __restrict__ bounds,
+                             const unsigned int* __restrict__ flags, const uint32_t* __restrict__ seg_sfirst, int n_segs,
+                             const float* __restrict__ seg_box, int32_t ref_offset, float4* __restrict__ nodes) {
   uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n) return;
-  float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
-  if (flags[g] == 2u) {  // a built inner node
-    float a[6], c[6];
-    int32_t L = left[g], R = right[g];
-    load_ref_box(L, order, prim_box, bounds, a);
-    load_ref_box(R, order, prim_box, bounds, c);
+  float lo[3][4], hi[3][4];
+  int32_t ref[4];
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    ref[k] = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { lo[a][k] = __int_as_float(0x7fc00000); hi[a][k] = __int_as_float(0x7fc00000); }
+  }
+  bool wide = flags[g] == 2u;  // a built inner node ...
+  if (wide) {                  // ... at even depth
+    unsigned depth = 0;
+    for (int32_t q = parent[g]; q >= 0; q = parent[q]) depth++;
+    wide = (depth & 1u) == 0u;
+  }
+  if (wide) {
     const int s = seg_search(seg_sfirst, n_segs, (uint32_t)g);
     float sb[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) sb[k] = __ldg(seg_box + 6 * s + k);
     const float d = box_delta(sb);
+    int32_t kids[4];
+    const int32_t c2[2] = {left[g], right[g]};
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { a[k] -= d; c[k] -= d; a[3 + k] += d; c[3 + k] += d; }
-    // inner: index in the combined node array; leaf: -(slot + 2)  (so that -1 is free for "pop", rr_render.cu)
-    L = L >= 0 ? L + ref_offset : L - 1;
-    R = R >= 0 ? R + ref_offset : R - 1;
-    q0 = make_float4(a[0], a[1], a[2], a[3]);
-    q1 = make_float4(a[4], a[5], c[0], c[1]);
-    q2 = make_float4(c[2], c[3], c[4], c[5]);
-    q3 = make_float4(__int_as_float(L), __int_as_float(R), 0.0f, 0.0f);
+    for (int j = 0; j < 2; ++j) {
+      if (c2[j] < 0) kids[cnt++] = c2[j];
+      else { kids[cnt++] = left[c2[j]]; kids[cnt++] = right[c2[j]]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < cnt) {
+        float bx[6];
+        load_ref_box(kids[k], order, prim_box, bounds, bx);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a][k] = bx[a] - d; hi[a][k] = bx[3 + a] + d; }
+        ref[k] = kids[k] >= 0 ? kids[k] + ref_offset : kids[k] - 1;
+      }
+    }
   }
-  nodes[4 * g + 0] = q0;
-  nodes[4 * g + 1] = q1;
-  nodes[4 * g + 2] = q2;
-  nodes[4 * g + 3] = q3;
+  float4* o = nodes + 8 * g;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    o[a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
+    o[3 + a] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
+  }
+  o[6] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
+  o[7] = make_float4(__int_as_float(cnt), 0.0f, 0.0f, 0.0f);
 }
 
 // Sorted triangle arrays.  geom: (A, prim) (B-A) (C-A) -- the edge vectors are
@@ -529,7 +555,7 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
   RR_TRY(dalloc(&out.seg_first, n_segs));
   RR_TRY(dalloc(&out.seg_count, n_segs));
   RR_TRY(dalloc(&out.seg_sfirst, n_segs));
-  RR_TRY(dalloc(&out.nodes, (n ? n : 1) * 4));
+  RR_TRY(dalloc(&out.nodes, (n ? n : 1) * RR_NODE_QUADS));
   RR_TRY(dalloc(&keys_a, n_total));
   RR_TRY(dalloc(&keys_b, n_total));
   RR_TRY(dalloc(&vals_a, n_total));
@@ -588,8 +614,8 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
                                                out.parent, leaf_parent);
     k_refit<<<grid_for(n, 128), 128, 0, st>>>(n, out.order, d_prim_box, out.left, out.right, out.parent, leaf_parent,
                                               out.bounds, flags, d_depth);
-    k_pack_nodes<<<grid_for(n, 128), 128, 0, st>>>(n, out.order, d_prim_box, out.left, out.right, out.bounds, flags,
-                                                   out.seg_sfirst, (int)n_segs, out.seg_box, ref_offset, out.nodes);
+    k_pack_nodes<<<grid_for(n, 128), 128, 0, st>>>(n, out.order, d_prim_box, out.left, out.right, out.parent, out.bounds,
+                                                   flags, out.seg_sfirst, (int)n_segs, out.seg_box, ref_offset, out.nodes);
     RR_TRY(cudaGetLastError());
   }
   RR_TRY(cudaMemcpyAsync(&out.max_depth, d_depth, 4, cudaMemcpyDeviceToHost, st));

@@ -21,9 +21,9 @@
 //     leaf test); each round the warp votes and runs the phase with the most
 //     ready lanes, so the hot node-step loop executes with most lanes active
 //     instead of each lane walking its own ray while 31 others wait;
-//   * a node step is one 64-byte fetch (4 x LDG.128: both child boxes and both
-//     child references) and two slab tests; a lane may postpone one leaf and
-//     keep walking (speculative traversal);
+//   * a node step is one 128-byte fetch (a 4-wide node: the binary LBVH node
+//     collapsed with its grandchildren) and four slab tests; a slot may postpone
+//     one leaf and keep walking (speculative traversal);
 //   * the per-path colour state lives in shared memory so that the traversal
 //     fits 64 registers and 32 warps stay resident per SM.
 #include <math.h>
@@ -42,18 +42,24 @@ __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y -
 __device__ __forceinline__ V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
 __device__ __forceinline__ V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ V3 operator*(float s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
-__device__ __forceinline__ V3 operator/(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+__device__ __noinline__ V3 div3(V3 a, float s);
+__device__ __forceinline__ V3 operator/(V3 a, float s) { return div3(a, s); }
 __device__ __forceinline__ V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ V3 cross(V3 a, V3 b) {
   return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
+// Code size matters more than call overhead here: the SM's instruction cache holds 32 KB (about 2 000
+// instructions) and every warp walks through all phases of the kernel every few microseconds.  The IEEE
+// square root / division sequences and the software log / cos / powr are therefore kept out of line, one
+// copy each.
 // fast_normalize / normalize of the numerics contract
-__device__ __forceinline__ V3 normalize(V3 a) {
+__device__ __noinline__ V3 normalize(V3 a) {
   float inv = 1.0f / sqrtf(dot(a, a));
   return a * inv;
 }
-__device__ __forceinline__ float length(V3 a) { return sqrtf(dot(a, a)); }
+__device__ __noinline__ float length(V3 a) { return sqrtf(dot(a, a)); }
+__device__ __noinline__ V3 div3(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
 __device__ __forceinline__ V3 ld3(const float* p) { return mk(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
 __device__ __forceinline__ V3 xyz(float4 q) { return mk(q.x, q.y, q.z); }
 
@@ -79,14 +85,23 @@ __device__ __forceinline__ float rand01(uint32_t& state) {
   z = z ^ (z >> 16);
   return map_u32(z);
 }
-// src/Trace.cl:179-187
-__device__ __forceinline__ float random_normal(uint32_t& state) {
+// src/Trace.cl:179-187 (out of line; the state goes in and out by value so that it stays in a register)
+struct NormalDraw { float v; uint32_t state; };
+__device__ __noinline__ NormalDraw random_normal_draw(uint32_t state) {
   float u1 = random_value(state);
   float u2 = random_value(state);
   u1 = fmaxf(u1, RR_EPSILON);
   float r = sqrtf(-2.0f * log_c(u1));
   float theta = RR_TAU * u2;
-  return r * cos_c(theta);
+  NormalDraw d;
+  d.v = r * cos_c(theta);
+  d.state = state;
+  return d;
+}
+__device__ __forceinline__ float random_normal(uint32_t& state) {
+  const NormalDraw d = random_normal_draw(state);
+  state = d.state;
+  return d.v;
 }
 __device__ __forceinline__ bool finite_f(float x) { return (__float_as_uint(x) & 0x7f800000u) != 0x7f800000u; }
 // src/Trace.cl:189-200
@@ -218,7 +233,7 @@ __device__ __forceinline__ bool shade(const RenderParams& p, const SceneHit& hit
 }
 
 // src/Trace.cl:596-621 + the uv of :634-635
-__device__ __forceinline__ V3 primary_dir(const DCamera& cam, uint32_t x, uint32_t y, uint32_t W, uint32_t H) {
+__device__ __noinline__ V3 primary_dir(const DCamera cam, uint32_t x, uint32_t y, uint32_t W, uint32_t H) {
   const float u = (float)x / (float)W;
   const float v = (float)(1.0f - (float)y / (float)H);
   float ndc0 = u * 2.0f - 1.0f;
@@ -236,10 +251,11 @@ __device__ __forceinline__ V3 primary_dir(const DCamera& cam, uint32_t x, uint32
 }
 
 // src/Trace.cl:643-652 (+ host alpha = 255, src/image.hpp:271)
-__device__ __forceinline__ uint32_t tonemap_rgba(V3 c) {
-  const float r = powr_c(fminf(fmaxf(c.x, 0.0f), 1.0f), 1.0f / 2.2f);
-  const float g = powr_c(fminf(fmaxf(c.y, 0.0f), 1.0f), 1.0f / 2.2f);
-  const float b = powr_c(fminf(fmaxf(c.z, 0.0f), 1.0f), 1.0f / 2.2f);
+__device__ __noinline__ float gamma_c(float c) { return powr_c(fminf(fmaxf(c, 0.0f), 1.0f), 1.0f / 2.2f); }
+__device__ __noinline__ uint32_t tonemap_rgba(V3 c) {
+  const float r = gamma_c(c.x);
+  const float g = gamma_c(c.y);
+  const float b = gamma_c(c.z);
   const uint32_t R = (uint32_t)(unsigned char)(r * 255.0f), G = (uint32_t)(unsigned char)(g * 255.0f),
                  B = (uint32_t)(unsigned char)(b * 255.0f);
   return R | (G << 8) | (B << 16) | (255u << 24);
@@ -374,8 +390,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     return n;
   };
   auto trav_key = [&]() -> uint32_t {
-    if (cur == REF_END && pend_cnt == 0)  // mesh done: more candidates -> setup, none -> shade (which finishes the mesh itself)
-      return (cand != 0 || (m & ~31) + 32 <= p.last_mesh) ? K_S : K_H;
+    if (cur == REF_END && pend_cnt == 0) return K_S;  // mesh done: the setup phase finishes it and enters the next one
     return ((cur >= REF_POP && (speculate || pend_cnt == 0)) ? K_T : 0u) | (pend_cnt ? K_L : 0u);
   };
 
@@ -561,7 +576,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     if (nH * wH > best) { best = nH * wH; phase = PH_SHADE; }
     if (min(nP, 32u) * wP > best) { best = min(nP, 32u) * wP; phase = PH_PIXEL; }
     round++;
-
     if (phase == PH_TRAV) {
       // ================= node steps =================
       bool ready[ROUNDS];
@@ -608,30 +622,47 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         if (step) {
           if (cur == REF_POP) resolve(REF_POP);
           if (cur >= 0) {
-            const float4* nd = p.nodes + 4 * (size_t)cur;
-            const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
-            if (COUNT) c_box += 2;
-            float tA, tB;
-            const bool hA = box_cull(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, linv, lnoi, lt, tA);
-            const bool hB = box_cull(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, linv, lnoi, lt, tB);
-            const int32_t L = __float_as_int(q3.x), R = __float_as_int(q3.y);
+            // one 128-byte node: the boxes of up to four children (SoA) and their references
+            const float4* nd = p.nodes + RR_NODE_QUADS * (size_t)cur;
+            const float4 lx = __ldg(nd), ly = __ldg(nd + 1), lz = __ldg(nd + 2), hx = __ldg(nd + 3), hy = __ldg(nd + 4),
+                         hz = __ldg(nd + 5), rf = __ldg(nd + 6);
+            if (COUNT) c_box += (unsigned)__float_as_int(__ldg(&nd[7].x));
+            // sort key of a child: entry distance (clamped at 0, two low mantissa bits dropped) | child number;
+            // a child the ray misses sorts last
+            uint32_t k0, k1, k2, k3;
+            {
+              float tn;
+              k0 = box_cull(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, linv, lnoi, lt, tn) ? ((__float_as_uint(fmaxf(tn, 0.0f)) & ~3u) | 0u) : 0xffffffffu;
+              k1 = box_cull(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, linv, lnoi, lt, tn) ? ((__float_as_uint(fmaxf(tn, 0.0f)) & ~3u) | 1u) : 0xffffffffu;
+              k2 = box_cull(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, linv, lnoi, lt, tn) ? ((__float_as_uint(fmaxf(tn, 0.0f)) & ~3u) | 2u) : 0xffffffffu;
+              k3 = box_cull(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, linv, lnoi, lt, tn) ? ((__float_as_uint(fmaxf(tn, 0.0f)) & ~3u) | 3u) : 0xffffffffu;
+            }
+            {  // 5-comparator sorting network, ascending
+              uint32_t t;
+              t = min(k0, k1); k1 = max(k0, k1); k0 = t;
+              t = min(k2, k3); k3 = max(k2, k3); k2 = t;
+              t = min(k0, k2); k2 = max(k0, k2); k0 = t;
+              t = min(k1, k3); k3 = max(k1, k3); k1 = t;
+              t = min(k1, k2); k2 = max(k1, k2); k1 = t;
+            }
+            auto ref_of = [&](uint32_t k) -> int32_t {
+              const uint32_t c = k & 3u;
+              return __float_as_int(c == 0u ? rf.x : c == 1u ? rf.y : c == 2u ? rf.z : rf.w);
+            };
             int32_t next = REF_POP;
-            if (hA && hB) {
-              const bool aNear = tA < tB;
-              const int32_t nearRef = aNear ? L : R, farRef = aNear ? R : L;
-              if (pend_cnt == 0 && nearRef < REF_POP) {  // the near child is a leaf: postpone it, go on with the far one
-                if (farRef < REF_POP) {  // two leaves: adjacent slots, L first
-                  pend_slot = ref_slot(L); pend_cnt = 2;
-                } else {
-                  pend_slot = ref_slot(nearRef); pend_cnt = 1;
-                  next = farRef;
-                }
-              } else {
-                if (sp < RR_STACK) { stk[sp * POOL] = make_uint2((uint32_t)farRef, __float_as_uint(aNear ? tB : tA)); sp++; }
-                next = nearRef;
+            if (k0 != 0xffffffffu) {
+              int32_t r0 = ref_of(k0);
+              if (r0 < REF_POP && pend_cnt == 0) {  // the nearest child is a leaf: postpone it and go on with the next one
+                pend_slot = ref_slot(r0); pend_cnt = 1;
+                k0 = k1; k1 = k2; k2 = k3; k3 = 0xffffffffu;
+                r0 = k0 != 0xffffffffu ? ref_of(k0) : REF_POP;
               }
-            } else if (hA) next = L;
-            else if (hB) next = R;
+              // the farther children go to the stack, farthest first
+              if (k3 != 0xffffffffu && sp < RR_STACK) { stk[sp * POOL] = make_uint2((uint32_t)ref_of(k3), k3 & ~3u); sp++; }
+              if (k2 != 0xffffffffu && sp < RR_STACK) { stk[sp * POOL] = make_uint2((uint32_t)ref_of(k2), k2 & ~3u); sp++; }
+              if (k1 != 0xffffffffu && sp < RR_STACK) { stk[sp * POOL] = make_uint2((uint32_t)ref_of(k1), k1 & ~3u); sp++; }
+              next = r0;
+            }
             resolve(next);
           }
         }
@@ -641,8 +672,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         PW(W_CUR, s) = (uint32_t)cur;
         PW(W_SPC, s) = (uint32_t)sp | (pend_cnt << 8);
         PW(W_PSLOT, s) = pend_slot;
-        cand = PW(W_CAND, s);
-        m = (int)PW(W_M, s);
         PW(W_KEY, s) = trav_key();
       }
     } else if (phase == PH_LEAF) {
@@ -650,8 +679,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       bool ready[ROUNDS];
 #pragma unroll
       for (int r = 0; r < ROUNDS; ++r) ready[r] = (PW(W_KEY, lane + 32 * r) & K_L) != 0u;
-      const int n = select(ready);
-      if (COUNT) { ph_runs[PH_LEAF]++; ph_lanes[PH_LEAF] += n; }
+      const int n_sel = select(ready);
+      if (COUNT) { ph_runs[PH_LEAF]++; ph_lanes[PH_LEAF] += n_sel; }
       if (s >= 0) {
         cur = (int32_t)PW(W_CUR, s);
         const uint32_t spc = PW(W_SPC, s);
@@ -751,8 +780,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         }
         PW(W_SPC, s) = (uint32_t)sp | (pend_cnt << 8);
         PW(W_PSLOT, s) = pend_slot;
-        cand = PW(W_CAND, s);
-        m = (int)PW(W_M, s);
         PW(W_KEY, s) = trav_key();
       }
     } else if (phase == PH_SETUP) {
@@ -760,8 +787,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       bool ready[ROUNDS];
 #pragma unroll
       for (int r = 0; r < ROUNDS; ++r) ready[r] = (PW(W_KEY, lane + 32 * r) & K_S) != 0u;
-      const int n = select(ready);
-      if (COUNT) { ph_runs[PH_SETUP]++; ph_lanes[PH_SETUP] += n; }
+      const int n_sel = select(ready);
+      if (COUNT) { ph_runs[PH_SETUP]++; ph_lanes[PH_SETUP] += n_sel; }
       if (s >= 0) {
         origin = PLD3(W_OX, s);
         dir = PLD3(W_DX, s);
@@ -782,15 +809,17 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       bool ready[ROUNDS];
 #pragma unroll
       for (int r = 0; r < ROUNDS; ++r) ready[r] = (PW(W_KEY, lane + 32 * r) & K_H) != 0u;
-      const int n = select(ready);
-      if (COUNT) { ph_runs[PH_SHADE]++; ph_lanes[PH_SHADE] += n; }
+      const int n_sel = select(ready);
+      if (COUNT) { ph_runs[PH_SHADE]++; ph_lanes[PH_SHADE] += n_sel; }
       bool pixel_done = false;
       if (s >= 0) {
         origin = PLD3(W_OX, s);
         dir = PLD3(W_DX, s);
-        m = (int)PW(W_M, s);
-        load_ray_state();
-        finish_mesh();
+        best_dst = PF(W_BDST, s);
+        const uint32_t bm = PW(W_BMAT, s);
+        best_mat = (int32_t)(bm & 0x7fffffffu);
+        best_back = (bm >> 31) != 0u;
+        if (PRIMARY) { best_mesh = (int32_t)PW(W_BMESH, s); best_prim = (int32_t)CW(C_BPRIM, s); }
         pix = (int32_t)PW(W_PIX, s);
         if (PRIMARY) {
           if (p.hit_mesh) p.hit_mesh[pix] = best_dst < INFINITY ? best_mesh : -1;
@@ -854,8 +883,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       bool ready[ROUNDS];
 #pragma unroll
       for (int r = 0; r < ROUNDS; ++r) ready[r] = (int32_t)PW(W_PIX, lane + 32 * r) == PIX_NEED;
-      const int n = select(ready);
-      if (COUNT) { ph_runs[PH_PIXEL]++; ph_lanes[PH_PIXEL] += n; }
+      const int n_sel = select(ready);
+      if (COUNT) { ph_runs[PH_PIXEL]++; ph_lanes[PH_PIXEL] += n_sel; }
       bool need = s >= 0;
       while (__any_sync(full, need)) {
         if (tile_next >= tile_pixels) {

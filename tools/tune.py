@@ -56,7 +56,7 @@ def run(tune, label):
 base = [4, 4, 4, 4, 4, 22, 1, 0]
 run(base, "base")
 if a.grid == "default":
-    for keep in (1, 8, 16, 20, 24, 28, 32):
+    for keep in (1, 8, 12, 16, 20, 24, 32):
         t = list(base); t[5] = keep
         run(t, f"keep={keep}")
     t = list(base); t[6] = 0
