@@ -294,6 +294,7 @@ enum {
   W_LOX, W_LOY, W_LOZ, W_LDX, W_LDY, W_LDZ, W_LIX, W_LIY, W_LIZ,  // mesh-local ray and its reciprocal direction
   W_LT, W_LPRIM, W_LNX, W_LNY, W_LNZ,           // closest hit inside the current mesh
   W_CUR, W_SPC, W_PSLOT,                        // traversal: node ref, stack pointer | postponed count << 8, postponed slot
+  W_TOPN, W_TOPD,                               // the top entry of the traversal stack (the rest is in global scratch)
   NW
 };
 enum {
@@ -374,18 +375,22 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
 
   // Up to 32 slots with `ready` set are handed to the lanes (lane j gets the j-th ready slot); returns how many.
   auto select = [&](const bool (&ready)[ROUNDS]) -> int {
+    static_assert(ROUNDS == 2, "select() serves the two halves of the pool");
     __syncwarp();
-    int base = 0;
-#pragma unroll
-    for (int q = 0; q < ROUNDS; ++q) {
-      const int r = (q + (int)(round % ROUNDS)) % ROUNDS;  // rotate which part of the pool is served first
-      const unsigned b = __ballot_sync(full, ready[r]);
-      const int rank = base + __popc(b & lanes_below);
-      if (ready[r] && rank < 32) sel[rank] = lane + 32 * r;
-      base += __popc(b);
+    const unsigned b0 = __ballot_sync(full, ready[0]), b1 = __ballot_sync(full, ready[1]);
+    const bool flip = (round & 1u) != 0u;  // alternate which half of the pool is served first (no dynamic indexing:
+                                           // a runtime-indexed ready[] would live in local memory)
+    const unsigned bf = flip ? b1 : b0, bs = flip ? b0 : b1;
+    const bool rf = flip ? ready[1] : ready[0], rs = flip ? ready[0] : ready[1];
+    const unsigned of = flip ? 32u : 0u, os = flip ? 0u : 32u;
+    const int nf = __popc(bf);
+    if (rf) sel[__popc(bf & lanes_below)] = lane + of;
+    if (rs) {
+      const int rank = nf + __popc(bs & lanes_below);
+      if (rank < 32) sel[rank] = lane + os;
     }
     __syncwarp();
-    const int n = min(base, 32);
+    const int n = min(nf + __popc(bs), 32);
     s = (int)lane < n ? (int)sel[lane] : -1;
     return n;
   };
@@ -597,14 +602,26 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         cur = REF_END; sp = 0; pend_cnt = 0;
       }
       uint2* const stk = stack + (mine ? s : 0);
+      // Entry sp-1 (the top) is kept in registers / shared memory, entries 0..sp-2 in the global scratch.  A pop
+      // hands out the top at once and only ISSUES the load of the next entry, so that its L2 latency overlaps
+      // with the node fetch that follows instead of preceding it.
+      uint2 top = make_uint2(0u, 0u);
+      if (mine && sp > 0) top = make_uint2(PW(W_TOPN, s), PW(W_TOPD, s));
+      auto push = [&](int32_t ref, uint32_t dist_bits) {
+        if (sp >= RR_STACK) return;
+        if (sp > 0) stk[(sp - 1) * POOL] = top;
+        top = make_uint2((uint32_t)ref, dist_bits);
+        sp++;
+      };
       // Pops the stack / postpones leaves until `cur` is an inner node, a leaf the slot must wait for, or REF_END.
       auto resolve = [&](int32_t next) {
         for (;;) {
           if (next == REF_POP) {
             bool found = false;
             while (sp > 0) {
+              const uint2 e = top;
               --sp;
-              const uint2 e = stk[sp * POOL];
+              if (sp > 0) top = stk[(sp - 1) * POOL];
               if (__uint_as_float(e.y) <= lt) { next = (int32_t)e.x; found = true; break; }
             }
             if (!found) { cur = REF_END; break; }
@@ -658,9 +675,9 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
                 r0 = k0 != 0xffffffffu ? ref_of(k0) : REF_POP;
               }
               // the farther children go to the stack, farthest first
-              if (k3 != 0xffffffffu && sp < RR_STACK) { stk[sp * POOL] = make_uint2((uint32_t)ref_of(k3), k3 & ~3u); sp++; }
-              if (k2 != 0xffffffffu && sp < RR_STACK) { stk[sp * POOL] = make_uint2((uint32_t)ref_of(k2), k2 & ~3u); sp++; }
-              if (k1 != 0xffffffffu && sp < RR_STACK) { stk[sp * POOL] = make_uint2((uint32_t)ref_of(k1), k1 & ~3u); sp++; }
+              if (k3 != 0xffffffffu) push(ref_of(k3), k3 & ~3u);
+              if (k2 != 0xffffffffu) push(ref_of(k2), k2 & ~3u);
+              if (k1 != 0xffffffffu) push(ref_of(k1), k1 & ~3u);
               next = r0;
             }
             resolve(next);
@@ -672,6 +689,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         PW(W_CUR, s) = (uint32_t)cur;
         PW(W_SPC, s) = (uint32_t)sp | (pend_cnt << 8);
         PW(W_PSLOT, s) = pend_slot;
+        PW(W_TOPN, s) = top.x;
+        PW(W_TOPD, s) = top.y;
         PW(W_KEY, s) = trav_key();
       }
     } else if (phase == PH_LEAF) {
@@ -970,7 +989,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
 
 void default_tuning(Tuning& t) {
   for (int k = 0; k < 5; ++k) t.weight[k] = 4;
-  t.trav_keep = 22;
+  t.trav_keep = 16;
   t.speculate = 1;
   t.ctas_per_sm = 0;
 }
