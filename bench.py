@@ -227,21 +227,17 @@ def main():
     # ---- multi-GPU plumbing: rank 0 owns the tile counter and the frame; peers attach over CUDA IPC ----
     mode = "local"
     if world > 1:
-        handles = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            q, f = r.queue_export(W, H)
-            handles.copy_(torch.from_numpy(np.concatenate([q, f])))
-        dist.broadcast(handles, 0)
-        ok = torch.ones(1, device="cuda")
+        from ripoff_raytracer_b200 import multigpu
+
+        q, f = multigpu.exchange_handles(dist, rank, lambda: r.queue_export(W, H), device="cuda")
+        attached = True
         if rank != 0:
-            h = handles.cpu().numpy()
             try:
-                r.queue_import(W, H, h[:64], h[64:])
+                r.queue_import(W, H, q, f)
             except _abi.RRError as e:
                 print(f"[rank {rank}] IPC import failed ({e}); falling back to a static tile partition", file=sys.stderr)
-                ok.zero_()
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        mode = "shared" if ok.item() > 0 else "strided"
+                attached = False
+        mode = multigpu.negotiate_mode(dist, attached, device="cuda")
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -285,14 +281,18 @@ def main():
             st = device_step()
             rays_total += st["rays"] + st["rays_reused"]
             rays_traced += st["rays"]
-            kernel_ms.append(st["render_ms"])
+            kernel_ms.append(st["render_ms"])  # CUDA events on the library's own stream, around the render kernel
         barrier()
-        dt = time.perf_counter() - t0
-    dt = total(dt, dist.ReduceOp.MAX if world > 1 else None)
+        wall = time.perf_counter() - t0
+    wall = total(wall, dist.ReduceOp.MAX if world > 1 else None)
     rays_all = total(float(rays_total))
     traced_all = total(float(rays_traced))
-    kernel_s = float(np.mean(kernel_ms)) / 1e3 if kernel_ms else 0.0
-    kernel_s = total(kernel_s, dist.ReduceOp.MAX if world > 1 else None)
+    # device time of a step = the slowest rank's kernel (all ranks start together behind the barrier)
+    step_ms = torch.tensor(kernel_ms, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
+    dt = float(step_ms.sum().item()) / 1e3
+    kernel_s = dt / max(args.steps, 1)
     samples_all = float(W) * H * spp * args.steps
     value = rays_all / dt / 1e6
     clk = clocks.summary()
@@ -338,23 +338,34 @@ def main():
     ach_tflops = per_launch_rays * flops_per_ray / kernel_s / 1e12 if kernel_s else 0.0
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     ach_gbs = per_launch_rays * bytes_per_ray / kernel_s / 1e9 if kernel_s else 0.0
+    traffic, traffic_src = None, None
+    try:  # dram__bytes_read+write of k_render from the committed `ncu --set full` capture, per traced ray
+        ncu = json.loads((ROOT / "profiles" / "ncu_summary.json").read_text())
+        per_ray = ncu["k_render"]["dram_bytes_per_ray"]
+        traffic = per_ray * per_launch_rays
+        traffic_src = f"{per_ray:.1f} B/ray x rays of this launch; measured by ncu on {ncu['k_render']['config']}"
+    except Exception:
+        pass
     roofline = {
         "bound": "fp32", "kernel": "k_render", "achieved": ach_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-        "frac": ach_tflops / fp32_peak_tflops, "traffic": None,
+        "frac": ach_tflops / fp32_peak_tflops, "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": f"nominal FP32 FMA peak: {sm_count} SMs x 128 lanes x 2 flop x {sm_max:.0f} MHz (MEASURED_PEAKS.json holds no FP32 figure)",
         "flops_per_ray": flops_per_ray, "bytes_per_ray": bytes_per_ray, "box_tests_per_ray": n_box, "tri_tests_per_ray": n_tri,
         "sphere_tests_per_ray": n_sph, "kernel_ms": kernel_s * 1e3,
-        "note": "arithmetic is issued unfused (-fmad=false, numerics contract): the reachable ceiling is half the FMA peak",
+        "note": "result arithmetic is issued unfused (numerics contract); slab tests use FFMA.  A divergent BVH walk is "
+                "latency- and instruction-fetch-bound, not FMA-bound: see DESIGN.md section 7",
     }
     roofline_mem = {"bound": "hbm", "kernel": "k_render", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach_gbs / hbm_peak, "traffic": None,
+                    "frac": ach_gbs / hbm_peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"}
 
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(wl, world),
-        "msamples_per_s": samples_all / dt / 1e6, "frame_time_s": dt / args.steps, "rays_per_sample": rays_all / samples_all,
+        "msamples_per_s": samples_all / dt / 1e6, "frame_time_s": dt / args.steps, "wall_ms_per_step": wall / args.steps * 1e3,
+        "timing": "CUDA events on the launching stream around each render kernel, max over ranks per step",
+        "rays_per_sample": rays_all / samples_all,
         "rays_traced_fraction": traced_all / max(rays_all, 1.0), "tile_queue": mode,
         "clocks": clk, "gpu_launches": args.steps * world, "roofline": roofline, "roofline_memory": roofline_mem,
     }
@@ -387,12 +398,12 @@ def device_step_e2e(r, rr, wl, mode, rank, world, barrier, frame_host):
     import torch
     import torch.distributed as dist
 
+    from ripoff_raytracer_b200 import multigpu
+
     st = r.render_strided(wl.cam, W, H, wl.spp, wl.bounces, rank, world)
-    fr = r.read_frame(W, H)  # strided fallback: host-side merge through NCCL on an int32 view
-    t = torch.from_numpy(fr.view(np.int32).copy()).cuda()
-    dist.reduce(t, 0, op=dist.ReduceOp.SUM)
+    merged = multigpu.merge_strided_frames(dist, r.read_frame(W, H), rank, device="cuda")  # one NCCL reduce
     if rank == 0:
-        frame_host[...] = t.cpu().numpy().view(np.uint8).reshape(H, W, 4)
+        frame_host[...] = merged
     return st
 
 
