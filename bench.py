@@ -26,6 +26,8 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# NCCL writes its banner / debug lines to stdout by default; stdout carries exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 F_BOX, F_TRI, F_SPH = 24, 53, 24     # algorithmic flop per test (sphere: DESIGN.md 6)
 B_BOX, B_TRI, B_SPH = 32, 48, 16     # algorithmic bytes per test

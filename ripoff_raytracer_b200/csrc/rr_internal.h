@@ -20,8 +20,8 @@
 #ifndef RR_MIN_CTAS
 #define RR_MIN_CTAS 6     // resident 128-thread CTAs per SM the render kernel is compiled for
 #endif
-#define RR_POOL_WORDS 33  // 32-bit words of one slot in shared memory
-#define RR_COLD_WORDS 22  // ... and in the per-warp global scratch
+#define RR_POOL_WORDS 29  // 32-bit words of one slot in shared memory
+#define RR_COLD_WORDS 25  // ... and in the per-warp global scratch
 
 namespace rr {
 

@@ -289,10 +289,10 @@ constexpr int32_t PIX_NEED = -1, PIX_IDLE = -2;
 enum {
   W_KEY = 0, W_PIX,
   W_OX, W_OY, W_OZ, W_DX, W_DY, W_DZ,           // world ray
-  W_BDST, W_BMAT, W_BMESH,                      // closest hit so far: distance, material | back << 31, mesh
+  W_BDST, W_BMAT,                               // closest hit so far: distance, material | back << 31 (mesh = min(material, n_meshes))
   W_CAND, W_M, W_MFLAGS,                        // candidate meshes of the chunk, current mesh (-1: new ray), flags | lback << 31
   W_LOX, W_LOY, W_LOZ, W_LDX, W_LDY, W_LDZ, W_LIX, W_LIY, W_LIZ,  // mesh-local ray and its reciprocal direction
-  W_LT, W_LPRIM, W_LNX, W_LNY, W_LNZ,           // closest hit inside the current mesh
+  W_LT, W_LPRIM,                                // closest hit inside the current mesh (its normal: C_LNX)
   W_CUR, W_SPC, W_PSLOT,                        // traversal: node ref, stack pointer | postponed count << 8, postponed slot
   W_TOPN, W_TOPD,                               // the top entry of the traversal stack (the rest is in global scratch)
   NW
@@ -300,6 +300,7 @@ enum {
 enum {
   C_RNG = 0, C_SAMPLE, C_BOUNCE,                // bounce | passes << 16
   C_BPRIM, C_BPX, C_BPY, C_BPZ, C_BNX, C_BNY, C_BNZ,  // primitive, point and normal of the closest hit
+  C_LNX, C_LNY, C_LNZ,                          // normal of the closest hit inside the current mesh
   C_THR, C_THR1, C_THR2, C_INC, C_INC1, C_INC2, C_ACC, C_ACC1, C_ACC2, C_PD, C_PD1, C_PD2,
   NC
 };
@@ -345,7 +346,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   const uint32_t wP = p.tune.weight[PH_PIXEL], wH = p.tune.weight[PH_SHADE], wS = p.tune.weight[PH_SETUP],
                  wT = p.tune.weight[PH_TRAV], wL = p.tune.weight[PH_LEAF];
   const uint32_t trav_keep = p.tune.trav_keep;
-  const bool speculate = p.tune.speculate != 0;
+  const bool speculate = (p.tune.speculate & 1u) != 0;
+  const bool prefetch = (p.tune.speculate & 2u) != 0;  // parked slots prefetch the line they will need next
 
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         best_dst = lt; best_mat = mat; best_back = lback; best_mesh = mesh_index; best_prim = lprim;
         const V3 wp = origin + dir * lt;
         CST3(C_BPX, s, wp);
-        CW(C_BNX, s) = PW(W_LNX, s); CW(C_BNY, s) = PW(W_LNY, s); CW(C_BNZ, s) = PW(W_LNZ, s);
+        CW(C_BNX, s) = CW(C_LNX, s); CW(C_BNY, s) = CW(C_LNY, s); CW(C_BNZ, s) = CW(C_LNZ, s);
       }
     } else {
       const int32_t type = (int32_t)((mflags >> RR_MF_TYPE_SHIFT) & 0xffu);
@@ -447,7 +449,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         const V3 pos = mk(__ldg(&M->ri0.w), __ldg(&M->ri1.w), __ldg(&M->ri2.w));
         const V3 lp = (lo + ld * lt) * r0.w;
         const V3 wp = mk(dot(xyz(r0), lp), dot(xyz(r1), lp), dot(xyz(r2), lp)) + pos;
-        const V3 ln = PLD3(W_LNX, s);
+        const V3 ln = CLD3(C_LNX, s);
         const V3 wn = normalize(mk(dot(xyz(r0), ln), dot(xyz(r1), ln), dot(xyz(r2), ln)));
         const float wd = length(wp - origin);
         if (wd < best_dst || (wd == best_dst && mesh_index < best_mesh)) {
@@ -523,7 +525,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   auto store_ray_state = [&](uint32_t key) {
     PSF(W_BDST, s, best_dst);
     PW(W_BMAT, s) = (uint32_t)best_mat | (best_back ? 0x80000000u : 0u);
-    PW(W_BMESH, s) = (uint32_t)best_mesh;
     if (PRIMARY) CW(C_BPRIM, s) = (uint32_t)best_prim;
     PW(W_CAND, s) = cand;
     PW(W_M, s) = (uint32_t)m;
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     const uint32_t bm = PW(W_BMAT, s);
     best_mat = (int32_t)(bm & 0x7fffffffu);
     best_back = (bm >> 31) != 0u;
-    best_mesh = (int32_t)PW(W_BMESH, s);
+    best_mesh = best_dst < INFINITY ? min(best_mat, p.n_meshes) : 0x7fffffff;
     if (PRIMARY) best_prim = (int32_t)CW(C_BPRIM, s);
     cand = PW(W_CAND, s);
     const uint32_t mf = PW(W_MFLAGS, s);
@@ -692,6 +693,10 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         PW(W_TOPN, s) = top.x;
         PW(W_TOPD, s) = top.y;
         PW(W_KEY, s) = trav_key();
+        if (prefetch) {  // the slot now waits for a later round: start fetching what that round will read
+          if (cur >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.nodes + RR_NODE_QUADS * (size_t)cur));
+          if (pend_cnt) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.tri_geom + 3 * (size_t)pend_slot));
+        }
       }
     } else if (phase == PH_LEAF) {
       // ================= leaf tests =================
@@ -789,7 +794,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
           PSF(W_LT, s, lt);
           PW(W_LPRIM, s) = (uint32_t)lprim;
           PW(W_MFLAGS, s) = mflags | (lback ? 0x80000000u : 0u);
-          PST3(W_LNX, s, n3);
+          CST3(C_LNX, s, n3);
         }
         if (pend_cnt == 0 && ref_is_leaf(cur)) {  // the leaf this slot was waiting on becomes the postponed one
           pend_slot = ref_slot(cur);
@@ -838,7 +843,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         const uint32_t bm = PW(W_BMAT, s);
         best_mat = (int32_t)(bm & 0x7fffffffu);
         best_back = (bm >> 31) != 0u;
-        if (PRIMARY) { best_mesh = (int32_t)PW(W_BMESH, s); best_prim = (int32_t)CW(C_BPRIM, s); }
+        if (PRIMARY) { best_mesh = min(best_mat, p.n_meshes); best_prim = (int32_t)CW(C_BPRIM, s); }
         pix = (int32_t)PW(W_PIX, s);
         if (PRIMARY) {
           if (p.hit_mesh) p.hit_mesh[pix] = best_dst < INFINITY ? best_mesh : -1;

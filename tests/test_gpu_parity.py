@@ -361,3 +361,31 @@ def test_statistical_parity_at_config_spp(renderer, knight_obj):
     want, wrad, _ = Oracle(t, m, r).render(cam, W, H, 64, 50, radiance=True)
     assert_images_equal(got, want, "64 spp")
     assert np.array_equal(bits(grad), bits(wrad))
+
+
+def _device_count():
+    import ctypes as C
+
+    n = C.c_int(0)
+    _abi.lib().rr_device_count(C.byref(n))
+    return n.value
+
+
+def test_two_gpus_share_one_tile_queue_and_frame(knight_obj):
+    """multiThreadedCompute (src/image.hpp:280-350) on two GPUs: both pop tiles from device 0's atomic counter and
+    store pixels into device 0's frame over NVLink; the image is identical to the single-GPU one."""
+    if _device_count() < 2:
+        pytest.skip("needs two GPUs with peer access")
+    s = rr.default_scene(knight_obj)
+    W, H = 640, 360
+    cam = rr.default_camera(W, H)
+    one = rr.Renderer((0,))
+    one.upload(s)
+    want, _, st1 = one.render(cam, W, H, 4, 12)
+    one.close()
+    two = rr.Renderer((0, 1))
+    two.upload(s)
+    got, _, st2 = two.render(cam, W, H, 4, 12)
+    two.close()
+    assert np.array_equal(got, want)
+    assert st2["rays"] == st1["rays"] and st2["tiles"] == st1["tiles"]

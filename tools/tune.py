@@ -53,18 +53,22 @@ def run(tune, label):
 
 
 #        wP wH wS wT wL keep spec ctas
-base = [4, 4, 4, 4, 4, 22, 1, 0]
+base = [4, 4, 4, 4, 4, 16, 1, 0]
 run(base, "base")
 if a.grid == "default":
-    for keep in (1, 8, 12, 16, 20, 24, 32):
+    for keep in (1, 8, 12, 20, 24, 32):
         t = list(base); t[5] = keep
         run(t, f"keep={keep}")
+    for keep in (8, 16, 24, 32):
+        t = list(base); t[5] = keep; t[6] = 3
+        run(t, f"prefetch keep={keep}")
     t = list(base); t[6] = 0
     run(t, "spec=0")
-    for ctas in (1, 2, 3):
+    for ctas in (3, 4, 5):
         t = list(base); t[7] = ctas
         run(t, f"ctas={ctas}")
     for i, name in ((3, "wT"), (4, "wL"), (2, "wS"), (1, "wH")):
         for w in (2, 8):
             t = list(base); t[i] = w
             run(t, f"{name}={w}")
+    run(base, "base again")
