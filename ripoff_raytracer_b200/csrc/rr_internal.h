@@ -15,12 +15,12 @@
 #define RR_TILE_H 4
 #define RR_NODE_QUADS 8   // float4 per traversal node (4-wide node, 128 bytes)
 #ifndef RR_POOL
-#define RR_POOL 64        // path slots per warp of the render kernel (rr_render.cu)
+#define RR_POOL 96        // path slots per warp of the render kernel (rr_render.cu)
 #endif
 #ifndef RR_MIN_CTAS
-#define RR_MIN_CTAS 6     // resident 128-thread CTAs per SM the render kernel is compiled for
+#define RR_MIN_CTAS 5     // resident 128-thread CTAs per SM the render kernel is compiled for
 #endif
-#define RR_POOL_WORDS 29  // 32-bit words of one slot in shared memory
+#define RR_POOL_WORDS 28  // 32-bit words of one slot in shared memory
 #define RR_COLD_WORDS 25  // ... and in the per-warp global scratch
 
 namespace rr {

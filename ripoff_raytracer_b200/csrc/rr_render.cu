@@ -290,7 +290,7 @@ enum {
   W_KEY = 0, W_PIX,
   W_OX, W_OY, W_OZ, W_DX, W_DY, W_DZ,           // world ray
   W_BDST, W_BMAT,                               // closest hit so far: distance, material | back << 31 (mesh = min(material, n_meshes))
-  W_CAND, W_M, W_MFLAGS,                        // candidate meshes of the chunk, current mesh (-1: new ray), flags | lback << 31
+  W_CAND, W_M,                                  // candidate meshes of the chunk; (current mesh + 1, 0 = new ray) | lback << 31
   W_LOX, W_LOY, W_LOZ, W_LDX, W_LDY, W_LDZ, W_LIX, W_LIY, W_LIZ,  // mesh-local ray and its reciprocal direction
   W_LT, W_LPRIM,                                // closest hit inside the current mesh (its normal: C_LNX)
   W_CUR, W_SPC, W_PSLOT,                        // traversal: node ref, stack pointer | postponed count << 8, postponed slot
@@ -377,22 +377,17 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
 
   // Up to 32 slots with `ready` set are handed to the lanes (lane j gets the j-th ready slot); returns how many.
   auto select = [&](const bool (&ready)[ROUNDS]) -> int {
-    static_assert(ROUNDS == 2, "select() serves the two halves of the pool");
     __syncwarp();
-    const unsigned b0 = __ballot_sync(full, ready[0]), b1 = __ballot_sync(full, ready[1]);
-    const bool flip = (round & 1u) != 0u;  // alternate which half of the pool is served first (no dynamic indexing:
-                                           // a runtime-indexed ready[] would live in local memory)
-    const unsigned bf = flip ? b1 : b0, bs = flip ? b0 : b1;
-    const bool rf = flip ? ready[1] : ready[0], rs = flip ? ready[0] : ready[1];
-    const unsigned of = flip ? 32u : 0u, os = flip ? 0u : 32u;
-    const int nf = __popc(bf);
-    if (rf) sel[__popc(bf & lanes_below)] = lane + of;
-    if (rs) {
-      const int rank = nf + __popc(bs & lanes_below);
-      if (rank < 32) sel[rank] = lane + os;
+    int base = 0;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {  // static indexing only: a runtime-indexed ready[] would live in local memory
+      const unsigned b = __ballot_sync(full, ready[r]);
+      const int rank = base + __popc(b & lanes_below);
+      if (ready[r] && rank < 32) sel[rank] = lane + 32u * r;
+      base += __popc(b);
     }
     __syncwarp();
-    const int n = min(nf + __popc(bs), 32);
+    const int n = min(base, 32);
     s = (int)lane < n ? (int)sel[lane] : -1;
     return n;
   };
@@ -527,8 +522,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     PW(W_BMAT, s) = (uint32_t)best_mat | (best_back ? 0x80000000u : 0u);
     if (PRIMARY) CW(C_BPRIM, s) = (uint32_t)best_prim;
     PW(W_CAND, s) = cand;
-    PW(W_M, s) = (uint32_t)m;
-    PW(W_MFLAGS, s) = (mflags & 0x7fffffffu) | (lback ? 0x80000000u : 0u);
+    PW(W_M, s) = (uint32_t)(m + 1) | (lback ? 0x80000000u : 0u);
     PST3(W_LOX, s, lo);
     PST3(W_LDX, s, ld);
     PST3(W_LIX, s, linv);
@@ -547,19 +541,22 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     best_mesh = best_dst < INFINITY ? min(best_mat, p.n_meshes) : 0x7fffffff;
     if (PRIMARY) best_prim = (int32_t)CW(C_BPRIM, s);
     cand = PW(W_CAND, s);
-    const uint32_t mf = PW(W_MFLAGS, s);
-    mflags = mf & 0x7fffffffu;
-    lback = (mf >> 31) != 0u;
+    mflags = __float_as_uint(__ldg(&p.meshes[m].wmin.w));  // m and lback were decoded from W_M by the caller
     lo = PLD3(W_LOX, s);
     ld = PLD3(W_LDX, s);
     lt = PF(W_LT, s);
     lprim = (int32_t)PW(W_LPRIM, s);
   };
+  auto load_mesh_word = [&]() {  // W_M -> m (-1: new ray), lback
+    const uint32_t mw = PW(W_M, s);
+    m = (int)(mw & 0x7fffffffu) - 1;
+    lback = (mw >> 31) != 0u;
+  };
   // shade / pixel hand the new ray to the setup phase: W_M = -1 marks "collect the candidates first"
   auto store_new_ray = [&]() {
     PST3(W_OX, s, origin);
     PST3(W_DX, s, dir);
-    PW(W_M, s) = 0xffffffffu;
+    PW(W_M, s) = 0u;
     PW(W_KEY, s) = K_S;
   };
 
@@ -715,9 +712,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         lprim = (int32_t)PW(W_LPRIM, s);
         lo = PLD3(W_LOX, s);
         ld = PLD3(W_LDX, s);
-        const uint32_t mf = PW(W_MFLAGS, s);
-        mflags = mf & 0x7fffffffu;
-        lback = (mf >> 31) != 0u;
+        load_mesh_word();
+        mflags = __float_as_uint(__ldg(&p.meshes[m].wmin.w));
         const uint32_t slot = pend_slot;
         pend_slot++;
         pend_cnt--;
@@ -793,7 +789,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         if (accepted) {
           PSF(W_LT, s, lt);
           PW(W_LPRIM, s) = (uint32_t)lprim;
-          PW(W_MFLAGS, s) = mflags | (lback ? 0x80000000u : 0u);
+          PW(W_M, s) = (uint32_t)(m + 1) | (lback ? 0x80000000u : 0u);
           CST3(C_LNX, s, n3);
         }
         if (pend_cnt == 0 && ref_is_leaf(cur)) {  // the leaf this slot was waiting on becomes the postponed one
@@ -816,7 +812,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       if (s >= 0) {
         origin = PLD3(W_OX, s);
         dir = PLD3(W_DX, s);
-        m = (int)PW(W_M, s);
+        load_mesh_word();
         const V3 winv = mk(rcp_approx(dir.x), rcp_approx(dir.y), rcp_approx(dir.z));
         const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
         if (m < 0) {
@@ -994,7 +990,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
 
 void default_tuning(Tuning& t) {
   for (int k = 0; k < 5; ++k) t.weight[k] = 4;
-  t.trav_keep = 16;
+  t.trav_keep = 20;
   t.speculate = 1;
   t.ctas_per_sm = 0;
 }

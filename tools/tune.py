@@ -56,7 +56,7 @@ def run(tune, label):
 base = [4, 4, 4, 4, 4, 16, 1, 0]
 run(base, "base")
 if a.grid == "default":
-    for keep in (1, 8, 12, 20, 24, 32):
+    for keep in (8, 12, 20, 24, 28, 32):
         t = list(base); t[5] = keep
         run(t, f"keep={keep}")
     for keep in (8, 16, 24, 32):
