@@ -389,3 +389,25 @@ def test_two_gpus_share_one_tile_queue_and_frame(knight_obj):
     two.close()
     assert np.array_equal(got, want)
     assert st2["rays"] == st1["rays"] and st2["tiles"] == st1["tiles"]
+
+
+def test_command_line_driver_writes_the_same_bmp(knight_obj, tmp_path):
+    """gputest_b200 (csrc/rr_main.cpp): the reference's prompts and scene assembly over the C ABI; its output.bmp is
+    byte-identical to the one the library path writes for the same settings."""
+    import subprocess
+    from pathlib import Path
+
+    exe = Path(_abi.PKG_DIR) / "csrc" / "gputest_b200"
+    if not exe.exists():
+        pytest.skip("gputest_b200 not built")
+    W, H, spp, bounces = 96, 64, 3, 7
+    answers = f"\n{W}\n{H}\n{spp}\n{bounces}\n{knight_obj}\n"  # device prompt: empty line = default, as in the reference
+    p = subprocess.run([str(exe)], input=answers, text=True, capture_output=True, cwd=tmp_path, timeout=120)
+    assert p.returncode == 0, p.stderr
+    assert "Wrote output.bmp" in p.stdout
+    r = rr.Renderer()
+    r.upload(rr.default_scene(knight_obj))
+    img = r.render_plain(rr.default_camera(W, H), W, H, spp, bounces)
+    r.close()
+    rr.write_bmp(tmp_path / "want.bmp", img)
+    assert (tmp_path / "output.bmp").read_bytes() == (tmp_path / "want.bmp").read_bytes()
