@@ -26,8 +26,23 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
-# NCCL writes its banner / debug lines to stdout by default; stdout carries exactly one JSON line
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+class stdout_to_stderr:
+    """NCCL prints its version banner / debug lines to fd 1 when the communicator is created; stdout must carry
+    exactly one JSON line, so fd 1 points at stderr while the process group and its first collective come up."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
 
 F_BOX, F_TRI, F_SPH = 24, 53, 24     # algorithmic flop per test (SURVEY.md 8d; sphere: DESIGN.md 6)
 B_BOX, B_TRI, B_SPH = 32, 48, 16     # algorithmic bytes per test
@@ -196,7 +211,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the render path has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()  # creates the NCCL communicator (and prints its banner) now
+            torch.cuda.synchronize()
 
     def barrier():
         torch.cuda.synchronize()

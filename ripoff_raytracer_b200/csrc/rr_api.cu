@@ -275,9 +275,10 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   cudaFree(d_mesh_pos);
   cudaFree(d.tb.nodes); d.tb.nodes = nullptr;  // copied into d.nodes
   cudaFree(d.sb.nodes); d.sb.nodes = nullptr;
-  if (d.tb.max_depth > RR_STACK || d.sb.max_depth > RR_STACK)
+  static_assert(3 * ((RR_MAX_DEPTH + 1) / 2) <= RR_STACK, "traversal stack too small for the accepted depth");
+  if (d.tb.max_depth > RR_MAX_DEPTH || d.sb.max_depth > RR_MAX_DEPTH)
     return fail(RR_ERR_BVH_DEPTH, "LBVH depth " + std::to_string(std::max(d.tb.max_depth, d.sb.max_depth)) +
-                                      " exceeds the traversal stack (" + std::to_string(RR_STACK) + ")");
+                                      " exceeds the traversal stack (" + std::to_string(RR_MAX_DEPTH) + " levels)");
   return RR_OK;
 }
 

@@ -8,7 +8,8 @@
 
 #define RR_EPSILON 1e-6f              // reference src/Trace.cl:6
 #define RR_TAU 6.28318530717958647692f // reference src/Trace.cl:5
-#define RR_STACK 64                   // reference src/Trace.cl:2 (BVHStackSize)
+#define RR_MAX_DEPTH 64               // deepest binary hierarchy accepted (the reference's BVHStackSize, src/Trace.cl:2)
+#define RR_STACK 96                   // traversal stack entries: a 4-wide node pushes up to 3 per two binary levels
 #define RR_MAX_INVISIBLE_PASSES 256u   // pass-throughs of Invisible surfaces per path before it is ended
 #define RR_DIRECT_MAX 4               // segments this small are tested without a hierarchy
 #define RR_TILE_W 8                   // default work tile: 8 x 4 pixels = one warp

@@ -599,18 +599,15 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       } else {
         cur = REF_END; sp = 0; pend_cnt = 0;
       }
+      // which quad of a node holds the entry / exit plane of each axis (node layout: min.x min.y min.z max.x max.y max.z)
+      const int qnx = linv.x < 0.0f ? 3 : 0, qny = linv.y < 0.0f ? 4 : 1, qnz = linv.z < 0.0f ? 5 : 2;
+      const int qfx = 3 - qnx, qfy = 5 - qny, qfz = 7 - qnz;
       uint2* const stk = stack + (mine ? s : 0);
       // Entry sp-1 (the top) is kept in registers / shared memory, entries 0..sp-2 in the global scratch.  A pop
       // hands out the top at once and only ISSUES the load of the next entry, so that its L2 latency overlaps
       // with the node fetch that follows instead of preceding it.
       uint2 top = make_uint2(0u, 0u);
       if (mine && sp > 0) top = make_uint2(PW(W_TOPN, s), PW(W_TOPD, s));
-      auto push = [&](int32_t ref, uint32_t dist_bits) {
-        if (sp >= RR_STACK) return;
-        if (sp > 0) stk[(sp - 1) * POOL] = top;
-        top = make_uint2((uint32_t)ref, dist_bits);
-        sp++;
-      };
       // Pops the stack / postpones leaves until `cur` is an inner node, a leaf the slot must wait for, or REF_END.
       auto resolve = [&](int32_t next) {
         for (;;) {
@@ -637,21 +634,23 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         if (step) {
           if (cur == REF_POP) resolve(REF_POP);
           if (cur >= 0) {
-            // one 128-byte node: the boxes of up to four children (SoA) and their references
+            // one 128-byte node: the boxes of up to four children (SoA) and their references.  The quads holding the
+            // planes the ray ENTERS / LEAVES through are picked by the sign of its direction (qn*/qf*, set up
+            // once per run), so no per-child min/max is needed to order the two planes of a slab.
             const float4* nd = p.nodes + RR_NODE_QUADS * (size_t)cur;
-            const float4 lx = __ldg(nd), ly = __ldg(nd + 1), lz = __ldg(nd + 2), hx = __ldg(nd + 3), hy = __ldg(nd + 4),
-                         hz = __ldg(nd + 5), rf = __ldg(nd + 6);
+            const float4 nx = __ldg(nd + qnx), ny = __ldg(nd + qny), nz = __ldg(nd + qnz), fx = __ldg(nd + qfx),
+                         fy = __ldg(nd + qfy), fz = __ldg(nd + qfz), rf = __ldg(nd + 6);
             if (COUNT) c_box += (unsigned)__float_as_int(__ldg(&nd[7].x));
             // sort key of a child: entry distance (clamped at 0, two low mantissa bits dropped) | child number;
-            // a child the ray misses sorts last
-            uint32_t k0, k1, k2, k3;
-            {
-              float tn;
-              k0 = box_cull(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, linv, lnoi, lt, tn) ? ((__float_as_uint(fmaxf(tn, 0.0f)) & ~3u) | 0u) : 0xffffffffu;
-              k1 = box_cull(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, linv, lnoi, lt, tn) ? ((__float_as_uint(fmaxf(tn, 0.0f)) & ~3u) | 1u) : 0xffffffffu;
-              k2 = box_cull(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, linv, lnoi, lt, tn) ? ((__float_as_uint(fmaxf(tn, 0.0f)) & ~3u) | 2u) : 0xffffffffu;
-              k3 = box_cull(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, linv, lnoi, lt, tn) ? ((__float_as_uint(fmaxf(tn, 0.0f)) & ~3u) | 3u) : 0xffffffffu;
-            }
+            // a child the ray misses (or an unused NaN box) sorts last
+            auto child_key = [&](float pnx, float pny, float pnz, float pfx, float pfy, float pfz, uint32_t c) -> uint32_t {
+              const float tn = fmaxf(fmaxf(__fmaf_rn(pnx, linv.x, lnoi.x), __fmaf_rn(pny, linv.y, lnoi.y)), __fmaf_rn(pnz, linv.z, lnoi.z));
+              const float tf = fminf(fminf(__fmaf_rn(pfx, linv.x, lnoi.x), __fmaf_rn(pfy, linv.y, lnoi.y)), __fmaf_rn(pfz, linv.z, lnoi.z));
+              const float t0 = fmaxf(tn, 0.0f);
+              return (tf >= t0 && tn <= lt) ? ((__float_as_uint(t0) & ~3u) | c) : 0xffffffffu;
+            };
+            uint32_t k0 = child_key(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, 0u), k1 = child_key(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, 1u),
+                     k2 = child_key(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, 2u), k3 = child_key(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, 3u);
             {  // 5-comparator sorting network, ascending
               uint32_t t;
               t = min(k0, k1); k1 = max(k0, k1); k0 = t;
@@ -660,24 +659,29 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
               t = min(k1, k3); k3 = max(k1, k3); k1 = t;
               t = min(k1, k2); k2 = max(k1, k2); k1 = t;
             }
+            // the references in sorted order, computed once for all lanes (two-level select on the child number)
             auto ref_of = [&](uint32_t k) -> int32_t {
-              const uint32_t c = k & 3u;
-              return __float_as_int(c == 0u ? rf.x : c == 1u ? rf.y : c == 2u ? rf.z : rf.w);
+              const float lo2 = (k & 1u) ? rf.y : rf.x, hi2 = (k & 1u) ? rf.w : rf.z;
+              return __float_as_int((k & 2u) ? hi2 : lo2);
             };
-            int32_t next = REF_POP;
-            if (k0 != 0xffffffffu) {
-              int32_t r0 = ref_of(k0);
-              if (r0 < REF_POP && pend_cnt == 0) {  // the nearest child is a leaf: postpone it and go on with the next one
-                pend_slot = ref_slot(r0); pend_cnt = 1;
-                k0 = k1; k1 = k2; k2 = k3; k3 = 0xffffffffu;
-                r0 = k0 != 0xffffffffu ? ref_of(k0) : REF_POP;
-              }
-              // the farther children go to the stack, farthest first
-              if (k3 != 0xffffffffu) push(ref_of(k3), k3 & ~3u);
-              if (k2 != 0xffffffffu) push(ref_of(k2), k2 & ~3u);
-              if (k1 != 0xffffffffu) push(ref_of(k1), k1 & ~3u);
-              next = r0;
+            int32_t r0 = ref_of(k0), r1 = ref_of(k1), r2 = ref_of(k2), r3 = ref_of(k3);
+            int hits = (k0 != 0xffffffffu) + (k1 != 0xffffffffu) + (k2 != 0xffffffffu) + (k3 != 0xffffffffu);
+            if (hits > 0 && r0 < REF_POP && pend_cnt == 0) {  // the nearest child is a leaf: postpone it, go on with the next one
+              pend_slot = ref_slot(r0); pend_cnt = 1;
+              k0 = k1; k1 = k2; k2 = k3;
+              r0 = r1; r1 = r2; r2 = r3;
+              hits--;
             }
+            // misses sort last, so the children to push are a suffix of the hits: farthest first, the nearest of
+            // them ends up as the (register-resident) top; the previous top is spilled once
+            if (hits >= 2 && sp + hits - 1 <= RR_STACK) {
+              if (sp > 0) stk[(sp - 1) * POOL] = top;
+              if (hits == 4) { stk[sp * POOL] = make_uint2((uint32_t)r3, k3 & ~3u); sp++; }
+              if (hits >= 3) { stk[sp * POOL] = make_uint2((uint32_t)r2, k2 & ~3u); sp++; }
+              top = make_uint2((uint32_t)r1, k1 & ~3u);
+              sp++;
+            }
+            const int32_t next = hits > 0 ? r0 : REF_POP;
             resolve(next);
           }
         }
