@@ -311,6 +311,22 @@ constexpr int32_t REF_END = (int32_t)0x80000000;  // traversal of this mesh fini
 __device__ __forceinline__ bool ref_is_leaf(int32_t r) { return r < REF_POP && r != REF_END; }
 __device__ __forceinline__ uint32_t ref_slot(int32_t r) { return (uint32_t)(-r) - 2u; }
 
+// World-box tests of the meshes [base, base + 32): bit k set = the ray enters mesh base + k's box before `tmax`.
+// Every lane walks the whole chunk, so the loop is convergent.  Out of line: one copy serves shade, pixel and setup.
+__device__ __noinline__ uint32_t scan_meshes_fn(const DMesh* __restrict__ meshes, int32_t base, int32_t last_mesh, V3 winv,
+                                                V3 wnoi, float tmax) {
+  uint32_t mask = 0;
+  const int32_t end = min(base + 32, last_mesh + 1);
+  for (int32_t k = base; k < end; ++k) {
+    const DMesh* M = meshes + k;
+    const float4 wlo = __ldg(&M->wmin), whi = __ldg(&M->wmax);
+    float tn;
+    const bool hit = box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, tmax, tn);
+    if (hit && !(__float_as_uint(wlo.w) & RR_MF_SKIP)) mask |= 1u << (k - base);
+  }
+  return mask;
+}
+
 template <bool COUNT, bool PRIMARY>
 __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p) {
   extern __shared__ uint32_t pool_all[];
@@ -396,29 +412,9 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     return ((cur >= REF_POP && (speculate || pend_cnt == 0)) ? K_T : 0u) | (pend_cnt ? K_L : 0u);
   };
 
-  // World-box tests of the meshes [base, base + 32): bit k set = the ray enters mesh base + k's box before `tmax`.
-  // Every lane walks the whole chunk, so the loop is convergent.
   auto scan_meshes = [&](int32_t base, const V3& winv, const V3& wnoi, float tmax) -> uint32_t {
-    uint32_t mask = 0;
-    const int32_t end = min(base + 32, p.last_mesh + 1);
-    for (int32_t k = base; k < end; ++k) {
-      const DMesh* M = p.meshes + k;
-      const float4 wlo = __ldg(&M->wmin), whi = __ldg(&M->wmax);
-      float tn;
-      const bool hit = box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, tmax, tn);
-      if (hit && !(__float_as_uint(wlo.w) & RR_MF_SKIP)) mask |= 1u << (k - base);
-    }
-    if (COUNT) c_box += (unsigned)max(end - base, 0);
-    return mask;
-  };
-  // A new ray starts: reset the closest hit (src/Trace.cl:437-444) and collect the candidate meshes.
-  auto begin_ray = [&](const V3& winv, const V3& wnoi) {
-    best_dst = INFINITY; best_mat = 0; best_mesh = 0x7fffffff; best_prim = -1; best_back = false;
-    lprim = NO_PRIM;
-    m = 0;
-    cand = scan_meshes(0, winv, wnoi, INFINITY);
-    cur = REF_END; sp = 0; pend_cnt = 0; pend_slot = 0;
-    n_rays++;
+    if (COUNT) c_box += (unsigned)max(min(base + 32, p.last_mesh + 1) - base, 0);
+    return scan_meshes_fn(p.meshes, base, p.last_mesh, winv, wnoi, tmax);
   };
   // The mesh just traversed has a closest hit (local space): LocalToWorldHit and the keep-min of
   // src/Trace.cl:465-481.  Meshes are visited in our own order, so equal distances are resolved by the
@@ -552,11 +548,20 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     m = (int)(mw & 0x7fffffffu) - 1;
     lback = (mw >> 31) != 0u;
   };
-  // shade / pixel hand the new ray to the setup phase: W_M = -1 marks "collect the candidates first"
+  // shade / pixel start the next segment: reset the closest hit (src/Trace.cl:437-444), collect the candidate
+  // meshes (convergent here: every lane of these phases does it) and hand the slot to the setup phase
   auto store_new_ray = [&]() {
     PST3(W_OX, s, origin);
     PST3(W_DX, s, dir);
-    PW(W_M, s) = 0u;
+    const V3 winv = mk(rcp_approx(dir.x), rcp_approx(dir.y), rcp_approx(dir.z));
+    const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
+    PW(W_CAND, s) = scan_meshes(0, winv, wnoi, INFINITY);
+    PW(W_M, s) = 1u;  // chunk 0, no backface flag
+    PSF(W_BDST, s, INFINITY);
+    PW(W_BMAT, s) = 0u;
+    PW(W_LPRIM, s) = (uint32_t)NO_PRIM;
+    if (PRIMARY) CW(C_BPRIM, s) = 0xffffffffu;
+    n_rays++;
     PW(W_KEY, s) = K_S;
   };
 
@@ -819,12 +824,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         load_mesh_word();
         const V3 winv = mk(rcp_approx(dir.x), rcp_approx(dir.y), rcp_approx(dir.z));
         const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
-        if (m < 0) {
-          begin_ray(winv, wnoi);
-        } else {
-          load_ray_state();
-          finish_mesh();
-        }
+        load_ray_state();
+        finish_mesh();  // nothing to finish for a new ray (no local hit)
         const uint32_t key = enter_next_mesh(winv, wnoi);
         store_ray_state(key);
       }
