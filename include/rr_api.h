@@ -185,7 +185,9 @@ typedef struct rr_stats {
  * rgba_out: width*height*4 bytes, row 0 = top, RGBA, alpha = 255
  * (src/image.hpp:267-271).  Blocking.  frameIndex is kernel arg 7, which the
  * reference always evaluates to 0 (src/image.hpp:228).  tile_size == 0 picks
- * the library default; the image does not depend on it. */
+ * the library default (8 x 4 pixels, the unit one warp pops from the tile
+ * queue); larger values are honoured up to 32 x 32.  The image does not depend
+ * on it. */
 int rr_render(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_bounces,
               int32_t frame_index, uint32_t tile_size, uint8_t* rgba_out);
 

@@ -318,8 +318,11 @@ static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam
   for (int k = 0; k < 3; ++k) p.cam.pos[k] = cam->position.s[k];
   p.cam.pitch = cam->pitch; p.cam.yaw = cam->yaw; p.cam.roll = cam->roll; p.cam.fov = cam->fov; p.cam.aspect = cam->aspectRatio;
   p.width = W; p.height = H; p.spp = spp; p.max_bounces = bounces; p.frame_index = frame_index;
-  p.tile_w = tile_size ? tile_size : RR_TILE_W;
-  p.tile_h = tile_size ? tile_size : RR_TILE_H;
+  // Work tiles: 8 x 4 pixels by default.  A caller's tile size (the reference's TILE_SIZE, src/settings.hpp:48, bounds
+  // the length of one OpenCL launch) is honoured up to 32 x 32: a tile is the unit ONE warp pops from the queue, and
+  // the image does not depend on the tiling (src/image.hpp:228: the per-tile seed term is 0).
+  p.tile_w = tile_size ? std::min<uint32_t>(tile_size, 32u) : RR_TILE_W;
+  p.tile_h = tile_size ? std::min<uint32_t>(tile_size, 32u) : RR_TILE_H;
   p.tiles_x = (W + p.tile_w - 1) / p.tile_w;
   p.tiles_y = (H + p.tile_h - 1) / p.tile_h;
   p.tile_begin = 0;
