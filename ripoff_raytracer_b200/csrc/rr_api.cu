@@ -57,6 +57,7 @@ struct Device {
   uint2* stack = nullptr;               // traversal stacks of the render kernel (scratch)
   uint32_t* cold = nullptr;             // cold slot words of the render kernel (scratch)
   uint32_t stack_warps = 0;
+  uint32_t stack_entries = 0;           // per slot: 3 per level of the deepest wide hierarchy + slack
   unsigned long long* queue = nullptr;  // local tile counter
   Counters* counters = nullptr;
   // shared (multi-process) attachments
@@ -275,7 +276,17 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   cudaFree(d_mesh_pos);
   cudaFree(d.tb.nodes); d.tb.nodes = nullptr;  // copied into d.nodes
   cudaFree(d.sb.nodes); d.sb.nodes = nullptr;
-  static_assert(3 * ((RR_MAX_DEPTH + 1) / 2) <= RR_STACK, "traversal stack too small for the accepted depth");
+  static_assert(3 * RR_MAX_DEPTH + 4 <= RR_STACK_MAX, "stack pointer must fit the slot word");
+  {  // traversal stacks sized for THIS scene: a wide node pushes at most 3 children per level
+    const uint32_t need = 3u * std::max(d.tb.wide_levels, d.sb.wide_levels) + 4u;
+    if (need > d.stack_entries || !d.stack) {
+      cudaFree(d.stack);
+      d.stack = nullptr;
+      d.stack_entries = 0;
+      RR_CUDA(cudaMalloc(&d.stack, (size_t)d.stack_warps * render_stack_bytes_per_warp(need)));
+      d.stack_entries = need;
+    }
+  }
   if (d.tb.max_depth > RR_MAX_DEPTH || d.sb.max_depth > RR_MAX_DEPTH)
     return fail(RR_ERR_BVH_DEPTH, "LBVH depth " + std::to_string(std::max(d.tb.max_depth, d.sb.max_depth)) +
                                       " exceeds the traversal stack (" + std::to_string(RR_MAX_DEPTH) + " levels)");
@@ -328,6 +339,7 @@ static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam
   p.tile_begin = 0;
   p.tile_stride = 1;
   p.stack = d.stack;
+  p.stack_entries = d.stack_entries;
   p.cold = d.cold;
   p.stack_warps = d.stack_warps;
   p.queue = d.queue;
@@ -489,8 +501,7 @@ int rr_create(const int* cuda_ordinals, int n, rr_ctx** out) {
     if (e == cudaSuccess) e = cudaMalloc(&d.counters, sizeof(Counters));
     if (e == cudaSuccess) {
       d.stack_warps = (uint32_t)(prop.multiProcessorCount * render_max_warps_per_sm());
-      e = cudaMalloc(&d.stack, (size_t)d.stack_warps * render_stack_bytes_per_warp());
-      if (e == cudaSuccess) e = cudaMalloc(&d.cold, (size_t)d.stack_warps * render_cold_bytes_per_warp());
+      e = cudaMalloc(&d.cold, (size_t)d.stack_warps * render_cold_bytes_per_warp());
     }
     if (e != cudaSuccess) { rr_destroy(ctx); return cuda_fail(e, "rr_create"); }
     d.sm_count = prop.multiProcessorCount;

@@ -9,7 +9,7 @@
 #define RR_EPSILON 1e-6f              // reference src/Trace.cl:6
 #define RR_TAU 6.28318530717958647692f // reference src/Trace.cl:5
 #define RR_MAX_DEPTH 64               // deepest binary hierarchy accepted (the reference's BVHStackSize, src/Trace.cl:2)
-#define RR_STACK 96                   // traversal stack entries: a 4-wide node pushes up to 3 per two binary levels
+#define RR_STACK_MAX 200               // traversal stack entries at most: a 4-wide node pushes up to 3 per level
 #define RR_MAX_INVISIBLE_PASSES 256u   // pass-throughs of Invisible surfaces per path before it is ended
 #define RR_DIRECT_MAX 4               // segments this small are tested without a hierarchy
 #define RR_TILE_W 8                   // default work tile: 8 x 4 pixels = one warp
@@ -47,7 +47,8 @@ struct Lbvh {
   uint32_t* seg_sfirst = nullptr; // [n_segs] first slot
   // traversal arrays
   float4* nodes = nullptr;     // [n*RR_NODE_QUADS] 4-wide traversal nodes: delta-inflated child boxes + refs
-  uint32_t max_depth = 0;
+  uint32_t max_depth = 0;    // deepest leaf of the binary hierarchy (root = 1)
+  uint32_t wide_levels = 0;  // levels of the 4-wide hierarchy
 };
 
 // Per-mesh record read by the kernel: ten float4 (LDG.128 each).  When the scene has spheres one
@@ -117,7 +118,8 @@ struct RenderParams {
   int32_t frame_index;
   uint32_t tile_w, tile_h, tiles_x, tiles_y;
   uint32_t tile_begin, tile_stride;  // static partition: this rank renders tile_begin + k*tile_stride ...
-  uint2* stack;                      // traversal stacks, RR_STACK * RR_POOL entries per warp (scratch)
+  uint2* stack;                      // traversal stacks, stack_entries * RR_POOL entries per warp (scratch)
+  uint32_t stack_entries;            // 3 per level of the deepest 4-wide hierarchy + slack
   uint32_t* cold;                    // cold slot words, RR_COLD_WORDS * RR_POOL per warp (scratch)
   uint32_t stack_warps;              // warps the scratch was sized for
   unsigned long long* queue;         // tile counter (may live in a peer GPU's memory)
@@ -159,7 +161,7 @@ cudaError_t launch_pack_spheres(const rr_sphere* d_sph, const uint32_t* d_order,
 cudaError_t launch_render(const RenderParams& p, bool count_tests, int sm_count, cudaStream_t s);
 cudaError_t launch_primary(const RenderParams& p, int sm_count, cudaStream_t s);
 void default_tuning(Tuning& t);
-size_t render_stack_bytes_per_warp();
+size_t render_stack_bytes_per_warp(uint32_t stack_entries);
 size_t render_cold_bytes_per_warp();
 int render_max_warps_per_sm();
 cudaError_t launch_math_probe(int fn, const float* x, const float* y, float* out, uint64_t n, cudaStream_t s);

@@ -399,62 +399,81 @@ __global__ void k_refit(uint64_t n, const uint32_t* __restrict__ order, const fl
   if (depth > 1) atomicMax(max_depth, depth);
 }
 
-// Traversal node: a 4-wide node, 128 bytes = one cache line, made of a binary LBVH node and its grandchildren
-// (a child that is a leaf stays a child).  Only binary nodes at EVEN depth below their segment root become
-// wide nodes; they keep their binary index, the odd ones in between are never fetched.
+// Traversal node: a 4-wide node, 128 bytes = one cache line, collapsed from the binary LBVH top-down: a wide node
+// starts from the two children of a binary node and keeps replacing the inner child with the LARGEST SURFACE AREA by
+// that child's two children until it has four (or only leaves are left).  Every inner child becomes a wide node of
+// the next level (it keeps its binary index; binary nodes that were absorbed are never fetched).
 //   q0..q2 = min.x[4] min.y[4] min.z[4]   q3..q5 = max.x[4] max.y[4] max.z[4]   q6 = ref[4]   q7 = (#children, -, -, -)
 // Unused child slots hold a NaN box: every comparison of the slab test fails, no ray enters it (an inverted
 // box would not do: the test orders the two planes of a slab itself).  The boxes are inflated by
 // the segment's box_delta() so that culling is conservative (the closest hit then does not depend on the order
 // in which a traversal visits the nodes).  ref: inner = index in the combined node array (ref_offset added),
 // leaf = -(slot + 2) (so that -1 is free for "pop", rr_render.cu).
-__global__ void k_pack_nodes(uint64_t n, const uint32_t* __restrict__ order, const float* __restrict__ prim_box,
-                             const int32_t* __restrict__ left, const int32_t* __restrict__ right,
-                             const int32_t* __restrict__ parent, const float* __restrict__ bounds,
-                             const unsigned int* __restrict__ flags, const uint32_t* __restrict__ seg_sfirst, int n_segs,
-                             const float* __restrict__ seg_box, int32_t ref_offset, float4* __restrict__ nodes) {
-  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n) return;
+__global__ void k_wide_roots(const uint32_t* __restrict__ seg_sfirst, const uint32_t* __restrict__ seg_count, int n_segs,
+                             int32_t* __restrict__ frontier, unsigned int* __restrict__ count) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_segs) return;
+  if (seg_count[s] >= 2u) frontier[atomicAdd(count, 1u)] = (int32_t)seg_sfirst[s];  // the segment's root inner node
+}
+
+__device__ __forceinline__ float half_area(const float* __restrict__ b) {
+  const float dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
+  return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void k_pack_wide(const int32_t* __restrict__ frontier, unsigned int n_front, int32_t* __restrict__ next,
+                            unsigned int* __restrict__ next_count, const uint32_t* __restrict__ order,
+                            const float* __restrict__ prim_box, const int32_t* __restrict__ left,
+                            const int32_t* __restrict__ right, const float* __restrict__ bounds,
+                            const uint32_t* __restrict__ seg_sfirst, int n_segs, const float* __restrict__ seg_box,
+                            int32_t ref_offset, float4* __restrict__ nodes) {
+  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_front) return;
+  const int32_t g = frontier[i];
+  int32_t kids[4] = {left[g], right[g], 0, 0};
+  int cnt = 2;
+  while (cnt < 4) {
+    int best = -1;
+    float best_area = -1.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < cnt && kids[k] >= 0) {
+        const float a = half_area(bounds + 6 * (uint64_t)kids[k]);
+        if (a > best_area) { best_area = a; best = k; }  // ties: the earlier child
+      }
+    }
+    if (best < 0) break;
+    const int32_t c = kids[best];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k == best) kids[k] = left[c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k == cnt) kids[k] = right[c];
+    cnt++;
+  }
+  const int s = seg_search(seg_sfirst, n_segs, (uint32_t)g);
+  float sb[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) sb[k] = __ldg(seg_box + 6 * s + k);
+  const float d = box_delta(sb);
   float lo[3][4], hi[3][4];
   int32_t ref[4];
-  int cnt = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     ref[k] = 0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) { lo[a][k] = __int_as_float(0x7fc00000); hi[a][k] = __int_as_float(0x7fc00000); }
-  }
-  bool wide = flags[g] == 2u;  // a built inner node ...
-  if (wide) {                  // ... at even depth
-    unsigned depth = 0;
-    for (int32_t q = parent[g]; q >= 0; q = parent[q]) depth++;
-    wide = (depth & 1u) == 0u;
-  }
-  if (wide) {
-    const int s = seg_search(seg_sfirst, n_segs, (uint32_t)g);
-    float sb[6];
+    if (k < cnt) {
+      float bx[6];
+      load_ref_box(kids[k], order, prim_box, bounds, bx);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) sb[k] = __ldg(seg_box + 6 * s + k);
-    const float d = box_delta(sb);
-    int32_t kids[4];
-    const int32_t c2[2] = {left[g], right[g]};
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (c2[j] < 0) kids[cnt++] = c2[j];
-      else { kids[cnt++] = left[c2[j]]; kids[cnt++] = right[c2[j]]; }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (k < cnt) {
-        float bx[6];
-        load_ref_box(kids[k], order, prim_box, bounds, bx);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { lo[a][k] = bx[a] - d; hi[a][k] = bx[3 + a] + d; }
-        ref[k] = kids[k] >= 0 ? kids[k] + ref_offset : kids[k] - 1;
-      }
+      for (int a = 0; a < 3; ++a) { lo[a][k] = bx[a] - d; hi[a][k] = bx[3 + a] + d; }
+      ref[k] = kids[k] >= 0 ? kids[k] + ref_offset : kids[k] - 1;
+      if (kids[k] >= 0) next[atomicAdd(next_count, 1u)] = kids[k];
     }
   }
-  float4* o = nodes + 8 * g;
+  float4* o = nodes + RR_NODE_QUADS * (uint64_t)g;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     o[a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
@@ -538,7 +557,8 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
   uint32_t *vals_a = nullptr, *vals_b = nullptr, *seg_id = nullptr, *hist = nullptr;
   int* seg_box_ord = nullptr;
   int32_t* leaf_parent = nullptr;
-  unsigned int *flags = nullptr, *d_depth = nullptr;
+  unsigned int *flags = nullptr, *d_depth = nullptr, *front_count = nullptr;
+  int32_t *front_a = nullptr, *front_b = nullptr;
   const uint32_t n_tiles = (uint32_t)((n_total + SORT_TILE - 1) / SORT_TILE);
 #define RR_TRY(x)                   \
   do {                              \
@@ -614,15 +634,38 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
                                                out.parent, leaf_parent);
     k_refit<<<grid_for(n, 128), 128, 0, st>>>(n, out.order, d_prim_box, out.left, out.right, out.parent, leaf_parent,
                                               out.bounds, flags, d_depth);
-    k_pack_nodes<<<grid_for(n, 128), 128, 0, st>>>(n, out.order, d_prim_box, out.left, out.right, out.parent, out.bounds,
-                                                   flags, out.seg_sfirst, (int)n_segs, out.seg_box, ref_offset, out.nodes);
     RR_TRY(cudaGetLastError());
+    // 4-wide collapse, one launch per level of the wide hierarchy (the frontier size comes back to the host)
+    RR_TRY(dalloc(&front_a, n));
+    RR_TRY(dalloc(&front_b, n));
+    RR_TRY(dalloc(&front_count, 2));
+    RR_TRY(cudaMemsetAsync(out.nodes, 0, n * RR_NODE_QUADS * sizeof(float4), st));
+    RR_TRY(cudaMemsetAsync(front_count, 0, 8, st));
+    k_wide_roots<<<grid_for(n_segs, 128), 128, 0, st>>>(out.seg_sfirst, out.seg_count, (int)n_segs, front_a, front_count);
+    unsigned int h_count = 0;
+    RR_TRY(cudaMemcpyAsync(&h_count, front_count, 4, cudaMemcpyDeviceToHost, st));
+    RR_TRY(cudaStreamSynchronize(st));
+    int32_t *fin = front_a, *fout = front_b;
+    int level = 0;
+    while (h_count) {
+      unsigned int* cnt_out = front_count + ((level + 1) & 1);
+      RR_TRY(cudaMemsetAsync(cnt_out, 0, 4, st));
+      k_pack_wide<<<grid_for(h_count, 128), 128, 0, st>>>(fin, h_count, fout, cnt_out, out.order, d_prim_box, out.left, out.right,
+                                                          out.bounds, out.seg_sfirst, (int)n_segs, out.seg_box, ref_offset,
+                                                          out.nodes);
+      RR_TRY(cudaMemcpyAsync(&h_count, cnt_out, 4, cudaMemcpyDeviceToHost, st));
+      RR_TRY(cudaStreamSynchronize(st));
+      int32_t* t = fin; fin = fout; fout = t;
+      level++;
+    }
+    out.wide_levels = (uint32_t)level;
   }
   RR_TRY(cudaMemcpyAsync(&out.max_depth, d_depth, 4, cudaMemcpyDeviceToHost, st));
   RR_TRY(cudaStreamSynchronize(st));
 done:
   cudaFree(keys_a); cudaFree(keys_b); cudaFree(vals_a); cudaFree(vals_b); cudaFree(seg_id); cudaFree(hist);
   cudaFree(seg_box_ord); cudaFree(leaf_parent); cudaFree(flags); cudaFree(d_depth);
+  cudaFree(front_a); cudaFree(front_b); cudaFree(front_count);
   free(h_sfirst);
 #undef RR_TRY
   return err;

@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   const unsigned lanes_below = (1u << lane) - 1u;
   uint32_t* const pool = pool_all + warp * (NW * POOL + 32);
   uint32_t* const sel = pool + NW * POOL;  // slot picked for each lane in the current phase
-  uint2* const stack = p.stack + (size_t)(blockIdx.x * WARPS + warp) * (RR_STACK * POOL);  // [depth][slot]
+  uint2* const stack = p.stack + (size_t)(blockIdx.x * WARPS + warp) * ((size_t)p.stack_entries * POOL);  // [depth][slot]
   uint32_t* const cold = p.cold + (size_t)(blockIdx.x * WARPS + warp) * (NC * POOL);
 #define CW(w, s) cold[(w) * POOL + (s)]
 #define CF(w, s) __uint_as_float(cold[(w) * POOL + (s)])
@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             }
             // misses sort last, so the children to push are a suffix of the hits: farthest first, the nearest of
             // them ends up as the (register-resident) top; the previous top is spilled once
-            if (hits >= 2 && sp + hits - 1 <= RR_STACK) {
+            if (hits >= 2 && sp + hits - 1 <= (int)p.stack_entries) {
               if (sp > 0) stk[(sp - 1) * POOL] = top;
               if (hits == 4) { stk[sp * POOL] = make_uint2((uint32_t)r3, k3 & ~3u); sp++; }
               if (hits >= 3) { stk[sp * POOL] = make_uint2((uint32_t)r2, k2 & ~3u); sp++; }
@@ -1030,9 +1030,9 @@ cudaError_t launch_primary(const RenderParams& p, int sm_count, cudaStream_t s) 
   return launch_persistent(k_render<false, true>, p, sm_count, s);
 }
 
-size_t render_stack_bytes_per_warp() { return (size_t)RR_STACK * POOL * sizeof(uint2); }
+size_t render_stack_bytes_per_warp(uint32_t stack_entries) { return (size_t)stack_entries * POOL * sizeof(uint2); }
 size_t render_cold_bytes_per_warp() { return (size_t)NC * POOL * sizeof(uint32_t); }
-int render_max_warps_per_sm() { return 64; }
+int render_max_warps_per_sm() { return (RR_MIN_CTAS + 1) * WARPS; }  // the launch clamps its grid to this
 
 // ---- probes for the bit-level parity tests (tests/test_math_parity.py) ---------
 __global__ void k_math_probe(int fn, const float* x, const float* y, float* out, uint64_t n) {
