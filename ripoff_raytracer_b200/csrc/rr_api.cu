@@ -239,8 +239,14 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   if (d.tb.n) RR_CUDA(cudaMemcpyAsync(d.nodes, d.tb.nodes, d.tb.n * node_bytes, cudaMemcpyDeviceToDevice, st));
   if (d.sb.n) RR_CUDA(cudaMemcpyAsync(d.nodes + RR_NODE_QUADS * d.tb.n, d.sb.nodes, d.sb.n * node_bytes, cudaMemcpyDeviceToDevice, st));
   // mesh + material tables
-  rr_mesh* d_meshes_in = nullptr;
-  uint32_t *d_mesh_seg = nullptr, *d_mesh_pos = nullptr;
+  // temporaries of this upload: freed on every exit path
+  struct Temp {
+    rr_mesh* meshes_in = nullptr;
+    uint32_t *mesh_seg = nullptr, *mesh_pos = nullptr;
+    ~Temp() { cudaFree(meshes_in); cudaFree(mesh_seg); cudaFree(mesh_pos); }
+  } tmp;
+  rr_mesh*& d_meshes_in = tmp.meshes_in;
+  uint32_t *&d_mesh_seg = tmp.mesh_seg, *&d_mesh_pos = tmp.mesh_pos;
   // visiting order of the meshes: most primitives first (a hit there prunes the small ones by their world box);
   // equal world distances are resolved by the original index in the kernel, so the order does not change results
   std::vector<uint32_t> mesh_pos(n_meshes + 1, 0);
@@ -271,9 +277,6 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   RR_CUDA(cudaEventRecord(d.ev1, st));
   RR_CUDA(cudaStreamSynchronize(st));
   RR_CUDA(cudaEventElapsedTime(&d.build_ms, d.ev0, d.ev1));
-  cudaFree(d_meshes_in);
-  cudaFree(d_mesh_seg);
-  cudaFree(d_mesh_pos);
   cudaFree(d.tb.nodes); d.tb.nodes = nullptr;  // copied into d.nodes
   cudaFree(d.sb.nodes); d.sb.nodes = nullptr;
   static_assert(3 * RR_MAX_DEPTH + 4 <= RR_STACK_MAX, "stack pointer must fit the slot word");
