@@ -411,3 +411,22 @@ def test_command_line_driver_writes_the_same_bmp(knight_obj, tmp_path):
     r.close()
     rr.write_bmp(tmp_path / "want.bmp", img)
     assert (tmp_path / "output.bmp").read_bytes() == (tmp_path / "want.bmp").read_bytes()
+
+
+def test_bit_exact_radiance_on_a_terrain_and_blob_scene_with_millions_of_segments():
+    """The order-independence argument (delta-inflated boxes) at scale: a reduced C4 scene
+    (terrain + displaced blobs as one mesh + spheres, ~50 k triangles), 4-wide speculative walk on the GPU against
+    the oracle's strictly ordered binary walk -- several million path segments, every float of the radiance equal."""
+    from ripoff_raytracer_b200 import workloads
+
+    wl = workloads.c4_mixed1m(width=320, height=180, spp=24, bounces=50, terrain=120, blobs=6, blob_subdiv=4, n_spheres=64)
+    t, m, r, sp = wl.scene.arrays()
+    assert 40_000 < len(t) < 80_000
+    ren = rr.Renderer()
+    ren.upload(wl.scene)
+    got, grad, st = ren.render(wl.cam, wl.width, wl.height, wl.spp, wl.bounces, radiance=True)
+    ren.close()
+    want, wrad, ost = Oracle(t, m, r, sp).render(wl.cam, wl.width, wl.height, wl.spp, wl.bounces, radiance=True, threads=16)
+    assert st["rays"] == ost["rays"] and st["rays"] > 5_000_000
+    assert np.array_equal(bits(grad), bits(wrad))
+    assert_images_equal(got, want, "reduced C4")
