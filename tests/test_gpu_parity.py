@@ -430,3 +430,49 @@ def test_bit_exact_radiance_on_a_terrain_and_blob_scene_with_millions_of_segment
     assert st["rays"] == ost["rays"] and st["rays"] > 5_000_000
     assert np.array_equal(bits(grad), bits(wrad))
     assert_images_equal(got, want, "reduced C4")
+
+
+def test_more_than_32_meshes_candidate_chunks():
+    """The kernel keeps the candidate meshes of a ray in 32-bit masks, one chunk of 32 meshes at a time
+    (reference: a plain loop over meshCount, src/Trace.cl:444): 75 instances (rotated, scaled, shared triangle
+    ranges) + walls must render exactly like the oracle's in-order loop."""
+    rng = np.random.default_rng(7)
+    s = rr.Scene()
+    v, n, f = scenes.uv_sphere(12, 6, radius=20.0, center=(0.0, 0.0, 0.0))
+    ball = s.add_triangles(scenes.mesh_triangles(v, n, f))
+    s.add_quad((-400, 0, -400), (400, 0, -400), (400, 0, 400), (-400, 0, 400), (0, 1, 0), (0.7, 0.7, 0.7))
+    s.add_quad((-150, 320, -150), (150, 320, -150), (150, 320, 150), (-150, 320, 150), (0, -1, 0), (1, 1, 1))
+    lm = s.mesh(s.n_meshes - 1)["material"]
+    lm["emissionColor"][0, :3] = 1.0
+    lm["emissionStrength"] = 5.0
+    for k in range(75):
+        m = np.zeros(1, _abi.MESH)
+        m["pos"][0, :3] = rng.uniform((-300, 20, -300), (300, 250, 300))
+        m["pitch"], m["yaw"], m["roll"] = rng.uniform(-3, 3, 3)
+        m["scale"] = [0.5, 1.0, 1.7, 2.0][k % 4]
+        mm = m["material"]
+        mm["type"] = [_abi.MATERIAL_SOLID, _abi.MATERIAL_SOLID, _abi.MATERIAL_GLASSY, _abi.MATERIAL_ONESIDED][k % 4]
+        mm["ior"] = 1.4
+        mm["color"][0, :3] = rng.uniform(0.3, 0.9, 3)
+        mm["specularProbability"] = 0.3
+        mm["reflectiveness"] = 0.5
+        s.add_mesh(m, ball)
+    assert s.n_meshes == 77
+    t, m, r, sp = s.arrays()
+    W, H = 200, 120
+    cam = np.zeros(1, _abi.CAMERA)
+    cam["position"][0, :3] = (0.0, 160.0, 520.0)
+    cam["pitch"], cam["yaw"], cam["fov"], cam["aspectRatio"] = 0.1, 3.14159, 75.0, np.float32(W) / np.float32(H)
+    ren = rr.Renderer()
+    ren.upload(s)
+    o = Oracle(t, m, r, sp)
+    mesh, prim, dst = ren.primary_hits(cam, W, H)
+    om, op, od = o.primary(cam, W, H)
+    assert np.array_equal(mesh, om) and np.array_equal(prim, op) and np.array_equal(bits(dst), bits(od))
+    assert len(np.unique(mesh)) > 30
+    got, grad, st = ren.render(cam, W, H, 6, 16, radiance=True)
+    want, wrad, ost = o.render(cam, W, H, 6, 16, radiance=True, threads=16)
+    ren.close()
+    assert st["rays"] == ost["rays"]
+    assert np.array_equal(bits(grad), bits(wrad))
+    assert_images_equal(got, want, "77 meshes")
