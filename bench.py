@@ -324,20 +324,24 @@ def main():
         d2h = W * H * 4
         e2e_steps = max(1, min(args.steps, 2))
         e_rays = 0.0
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            r.upload_arrays(host["tris"], host["meshes"], host["ranges"], host["spheres"])  # H2D + LBVH build
-            if mode == "local":
-                _, _, st = r.render(wl.cam, W, H, spp, bounces, out=frame_host)              # render + D2H
-            else:
-                st = device_step_e2e(r, rr, wl, mode, rank, world, barrier, frame_host)
-            e_rays += st["rays"] + st["rays_reused"]
-        barrier()
-        e_dt = total(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+        e_kernel_ms = 0.0
+        with ClockSampler(local) as e_clocks:
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                r.upload_arrays(host["tris"], host["meshes"], host["ranges"], host["spheres"])  # H2D + LBVH build
+                if mode == "local":
+                    _, _, st = r.render(wl.cam, W, H, spp, bounces, out=frame_host)              # render + D2H
+                else:
+                    st = device_step_e2e(r, rr, wl, mode, rank, world, barrier, frame_host)
+                e_rays += st["rays"] + st["rays_reused"]
+                e_kernel_ms += st["render_ms"]
+            barrier()
+            e_dt = total(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
         e_rays = total(e_rays)
         e2e = {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e_dt / e2e_steps * 1e3, "steps": e2e_steps,
+               "ms_per_step": e_dt / e2e_steps * 1e3, "steps": e2e_steps, "kernel_ms_per_step": e_kernel_ms / e2e_steps,
+               "clocks": e_clocks.summary(),
                "includes": "rr_upload_scene (H2D from pinned memory + LBVH build) + rr_render (kernel + frame D2H)"}
 
     if rank != 0:

@@ -9,7 +9,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "rr_internal.h"
@@ -32,6 +34,72 @@ static int cuda_fail(cudaError_t e, const char* where) {
     cudaError_t e_ = (x);                          \
     if (e_ != cudaSuccess) return cuda_fail(e_, #x); \
   } while (0)
+
+// ---- scene memory cache (see rr_internal.h) ---------------------------------------
+namespace {
+struct CacheBlock { void* p; size_t bytes; int ordinal; };
+std::mutex g_cache_mu;
+std::vector<CacheBlock> g_parked;                           // free blocks kept for reuse
+std::unordered_map<void*, std::pair<size_t, int>> g_live;   // blocks handed out: size, device
+}  // namespace
+
+cudaError_t dev_malloc_bytes(void** p, size_t bytes) {
+  *p = nullptr;
+  bytes = (std::max<size_t>(bytes, 1) + 511) & ~size_t(511);
+  int ordinal = 0;
+  cudaError_t e = cudaGetDevice(&ordinal);
+  if (e != cudaSuccess) return e;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_parked.size(); ++i) {  // smallest parked block that fits without wasting more than half
+      const CacheBlock& b = g_parked[i];
+      if (b.ordinal != ordinal || b.bytes < bytes || b.bytes > 2 * bytes) continue;
+      if (best < 0 || b.bytes < g_parked[best].bytes) best = i;
+    }
+    if (best >= 0) {
+      *p = g_parked[best].p;
+      g_live[*p] = {g_parked[best].bytes, ordinal};
+      g_parked.erase(g_parked.begin() + best);
+      return cudaSuccess;
+    }
+  }
+  e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation) {  // give the parked blocks back and try once more
+    cudaGetLastError();
+    dev_trim(ordinal);
+    e = cudaMalloc(p, bytes);
+  }
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  g_live[*p] = {bytes, ordinal};
+  return cudaSuccess;
+}
+
+void dev_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  auto it = g_live.find(p);
+  if (it == g_live.end()) { cudaFree(p); return; }  // not ours
+  g_parked.push_back({p, it->second.first, it->second.second});
+  g_live.erase(it);
+}
+
+void dev_trim(int ordinal) {
+  std::vector<void*> drop;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    for (size_t i = 0; i < g_parked.size();) {
+      if (g_parked[i].ordinal == ordinal) { drop.push_back(g_parked[i].p); g_parked.erase(g_parked.begin() + i); }
+      else ++i;
+    }
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(ordinal);
+  for (void* q : drop) cudaFree(q);
+  cudaSetDevice(prev);
+}
 
 struct Device {
   int ordinal = -1;
@@ -174,9 +242,9 @@ __global__ void k_prepare_meshes(const rr_mesh* __restrict__ meshes, const uint3
 
 static void free_scene(Device& d) {
   cudaSetDevice(d.ordinal);
-  cudaFree(d.tris); cudaFree(d.spheres); cudaFree(d.tri_box); cudaFree(d.sph_box);
-  cudaFree(d.tri_geom); cudaFree(d.tri_nrm); cudaFree(d.sph_geom); cudaFree(d.meshes); cudaFree(d.materials);
-  cudaFree(d.nodes);
+  dev_free(d.tris); dev_free(d.spheres); dev_free(d.tri_box); dev_free(d.sph_box);
+  dev_free(d.tri_geom); dev_free(d.tri_nrm); dev_free(d.sph_geom); dev_free(d.meshes); dev_free(d.materials);
+  dev_free(d.nodes);
   d.tris = nullptr; d.spheres = nullptr; d.tri_box = nullptr; d.sph_box = nullptr;
   d.tri_geom = d.tri_nrm = d.sph_geom = nullptr; d.meshes = nullptr; d.materials = nullptr; d.nodes = nullptr;
   lbvh_free(d.tb);
@@ -216,26 +284,26 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   RR_CUDA(cudaSetDevice(d.ordinal));
   free_scene(d);
   cudaStream_t st = d.stream;
-  RR_CUDA(cudaMalloc(&d.tris, std::max<size_t>(n_tris, 1) * sizeof(rr_triangle)));
-  RR_CUDA(cudaMalloc(&d.tri_box, std::max<size_t>(n_tris, 1) * 24));
-  RR_CUDA(cudaMalloc(&d.spheres, std::max<size_t>(n_spheres, 1) * sizeof(rr_sphere)));
-  RR_CUDA(cudaMalloc(&d.sph_box, std::max<size_t>(n_spheres, 1) * 24));
+  RR_CUDA(dev_malloc(&d.tris, std::max<size_t>(n_tris, 1) * sizeof(rr_triangle)));
+  RR_CUDA(dev_malloc(&d.tri_box, std::max<size_t>(n_tris, 1) * 24));
+  RR_CUDA(dev_malloc(&d.spheres, std::max<size_t>(n_spheres, 1) * sizeof(rr_sphere)));
+  RR_CUDA(dev_malloc(&d.sph_box, std::max<size_t>(n_spheres, 1) * 24));
   if (n_tris) RR_CUDA(cudaMemcpyAsync(d.tris, tris, n_tris * sizeof(rr_triangle), cudaMemcpyHostToDevice, st));
   if (n_spheres) RR_CUDA(cudaMemcpyAsync(d.spheres, spheres, n_spheres * sizeof(rr_sphere), cudaMemcpyHostToDevice, st));
   RR_CUDA(cudaEventRecord(d.ev0, st));
   RR_CUDA(launch_tri_boxes(d.tris, n_tris, d.tri_box, st));
   RR_CUDA(lbvh_build(d.tb, d.tri_box, n_tris, plan.first.data(), plan.count.data(), (uint32_t)plan.first.size(), 0, st));
-  RR_CUDA(cudaMalloc(&d.tri_geom, std::max<uint64_t>(d.tb.n, 1) * 48));
-  RR_CUDA(cudaMalloc(&d.tri_nrm, std::max<uint64_t>(d.tb.n, 1) * 48));
+  RR_CUDA(dev_malloc(&d.tri_geom, std::max<uint64_t>(d.tb.n, 1) * 48));
+  RR_CUDA(dev_malloc(&d.tri_nrm, std::max<uint64_t>(d.tb.n, 1) * 48));
   RR_CUDA(launch_pack_tris(d.tris, d.tb.order, d.tb.n, d.tri_geom, d.tri_nrm, st));
   RR_CUDA(launch_sphere_boxes(d.spheres, n_spheres, d.sph_box, st));
   uint32_t sf = 0, sc = (uint32_t)n_spheres;
   RR_CUDA(lbvh_build(d.sb, d.sph_box, n_spheres, &sf, &sc, n_spheres ? 1u : 0u, (int32_t)d.tb.n, st));
-  RR_CUDA(cudaMalloc(&d.sph_geom, std::max<size_t>(n_spheres, 1) * 16));
+  RR_CUDA(dev_malloc(&d.sph_geom, std::max<size_t>(n_spheres, 1) * 16));
   RR_CUDA(launch_pack_spheres(d.spheres, d.sb.order, d.sb.n, d.sph_geom, st));
   // one node array: triangle hierarchies at [0, tb.n), the sphere hierarchy behind them
   const size_t node_bytes = RR_NODE_QUADS * sizeof(float4);
-  RR_CUDA(cudaMalloc(&d.nodes, std::max<uint64_t>(d.tb.n + d.sb.n, 1) * node_bytes));
+  RR_CUDA(dev_malloc(&d.nodes, std::max<uint64_t>(d.tb.n + d.sb.n, 1) * node_bytes));
   if (d.tb.n) RR_CUDA(cudaMemcpyAsync(d.nodes, d.tb.nodes, d.tb.n * node_bytes, cudaMemcpyDeviceToDevice, st));
   if (d.sb.n) RR_CUDA(cudaMemcpyAsync(d.nodes + RR_NODE_QUADS * d.tb.n, d.sb.nodes, d.sb.n * node_bytes, cudaMemcpyDeviceToDevice, st));
   // mesh + material tables
@@ -243,7 +311,7 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   struct Temp {
     rr_mesh* meshes_in = nullptr;
     uint32_t *mesh_seg = nullptr, *mesh_pos = nullptr;
-    ~Temp() { cudaFree(meshes_in); cudaFree(mesh_seg); cudaFree(mesh_pos); }
+    ~Temp() { dev_free(meshes_in); dev_free(mesh_seg); dev_free(mesh_pos); }
   } tmp;
   rr_mesh*& d_meshes_in = tmp.meshes_in;
   uint32_t *&d_mesh_seg = tmp.mesh_seg, *&d_mesh_pos = tmp.mesh_pos;
@@ -257,12 +325,12 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
     std::stable_sort(byCount.begin(), byCount.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
     for (size_t k = 0; k < byCount.size(); ++k) mesh_pos[byCount[k].second] = (uint32_t)k;
   }
-  RR_CUDA(cudaMalloc(&d_mesh_pos, (n_meshes + 1) * 4));
+  RR_CUDA(dev_malloc(&d_mesh_pos, (n_meshes + 1) * 4));
   RR_CUDA(cudaMemcpyAsync(d_mesh_pos, mesh_pos.data(), (n_meshes + 1) * 4, cudaMemcpyHostToDevice, st));
-  RR_CUDA(cudaMalloc(&d_meshes_in, std::max<size_t>(n_meshes, 1) * sizeof(rr_mesh)));
-  RR_CUDA(cudaMalloc(&d_mesh_seg, std::max<size_t>(n_meshes, 1) * 4));
-  RR_CUDA(cudaMalloc(&d.meshes, (n_meshes + 1) * sizeof(DMesh)));
-  RR_CUDA(cudaMalloc(&d.materials, std::max<size_t>(n_meshes + n_spheres, 1) * sizeof(DMaterial)));
+  RR_CUDA(dev_malloc(&d_meshes_in, std::max<size_t>(n_meshes, 1) * sizeof(rr_mesh)));
+  RR_CUDA(dev_malloc(&d_mesh_seg, std::max<size_t>(n_meshes, 1) * 4));
+  RR_CUDA(dev_malloc(&d.meshes, (n_meshes + 1) * sizeof(DMesh)));
+  RR_CUDA(dev_malloc(&d.materials, std::max<size_t>(n_meshes + n_spheres, 1) * sizeof(DMaterial)));
   if (n_meshes) {
     RR_CUDA(cudaMemcpyAsync(d_meshes_in, meshes, n_meshes * sizeof(rr_mesh), cudaMemcpyHostToDevice, st));
     RR_CUDA(cudaMemcpyAsync(d_mesh_seg, plan.mesh_seg.data(), n_meshes * 4, cudaMemcpyHostToDevice, st));
@@ -277,8 +345,8 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   RR_CUDA(cudaEventRecord(d.ev1, st));
   RR_CUDA(cudaStreamSynchronize(st));
   RR_CUDA(cudaEventElapsedTime(&d.build_ms, d.ev0, d.ev1));
-  cudaFree(d.tb.nodes); d.tb.nodes = nullptr;  // copied into d.nodes
-  cudaFree(d.sb.nodes); d.sb.nodes = nullptr;
+  dev_free(d.tb.nodes); d.tb.nodes = nullptr;  // copied into d.nodes
+  dev_free(d.sb.nodes); d.sb.nodes = nullptr;
   static_assert(3 * RR_MAX_DEPTH + 4 <= RR_STACK_MAX, "stack pointer must fit the slot word");
   {  // traversal stacks sized for THIS scene: a wide node pushes at most 3 children per level
     const uint32_t need = 3u * std::max(d.tb.wide_levels, d.sb.wide_levels) + 4u;
@@ -536,6 +604,7 @@ void rr_destroy(rr_ctx* ctx) {
       if (d.shared_frame) cudaIpcCloseMemHandle(d.shared_frame);
     }
     cudaFree(d.frame); cudaFree(d.radiance); cudaFree(d.queue); cudaFree(d.counters); cudaFree(d.stack); cudaFree(d.cold);
+    dev_trim(d.ordinal);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
     if (d.stream) cudaStreamDestroy(d.stream);

@@ -131,6 +131,16 @@ struct RenderParams {
   float* hit_dst;
 };
 
+// ---- device memory for scene data (rr_api.cu) -------------------------------
+// cudaMalloc / cudaFree of the large scene arrays cost hundreds of milliseconds per upload (the driver maps and
+// unmaps the memory each time).  Scene-sized blocks therefore go through a small per-device cache: dev_free() parks
+// a block, dev_malloc() reuses a parked block of a fitting size, dev_trim() gives parked blocks back to the driver.
+cudaError_t dev_malloc_bytes(void** p, size_t bytes);
+void dev_free(void* p);
+void dev_trim(int ordinal);
+template <class T>
+inline cudaError_t dev_malloc(T** p, size_t bytes) { return dev_malloc_bytes(reinterpret_cast<void**>(p), bytes); }
+
 // ---- builder (rr_lbvh.cu) -------------------------------------------------
 // boxes: prim boxes [n_total*6] on the device, segments on the HOST (first,count per segment,
 // sorted by first, non-overlapping).  Builds everything in `out` on `stream`.

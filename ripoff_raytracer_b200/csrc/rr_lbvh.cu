@@ -531,14 +531,14 @@ __global__ void k_fill_i32(int32_t* p, uint64_t n, int32_t v) {
 
 // ---- host driver ----------------------------------------------------------------
 void lbvh_free(Lbvh& b) {
-  cudaFree(b.codes); cudaFree(b.order); cudaFree(b.left); cudaFree(b.right); cudaFree(b.parent); cudaFree(b.bounds);
-  cudaFree(b.seg_box); cudaFree(b.seg_first); cudaFree(b.seg_count); cudaFree(b.seg_sfirst); cudaFree(b.nodes);
+  dev_free(b.codes); dev_free(b.order); dev_free(b.left); dev_free(b.right); dev_free(b.parent); dev_free(b.bounds);
+  dev_free(b.seg_box); dev_free(b.seg_first); dev_free(b.seg_count); dev_free(b.seg_sfirst); dev_free(b.nodes);
   b = Lbvh();
 }
 
 template <class T>
 static cudaError_t dalloc(T** p, uint64_t count) {
-  return cudaMalloc(reinterpret_cast<void**>(p), (count ? count : 1) * sizeof(T));
+  return dev_malloc(p, (count ? count : 1) * sizeof(T));  // cached: a re-upload of a scene of the same size allocates nothing
 }
 
 cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, const uint32_t* h_seg_first,
@@ -663,9 +663,9 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
   RR_TRY(cudaMemcpyAsync(&out.max_depth, d_depth, 4, cudaMemcpyDeviceToHost, st));
   RR_TRY(cudaStreamSynchronize(st));
 done:
-  cudaFree(keys_a); cudaFree(keys_b); cudaFree(vals_a); cudaFree(vals_b); cudaFree(seg_id); cudaFree(hist);
-  cudaFree(seg_box_ord); cudaFree(leaf_parent); cudaFree(flags); cudaFree(d_depth);
-  cudaFree(front_a); cudaFree(front_b); cudaFree(front_count);
+  dev_free(keys_a); dev_free(keys_b); dev_free(vals_a); dev_free(vals_b); dev_free(seg_id); dev_free(hist);
+  dev_free(seg_box_ord); dev_free(leaf_parent); dev_free(flags); dev_free(d_depth);
+  dev_free(front_a); dev_free(front_b); dev_free(front_count);
   free(h_sfirst);
 #undef RR_TRY
   return err;
