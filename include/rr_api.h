@@ -162,6 +162,29 @@ int rr_upload_scene(rr_ctx* ctx, const rr_triangle* tris, size_t n_tris, const r
 int rr_upload_scene_ref(rr_ctx* ctx, const rr_triangle* tris, size_t n_tris, const rr_mesh* meshes, size_t n_meshes,
                         const rr_ref_node* nodes, size_t n_nodes);
 
+/* Indexed upload (the step before the path).  The raw OBJ arrays go to the device and the
+ * Triangle array of src/readobj.hpp:69-73 is assembled THERE (one gather kernel), instead of being expanded to
+ * 96 bytes per triangle on the host (src/readobj.hpp:313-343) and copied.  positions / normals: x,y,z triples;
+ * corners: six 0-based indices per triangle, v0 v1 v2 n0 n1 n2.  Everything after the gather (LBVH build, render)
+ * is the same as for rr_upload_scene, and so is the image. */
+int rr_upload_scene_indexed(rr_ctx* ctx, const float* positions, size_t n_positions, const float* normals,
+                            size_t n_normals, const uint32_t* corners, size_t n_tris, const rr_mesh* meshes,
+                            const rr_mesh_range* ranges, size_t n_meshes, const rr_sphere* spheres, size_t n_spheres);
+
+/* OBJ text -> indexed arrays, with the limits of the reference loader lifted (src/readobj.hpp:289-344 accepts only
+ * `f a/b/c` or `f a//c` triangles with normals and silently drops a 4th corner): polygons are fan-triangulated,
+ * `f a`, `f a/b` (no normals) get one face normal per triangle, negative indices count from the end.  On the
+ * dialect the reference accepts, the triangles are the ones rr_scene_load_obj / the reference produce. */
+typedef struct rr_obj rr_obj;
+int rr_obj_load(const char* path, rr_obj** out);
+void rr_obj_destroy(rr_obj* o);
+size_t rr_obj_position_count(const rr_obj* o);
+size_t rr_obj_normal_count(const rr_obj* o);
+size_t rr_obj_triangle_count(const rr_obj* o);
+const float* rr_obj_positions(const rr_obj* o);
+const float* rr_obj_normals(const rr_obj* o);
+const uint32_t* rr_obj_corners(const rr_obj* o);
+
 /* Counters of one render (exact, from device atomics). */
 typedef struct rr_stats {
   uint64_t samples;      /* Trace() calls = W*H*spp                         */

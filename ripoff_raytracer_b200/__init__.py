@@ -6,6 +6,8 @@ reference's host-driver boundary (reference src/image.hpp).  This package is
 the thin Python mirror of that boundary used by the tests and bench.py.
 """
 from . import _abi, scenes  # noqa: F401
-from .api import Renderer, Scene, default_camera, default_scene, write_bmp  # noqa: F401
+from .api import (Renderer, Scene, default_camera, default_scene, load_obj_indexed, triangles_from_indexed,  # noqa: F401
+                  write_bmp)
 
-__all__ = ["Renderer", "Scene", "default_camera", "default_scene", "write_bmp", "scenes"]
+__all__ = ["Renderer", "Scene", "default_camera", "default_scene", "load_obj_indexed", "triangles_from_indexed",
+           "write_bmp", "scenes"]

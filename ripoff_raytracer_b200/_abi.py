@@ -112,6 +112,15 @@ SYMBOLS = {
     "rr_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "rr_device_info": (C.c_int, [C.c_int, C.c_char_p, _sz, C.POINTER(C.c_int), C.POINTER(_u64)]),
     "rr_upload_scene": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _sz]),
+    "rr_upload_scene_indexed": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _sz, _vp, _sz]),
+    "rr_obj_load": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "rr_obj_destroy": (None, [_vp]),
+    "rr_obj_position_count": (_sz, [_vp]),
+    "rr_obj_normal_count": (_sz, [_vp]),
+    "rr_obj_triangle_count": (_sz, [_vp]),
+    "rr_obj_positions": (_vp, [_vp]),
+    "rr_obj_normals": (_vp, [_vp]),
+    "rr_obj_corners": (_vp, [_vp]),
     "rr_upload_scene_ref": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, _sz]),
     "rr_render": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, _vp]),
     "rr_render_ex": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, _vp, _vp, C.POINTER(Stats), C.c_int]),

@@ -127,6 +127,37 @@ class Scene:
                 copy(l.rr_scene_spheres(self.h), self.n_spheres, SPHERE))
 
 
+def load_obj_indexed(path):
+    """rr_obj_load: OBJ text -> (positions (n,3) f32, normals (m,3) f32, corners (t,6) u32: v0 v1 v2 n0 n1 n2)."""
+    h = C.c_void_p()
+    check(lib().rr_obj_load(str(path).encode(), C.byref(h)), "rr_obj_load")
+    try:
+        l = lib()
+        npos, nnrm, ntri = l.rr_obj_position_count(h), l.rr_obj_normal_count(h), l.rr_obj_triangle_count(h)
+
+        def copy(p, n, dt):
+            if n == 0:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (n * np.dtype(dt).itemsize,)).view(dt).copy()
+
+        pos = copy(l.rr_obj_positions(h), npos * 3, np.float32).reshape(-1, 3)
+        nrm = copy(l.rr_obj_normals(h), nnrm * 3, np.float32).reshape(-1, 3)
+        cor = copy(l.rr_obj_corners(h), ntri * 6, np.uint32).reshape(-1, 6)
+        return pos, nrm, cor
+    finally:
+        lib().rr_obj_destroy(h)
+
+
+def triangles_from_indexed(positions, normals, corners) -> np.ndarray:
+    """Host-side expansion of indexed arrays to Triangle records (what the device gather produces)."""
+    t = np.zeros(len(corners), TRIANGLE)
+    for k, name in enumerate(("posA", "posB", "posC")):
+        t[name][:, :3] = positions[corners[:, k]]
+    for k, name in enumerate(("normalA", "normalB", "normalC")):
+        t[name][:, :3] = normals[corners[:, 3 + k]]
+    return t
+
+
 def default_scene(obj_path) -> Scene:
     """Scene assembly of the reference's main() (src/main.cpp:246-272, 298, 706):
     OBJ mesh (Solid white, specularProbability 1, scale 0.5), Cornell box around it,
@@ -181,6 +212,18 @@ class Renderer:
         spheres = None if ns == 0 else np.ascontiguousarray(spheres, SPHERE)
         check(lib().rr_upload_scene(self.h, ptr(tris), len(tris), ptr(meshes), ptr(ranges), len(meshes), ptr(spheres), ns),
               "rr_upload_scene")
+
+    def upload_indexed(self, positions, normals, corners, meshes, ranges, spheres=None):
+        """rr_upload_scene_indexed: raw OBJ arrays in, the Triangle records are assembled on the device."""
+        positions = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        normals = np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+        corners = np.ascontiguousarray(corners, np.uint32).reshape(-1, 6)
+        meshes = np.ascontiguousarray(meshes, MESH)
+        ranges = np.ascontiguousarray(ranges, MESH_RANGE)
+        spheres = np.zeros(0, SPHERE) if spheres is None else np.ascontiguousarray(spheres, SPHERE)
+        check(lib().rr_upload_scene_indexed(self.h, ptr(positions), len(positions), ptr(normals), len(normals), ptr(corners),
+                                            len(corners), ptr(meshes), ptr(ranges), len(meshes),
+                                            ptr(spheres) if len(spheres) else None, len(spheres)), "rr_upload_scene_indexed")
 
     def upload_ref(self, tris, meshes, ref_nodes):
         """generateBuffers' own argument list: triangleList, meshList, nodeList (host Node layout)."""

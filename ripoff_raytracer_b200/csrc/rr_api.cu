@@ -240,6 +240,34 @@ __global__ void k_prepare_meshes(const rr_mesh* __restrict__ meshes, const uint3
   mats[i] = mm;
 }
 
+// Triangle assembly on the device (replaces the host loop of src/readobj.hpp:313-343): corner indices -> the 96-byte
+// Triangle records, six coalesced 16-byte stores per triangle.  HBM-bound: 24 B of indices + 72 B of gathered vertex
+// data read, 96 B written per triangle.
+__global__ void k_gather_tris(const float* __restrict__ pos, const float* __restrict__ nrm, const uint32_t* __restrict__ corners,
+                              uint64_t n, float4* __restrict__ tris) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* c = corners + 6 * i;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float* v = pos + 3 * (uint64_t)__ldg(c + k);
+    tris[6 * i + k] = make_float4(__ldg(v), __ldg(v + 1), __ldg(v + 2), 0.0f);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float* v = nrm + 3 * (uint64_t)__ldg(c + 3 + k);
+    tris[6 * i + 3 + k] = make_float4(__ldg(v), __ldg(v + 1), __ldg(v + 2), 0.0f);
+  }
+}
+
+struct IndexedInput {  // host arrays of rr_upload_scene_indexed
+  const float* positions = nullptr;
+  size_t n_positions = 0;
+  const float* normals = nullptr;
+  size_t n_normals = 0;
+  const uint32_t* corners = nullptr;
+};
+
 static void free_scene(Device& d) {
   cudaSetDevice(d.ordinal);
   dev_free(d.tris); dev_free(d.spheres); dev_free(d.tri_box); dev_free(d.sph_box);
@@ -279,8 +307,8 @@ static int plan_segments(const rr_mesh_range* ranges, size_t n_meshes, size_t n_
   return RR_OK;
 }
 
-static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, const rr_mesh* meshes, size_t n_meshes,
-                         const SegPlan& plan, const rr_sphere* spheres, size_t n_spheres) {
+static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput* indexed, size_t n_tris, const rr_mesh* meshes,
+                         size_t n_meshes, const SegPlan& plan, const rr_sphere* spheres, size_t n_spheres) {
   RR_CUDA(cudaSetDevice(d.ordinal));
   free_scene(d);
   cudaStream_t st = d.stream;
@@ -288,7 +316,24 @@ static int upload_device(Device& d, const rr_triangle* tris, size_t n_tris, cons
   RR_CUDA(dev_malloc(&d.tri_box, std::max<size_t>(n_tris, 1) * 24));
   RR_CUDA(dev_malloc(&d.spheres, std::max<size_t>(n_spheres, 1) * sizeof(rr_sphere)));
   RR_CUDA(dev_malloc(&d.sph_box, std::max<size_t>(n_spheres, 1) * 24));
-  if (n_tris) RR_CUDA(cudaMemcpyAsync(d.tris, tris, n_tris * sizeof(rr_triangle), cudaMemcpyHostToDevice, st));
+  struct Staged {  // the raw OBJ arrays on the device, only until the triangles are assembled
+    float *pos = nullptr, *nrm = nullptr;
+    uint32_t* corners = nullptr;
+    ~Staged() { dev_free(pos); dev_free(nrm); dev_free(corners); }
+  } staged;
+  if (n_tris && !indexed) {
+    RR_CUDA(cudaMemcpyAsync(d.tris, tris, n_tris * sizeof(rr_triangle), cudaMemcpyHostToDevice, st));
+  } else if (n_tris) {
+    RR_CUDA(dev_malloc(&staged.pos, indexed->n_positions * 12));
+    RR_CUDA(dev_malloc(&staged.nrm, indexed->n_normals * 12));
+    RR_CUDA(dev_malloc(&staged.corners, n_tris * 24));
+    RR_CUDA(cudaMemcpyAsync(staged.pos, indexed->positions, indexed->n_positions * 12, cudaMemcpyHostToDevice, st));
+    RR_CUDA(cudaMemcpyAsync(staged.nrm, indexed->normals, indexed->n_normals * 12, cudaMemcpyHostToDevice, st));
+    RR_CUDA(cudaMemcpyAsync(staged.corners, indexed->corners, n_tris * 24, cudaMemcpyHostToDevice, st));
+    k_gather_tris<<<(unsigned)((n_tris + 255) / 256), 256, 0, st>>>(staged.pos, staged.nrm, staged.corners, n_tris,
+                                                                    reinterpret_cast<float4*>(d.tris));
+    RR_CUDA(cudaGetLastError());
+  }
   if (n_spheres) RR_CUDA(cudaMemcpyAsync(d.spheres, spheres, n_spheres * sizeof(rr_sphere), cudaMemcpyHostToDevice, st));
   RR_CUDA(cudaEventRecord(d.ev0, st));
   RR_CUDA(launch_tri_boxes(d.tris, n_tris, d.tri_box, st));
@@ -624,7 +669,35 @@ int rr_upload_scene(rr_ctx* ctx, const rr_triangle* tris, size_t n_tris, const r
   if (rc) return rc;
   ctx->has_scene = false;
   for (Device& d : ctx->dev) {
-    rc = upload_device(d, tris, n_tris, meshes, n_meshes, plan, spheres, n_spheres);
+    rc = upload_device(d, tris, nullptr, n_tris, meshes, n_meshes, plan, spheres, n_spheres);
+    if (rc) return rc;
+  }
+  ctx->n_tris = n_tris; ctx->n_meshes = n_meshes; ctx->n_spheres = n_spheres;
+  ctx->has_scene = true;
+  return RR_OK;
+}
+
+int rr_upload_scene_indexed(rr_ctx* ctx, const float* positions, size_t n_positions, const float* normals,
+                            size_t n_normals, const uint32_t* corners, size_t n_tris, const rr_mesh* meshes,
+                            const rr_mesh_range* ranges, size_t n_meshes, const rr_sphere* spheres, size_t n_spheres) {
+  if (!ctx) return fail(RR_ERR_INVALID_ARGUMENT, "null context");
+  if ((n_tris && (!positions || !normals || !corners)) || (n_meshes && (!meshes || !ranges)) || (n_spheres && !spheres))
+    return fail(RR_ERR_INVALID_ARGUMENT, "null array with non-zero count");
+  if (n_tris >= 0x7fffffffull || n_spheres >= 0x7fffffffull || n_positions >= 0xffffffffull || n_normals >= 0xffffffffull)
+    return fail(RR_ERR_INVALID_ARGUMENT, "too many primitives (31-bit indices)");
+  if (n_meshes >= 0xffff0ull) return fail(RR_ERR_INVALID_ARGUMENT, "too many meshes");
+  for (size_t i = 0; i < n_tris; ++i)  // the gather kernel trusts the indices
+    for (int k = 0; k < 6; ++k)
+      if (corners[6 * i + k] >= (k < 3 ? n_positions : n_normals))
+        return fail(RR_ERR_INVALID_ARGUMENT, "triangle " + std::to_string(i) + ": corner index out of range");
+  SegPlan plan;
+  int rc = plan_segments(ranges, n_meshes, n_tris, plan);
+  if (rc) return rc;
+  IndexedInput in;
+  in.positions = positions; in.n_positions = n_positions; in.normals = normals; in.n_normals = n_normals; in.corners = corners;
+  ctx->has_scene = false;
+  for (Device& d : ctx->dev) {
+    rc = upload_device(d, nullptr, &in, n_tris, meshes, n_meshes, plan, spheres, n_spheres);
     if (rc) return rc;
   }
   ctx->n_tris = n_tris; ctx->n_meshes = n_meshes; ctx->n_spheres = n_spheres;

@@ -6,6 +6,7 @@
 // Pure C++; no CUDA in this file.
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -13,6 +14,11 @@
 #include <vector>
 
 #include "../../include/rr_api.h"
+
+struct rr_obj {
+  std::vector<float> positions, normals;  // x,y,z triples
+  std::vector<uint32_t> corners;          // v0 v1 v2 n0 n1 n2 per triangle, 0-based
+};
 
 struct rr_scene {
   std::vector<rr_triangle> tris;
@@ -69,6 +75,91 @@ bool parse_corner(const char*& p, long& v, long& n) {
 }  // namespace
 
 extern "C" {
+
+// OBJ -> indexed arrays with the reference loader's limits lifted (see include/rr_api.h).
+int rr_obj_load(const char* path, rr_obj** out) {
+  if (!path || !out) return RR_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  std::ifstream file(path);
+  if (!file) return RR_ERR_IO;
+  rr_obj* o = new rr_obj();
+  std::string line;
+  std::vector<long> fv, fn;
+  std::vector<float> generated;  // face normals of faces without `vn`: appended behind the file's normals at the end,
+                                 // so that they never shift the file's own (possibly relative) normal indices
+  while (std::getline(file, line)) {
+    if (line.size() < 2) continue;
+    const char* c = line.c_str();
+    if (c[0] == 'v' && (c[1] == ' ' || c[1] == '\t')) {
+      float x, y, z;
+      if (sscanf(c + 1, "%f %f %f", &x, &y, &z) == 3) { o->positions.push_back(x); o->positions.push_back(y); o->positions.push_back(z); }
+    } else if (c[0] == 'v' && c[1] == 'n' && (c[2] == ' ' || c[2] == '\t')) {
+      float x, y, z;
+      if (sscanf(c + 2, "%f %f %f", &x, &y, &z) == 3) { o->normals.push_back(x); o->normals.push_back(y); o->normals.push_back(z); }
+    } else if (c[0] == 'f' && (c[1] == ' ' || c[1] == '\t')) {
+      fv.clear(); fn.clear();
+      const char* p = c + 1;
+      bool ok = true;
+      for (;;) {  // corners: v, v/vt, v//vn, v/vt/vn
+        while (*p == ' ' || *p == '\t' || *p == '\r') ++p;
+        if (!*p) break;
+        char* end;
+        long v = strtol(p, &end, 10), n = 0;
+        if (end == p) { ok = false; break; }
+        p = end;
+        if (*p == '/') {
+          ++p;
+          if (*p != '/') { strtol(p, &end, 10); p = end; }  // texture index, unused
+          if (*p == '/') {
+            ++p;
+            n = strtol(p, &end, 10);
+            if (end == p) { ok = false; break; }
+            p = end;
+          }
+        }
+        const long nv = (long)(o->positions.size() / 3), nn = (long)(o->normals.size() / 3);
+        v = v < 0 ? nv + v : v - 1;  // negative indices count from the end
+        n = n < 0 ? nn + n : n - 1;  // n == 0 (absent) becomes -1
+        if (v < 0 || v >= nv || n >= nn) { ok = false; break; }
+        fv.push_back(v);
+        fn.push_back(n);
+      }
+      if (!ok || fv.size() < 3) continue;
+      for (size_t k = 1; k + 1 < fv.size(); ++k) {  // fan triangulation; a triangle is a fan of one
+        const long v3[3] = {fv[0], fv[k], fv[k + 1]};
+        long n3[3] = {fn[0], fn[k], fn[k + 1]};
+        if (n3[0] < 0 || n3[1] < 0 || n3[2] < 0) {  // no normals: one face normal for the triangle
+          const float* A = &o->positions[3 * v3[0]];
+          const float* B = &o->positions[3 * v3[1]];
+          const float* C = &o->positions[3 * v3[2]];
+          const float e1[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, e2[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+          float nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
+          const float len = std::sqrt(nx * nx + ny * ny + nz * nz);
+          if (len > 0.0f) { nx /= len; ny /= len; nz /= len; } else { nx = 0.0f; ny = 1.0f; nz = 0.0f; }
+          const long idx = (long)(generated.size() / 3);
+          generated.push_back(nx); generated.push_back(ny); generated.push_back(nz);
+          n3[0] = n3[1] = n3[2] = idx | 0x40000000L;
+        }
+        for (int q = 0; q < 3; ++q) o->corners.push_back((uint32_t)v3[q]);
+        for (int q = 0; q < 3; ++q) o->corners.push_back((uint32_t)n3[q]);
+      }
+    }
+  }
+  const uint32_t n_file = (uint32_t)(o->normals.size() / 3);
+  for (size_t i = 0; i < o->corners.size(); i += 6)
+    for (int q = 3; q < 6; ++q)
+      if (o->corners[i + q] & 0x40000000u) o->corners[i + q] = n_file + (o->corners[i + q] & 0x3fffffffu);
+  o->normals.insert(o->normals.end(), generated.begin(), generated.end());
+  *out = o;
+  return RR_OK;
+}
+void rr_obj_destroy(rr_obj* o) { delete o; }
+size_t rr_obj_position_count(const rr_obj* o) { return o ? o->positions.size() / 3 : 0; }
+size_t rr_obj_normal_count(const rr_obj* o) { return o ? o->normals.size() / 3 : 0; }
+size_t rr_obj_triangle_count(const rr_obj* o) { return o ? o->corners.size() / 6 : 0; }
+const float* rr_obj_positions(const rr_obj* o) { return o ? o->positions.data() : nullptr; }
+const float* rr_obj_normals(const rr_obj* o) { return o ? o->normals.data() : nullptr; }
+const uint32_t* rr_obj_corners(const rr_obj* o) { return o ? o->corners.data() : nullptr; }
 
 int rr_scene_create(rr_scene** out) {
   if (!out) return RR_ERR_INVALID_ARGUMENT;

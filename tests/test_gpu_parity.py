@@ -476,3 +476,39 @@ def test_more_than_32_meshes_candidate_chunks():
     assert st["rays"] == ost["rays"]
     assert np.array_equal(bits(grad), bits(wrad))
     assert_images_equal(got, want, "77 meshes")
+
+
+def test_indexed_upload_assembles_the_same_triangles_on_the_device(knight_obj):
+    """rr_upload_scene_indexed (SURVEY 8f rank 1): raw v / vn / f arrays in, Triangle records gathered on the GPU;
+    image, radiance and LBVH identical to the upload of host-expanded triangles."""
+    pos, nrm, cor = rr.load_obj_indexed(knight_obj)
+    s = rr.default_scene(knight_obj)  # OBJ triangles first (range 0..n), then the 14 Cornell triangles
+    t, m, r, _ = s.arrays()
+    n_obj = len(cor)
+    assert len(t) == n_obj + 14
+    # append the Cornell quads to the indexed arrays
+    quad = t[n_obj:]
+    qpos = np.concatenate([quad["posA"][:, :3], quad["posB"][:, :3], quad["posC"][:, :3]])
+    qnrm = np.concatenate([quad["normalA"][:, :3], quad["normalB"][:, :3], quad["normalC"][:, :3]])
+    k = np.arange(14, dtype=np.uint32)
+    qcor = np.stack([len(pos) + k, len(pos) + 14 + k, len(pos) + 28 + k, len(nrm) + k, len(nrm) + 14 + k, len(nrm) + 28 + k], 1)
+    pos2, nrm2, cor2 = np.concatenate([pos, qpos]), np.concatenate([nrm, qnrm]), np.concatenate([cor, qcor.astype(np.uint32)])
+    W, H = 160, 120
+    cam = rr.default_camera(W, H)
+    a = rr.Renderer()
+    a.upload_arrays(t, m, r)
+    want, wrad, _ = a.render(cam, W, H, 4, 20, radiance=True)
+    wb = a.bvh(0)
+    a.close()
+    b = rr.Renderer()
+    b.upload_indexed(pos2, nrm2, cor2, m, r)
+    got, grad, _ = b.render(cam, W, H, 4, 20, radiance=True)
+    gb = b.bvh(0)
+    with pytest.raises(_abi.RRError):
+        bad = cor2.copy()
+        bad[3, 1] = len(pos2)
+        b.upload_indexed(pos2, nrm2, bad, m, r)
+    b.close()
+    assert np.array_equal(got, want) and np.array_equal(bits(grad), bits(wrad))
+    for key in ("codes", "order", "left", "right", "bounds"):
+        assert np.array_equal(gb[key], wb[key]), key

@@ -112,3 +112,36 @@ def test_mesh_ranges_are_validated_without_a_device():
     with pytest.raises(_abi.RRError) as e:
         s.add_mesh(np.zeros(1, _abi.MESH), bad)
     assert e.value.status == 6
+
+
+def test_indexed_obj_loader_matches_the_reference_dialect(tmp_path):
+    """rr_obj_load on the dialect the reference accepts == rr_scene_load_obj (== the reference loader, see above)."""
+    v, n, f = scenes.displaced_icosphere(2, seed=7)
+    p = tmp_path / "blob.obj"
+    scenes.write_obj(p, v, n, f)
+    pos, nrm, cor = rr.load_obj_indexed(p)
+    assert len(cor) == len(f) == 320 and len(pos) == len(v) and len(nrm) == len(n)
+    s = rr.Scene()
+    s.load_obj(p)
+    assert rr.triangles_from_indexed(pos, nrm, cor).tobytes() == s.arrays()[0].tobytes()
+
+
+def test_indexed_obj_loader_lifts_the_reference_limits(tmp_path):
+    p = tmp_path / "m.obj"
+    p.write_text(
+        "v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0 0 2\nvn 0 0 1\n"
+        "f 1//1 2//1 3//1 4//1\n"   # quad -> two triangles (the reference drops the 4th corner)
+        "f 1 2 3\n"                 # no normals -> face normal (the reference skips the face)
+        "f 1/5 2/6 5/7\n"           # v/vt
+        "f -5//-1 -4//-1 -3//-1\n"  # relative indices
+        "f 1//1 2//1 9//1\n"        # out of range: skipped
+        "f 1//1 2//1\n"             # degenerate: skipped
+    )
+    pos, nrm, cor = rr.load_obj_indexed(p)
+    assert len(pos) == 5 and len(cor) == 5
+    assert cor[0].tolist() == [0, 1, 2, 0, 0, 0] and cor[1].tolist() == [0, 2, 3, 0, 0, 0]
+    assert cor[2, :3].tolist() == [0, 1, 2] and np.allclose(nrm[cor[2, 3]], [0, 0, 1])      # face normal of a CCW triangle in z=0
+    assert cor[3, :3].tolist() == [0, 1, 4] and np.allclose(nrm[cor[3, 3]], [0, -1, 0])
+    assert cor[4].tolist() == [0, 1, 2, 0, 0, 0]
+    with pytest.raises(_abi.RRError):
+        rr.load_obj_indexed(tmp_path / "missing.obj")
