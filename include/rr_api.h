@@ -185,6 +185,14 @@ const float* rr_obj_positions(const rr_obj* o);
 const float* rr_obj_normals(const rr_obj* o);
 const uint32_t* rr_obj_corners(const rr_obj* o);
 
+/* Re-poses the meshes of the uploaded scene.  The reference's video loop calls
+ * setupNextVideoFrame and then generateBuffers again for every frame (src/main.cpp:691-693, src/image.hpp:385-390),
+ * re-uploading every triangle and node although only MeshInfo.yaw changed.  The hierarchies here live in mesh-local
+ * space, so a new position / rotation / scale / material only rewrites the per-mesh records (one small kernel);
+ * triangles and LBVH stay in HBM.  n_meshes must equal the uploaded count; nodeIdx is ignored.  The images are
+ * the ones a fresh rr_upload_scene with the same arrays would give. */
+int rr_update_meshes(rr_ctx* ctx, const rr_mesh* meshes, size_t n_meshes);
+
 /* Counters of one render (exact, from device atomics). */
 typedef struct rr_stats {
   uint64_t samples;      /* Trace() calls = W*H*spp                         */
@@ -233,6 +241,31 @@ int rr_set_tuning(rr_ctx* ctx, const uint32_t* values, size_t n);
 int rr_render_device(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
                      uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, rr_stats* stats_out);
 int rr_read_frame(rr_ctx* ctx, uint8_t* rgba_out, size_t bytes);
+
+/* ------------------------------------------------------------------------
+ * Progressive mode: the frame-averaging loop of the
+ * reference (FRAME_TOTAL, src/settings.hpp:29-31; the live copy of the loop is
+ * the viewer's, src/main.cpp:481, 535, 575-582): every frame is rendered with
+ * its own seed term (kernel arg 7 = the 1-based frame number), its 8-bit RGB is
+ * ADDED to per-pixel integer sums and the displayed image is sum / frames
+ * (integer division).  Here the sums stay in HBM (three u32 planes) and one
+ * byte-streaming kernel does add + divide, so a frame costs one render plus
+ * 32 B/pixel of HBM traffic instead of a read-back and a host loop.
+ * ---------------------------------------------------------------------- */
+/* Zeroes the sums (numFrames = 0, src/main.cpp:356). */
+int rr_accum_reset(rr_ctx* ctx, uint32_t width, uint32_t height);
+/* Renders one frame with `frame_index` as the seed term, adds it to the sums and, if rgba_avg_out != NULL,
+ * returns the running average (alpha 255).  width / height must match rr_accum_reset. */
+int rr_accum_add_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
+                       uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, uint8_t* rgba_avg_out,
+                       rr_stats* stats_out);
+/* Frames added since the last reset. */
+int rr_accum_frame_count(rr_ctx* ctx, uint32_t* frames_out);
+/* reset + n_frames x add_frame with frame_index = first_frame_index + k (the reference counts from 1);
+ * rgba_out is the final average.  stats_out sums the frames (render_ms: total kernel time). */
+int rr_render_progressive(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
+                          uint32_t max_bounces, int32_t first_frame_index, uint32_t n_frames, uint32_t tile_size,
+                          uint8_t* rgba_out, rr_stats* stats_out);
 
 /* Primary-ray closest hit per pixel (MakeRay + CalculateRayCollisionWithTriangle,
  * src/Trace.cl:596-621, 434-485).  mesh_out: mesh index (spheres: n_meshes),
@@ -322,6 +355,11 @@ const rr_sphere* rr_scene_spheres(const rr_scene* s);
 int rr_scene_upload(rr_ctx* ctx, const rr_scene* s);
 /* Default camera of src/main.cpp:299-304 + src/settings.hpp:23-28. */
 void rr_default_camera(rr_camera* cam, uint32_t width, uint32_t height);
+/* setupNextVideoFrame (src/image.hpp:385-390): the scene change before video frame `frame_index` of
+ * `frame_count` (VIDEO_FRAME_COUNT): the LAST mesh's yaw = 2*pi/frame_count * frame_index + 5.5, in float. */
+int rr_video_frame_setup(rr_mesh* meshes, size_t n_meshes, int32_t frame_index, int32_t frame_count);
+/* Path of video frame number `frame_number` (1-based, src/main.cpp:701): "<dir>/output_<n>.bmp". */
+int rr_video_frame_path(const char* dir, int32_t frame_number, char* out, size_t out_len);
 
 #ifdef __cplusplus
 }

@@ -165,6 +165,7 @@ class Reference:
             l.ref_rand01.argtypes = [C.POINTER(C.c_uint)]
             l.ref_random_direction.argtypes = [C.POINTER(C.c_uint), _vp]
             l.ref_write_bmp.argtypes = [_vp, C.c_int, C.c_int, C.c_char_p]
+            l.ref_video_frame_setup.argtypes = [C.c_int, C.c_int]
             self._libs[variant] = l
         self.l = self._libs[variant]
 
@@ -194,6 +195,11 @@ class Reference:
         self.l.ref_copy(1, _p(m))
         self.l.ref_copy(2, _p(n))
         return t, m, n
+
+    def video_frame_setup(self, frame_index, frame_count):
+        """setupNextVideoFrame (src/image.hpp:385-390) on the current mesh list; returns the mesh array."""
+        assert self.l.ref_video_frame_setup(frame_index, frame_count) == 0
+        return self.arrays()[1]
 
     def default_camera(self, W, H):
         from ripoff_raytracer_b200._abi import CAMERA

@@ -29,6 +29,16 @@
 #include "settings.hpp"
 #include "readobj.hpp"  // pulls math.hpp
 #include "image_scene_part.inc"
+// The same reference text once more with the compile-time VIDEO_FRAME_COUNT (src/settings.hpp:55) bound to a
+// variable, so that setupNextVideoFrame (src/image.hpp:385-390) can be checked for any frame count.
+static int g_video_frame_count = 1;
+namespace vid {
+#undef VIDEO_FRAME_COUNT
+#define VIDEO_FRAME_COUNT g_video_frame_count
+#include "image_scene_part.inc"
+#undef VIDEO_FRAME_COUNT
+#define VIDEO_FRAME_COUNT 1
+}  // namespace vid
 
 // ---- reference kernel text, compiled as C++ -----------------------------
 namespace clk {
@@ -163,6 +173,18 @@ int ref_scene_from_arrays(const void* tris, size_t ntris, const void* meshes, co
   if (!g_tris.empty()) memcpy((void*)g_tris.data(), triangleList.data(), g_tris.size() * 96);
   if (!g_meshes.empty()) memcpy((void*)g_meshes.data(), meshList.data(), g_meshes.size() * 112);
   if (!g_nodes.empty()) memcpy((void*)g_nodes.data(), gpuNodes.data(), g_nodes.size() * 48);
+  return 0;
+}
+
+// setupNextVideoFrame of the reference on the current mesh list (src/main.cpp:691, 706).
+int ref_video_frame_setup(int frameIndex, int frameCount) {
+  if (g_meshes.empty() || frameCount <= 0) return 1;
+  meshList.resize(g_meshes.size());
+  memcpy((void*)meshList.data(), g_meshes.data(), g_meshes.size() * 112);
+  g_video_frame_count = frameCount;
+  CameraInformation cam{};
+  vid::setupNextVideoFrame(cam, frameIndex);
+  memcpy((void*)g_meshes.data(), meshList.data(), g_meshes.size() * 112);
   return 0;
 }
 

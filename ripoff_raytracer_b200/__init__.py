@@ -7,7 +7,7 @@ the thin Python mirror of that boundary used by the tests and bench.py.
 """
 from . import _abi, scenes  # noqa: F401
 from .api import (Renderer, Scene, default_camera, default_scene, load_obj_indexed, triangles_from_indexed,  # noqa: F401
-                  write_bmp)
+                  video_frame_path, video_frame_setup, write_bmp)
 
 __all__ = ["Renderer", "Scene", "default_camera", "default_scene", "load_obj_indexed", "triangles_from_indexed",
-           "write_bmp", "scenes"]
+           "video_frame_path", "video_frame_setup", "write_bmp", "scenes"]

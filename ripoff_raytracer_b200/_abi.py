@@ -122,11 +122,16 @@ SYMBOLS = {
     "rr_obj_normals": (_vp, [_vp]),
     "rr_obj_corners": (_vp, [_vp]),
     "rr_upload_scene_ref": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "rr_update_meshes": (C.c_int, [_vp, _vp, _sz]),
     "rr_render": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, _vp]),
     "rr_render_ex": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, _vp, _vp, C.POINTER(Stats), C.c_int]),
     "rr_set_tuning": (C.c_int, [_vp, _vp, _sz]),
     "rr_render_device": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, C.POINTER(Stats)]),
     "rr_read_frame": (C.c_int, [_vp, _vp, _sz]),
+    "rr_accum_reset": (C.c_int, [_vp, _u32, _u32]),
+    "rr_accum_add_frame": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, _vp, C.POINTER(Stats)]),
+    "rr_accum_frame_count": (C.c_int, [_vp, C.POINTER(_u32)]),
+    "rr_render_progressive": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, _u32, _vp, C.POINTER(Stats)]),
     "rr_primary_hits": (C.c_int, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "rr_bvh_size": (C.c_int, [_vp, C.c_int, C.POINTER(_u64)]),
     "rr_bvh_read": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -156,6 +161,8 @@ SYMBOLS = {
     "rr_scene_spheres": (_vp, [_vp]),
     "rr_scene_upload": (C.c_int, [_vp, _vp]),
     "rr_default_camera": (None, [_vp, _u32, _u32]),
+    "rr_video_frame_setup": (C.c_int, [_vp, _sz, _i32, _i32]),
+    "rr_video_frame_path": (C.c_int, [C.c_char_p, _i32, C.c_char_p, _sz]),
 }
 
 _lib = None

@@ -28,6 +28,19 @@ def default_camera(width: int, height: int) -> np.ndarray:
     return cam
 
 
+def video_frame_setup(meshes: np.ndarray, frame_index: int, frame_count: int) -> None:
+    """setupNextVideoFrame (src/image.hpp:385-390): edits the LAST mesh's yaw in place."""
+    assert meshes.dtype == MESH and meshes.flags["C_CONTIGUOUS"]
+    check(lib().rr_video_frame_setup(ptr(meshes), len(meshes), frame_index, frame_count), "rr_video_frame_setup")
+
+
+def video_frame_path(directory, frame_number: int) -> str:
+    """<dir>/output_<n>.bmp (src/main.cpp:701; the pattern render.sh hands to ffmpeg)."""
+    buf = C.create_string_buffer(4096)
+    check(lib().rr_video_frame_path(str(directory).encode(), frame_number, buf, len(buf)), "rr_video_frame_path")
+    return buf.value.decode()
+
+
 def write_bmp(path, rgba: np.ndarray) -> None:
     """placeImageDataIntoBMP (src/math.hpp:117-164)."""
     rgba = np.ascontiguousarray(rgba, np.uint8)
@@ -232,6 +245,36 @@ class Renderer:
         ref_nodes = np.ascontiguousarray(ref_nodes, _abi.REF_NODE)
         check(lib().rr_upload_scene_ref(self.h, ptr(tris), len(tris), ptr(meshes), len(meshes), ptr(ref_nodes), len(ref_nodes)),
               "rr_upload_scene_ref")
+
+    def update_meshes(self, meshes):
+        """rr_update_meshes: new MeshInfo (pose / material) for the uploaded scene, no re-upload, no rebuild."""
+        meshes = np.ascontiguousarray(meshes, MESH)
+        check(lib().rr_update_meshes(self.h, ptr(meshes), len(meshes)), "rr_update_meshes")
+
+    # -- progressive mode (src/main.cpp:481, 575-582) ---------------------------------
+    def accum_reset(self, width, height):
+        check(lib().rr_accum_reset(self.h, width, height), "rr_accum_reset")
+
+    def accum_add_frame(self, cam, width, height, spp, bounces, frame_index, tile=0, want_average=True):
+        cam = np.ascontiguousarray(cam, CAMERA)
+        avg = np.zeros((height, width, 4), np.uint8) if want_average else None
+        st = Stats()
+        check(lib().rr_accum_add_frame(self.h, ptr(cam), width, height, spp, bounces, frame_index, tile, ptr(avg), C.byref(st)),
+              "rr_accum_add_frame")
+        return avg, st.as_dict()
+
+    def accum_frame_count(self) -> int:
+        n = C.c_uint32()
+        check(lib().rr_accum_frame_count(self.h, C.byref(n)), "rr_accum_frame_count")
+        return int(n.value)
+
+    def render_progressive(self, cam, width, height, spp, bounces, n_frames, first_frame_index=1, tile=0):
+        cam = np.ascontiguousarray(cam, CAMERA)
+        rgba = np.zeros((height, width, 4), np.uint8)
+        st = Stats()
+        check(lib().rr_render_progressive(self.h, ptr(cam), width, height, spp, bounces, first_frame_index, n_frames, tile,
+                                          ptr(rgba), C.byref(st)), "rr_render_progressive")
+        return rgba, st.as_dict()
 
     # -- singleThreadedCompute / multiThreadedCompute -----------------------------
     def render(self, cam, width, height, spp, bounces, frame_index=0, tile=0, radiance=False, count_tests=False,

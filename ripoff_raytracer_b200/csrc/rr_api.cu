@@ -116,7 +116,14 @@ struct Device {
   float4* nodes = nullptr;  // triangle hierarchies, then the sphere hierarchy
   DMesh* meshes = nullptr;
   DMaterial* materials = nullptr;
+  // inputs of k_prepare_meshes, kept so that rr_update_meshes can re-pose the scene without a rebuild
+  rr_mesh* meshes_in = nullptr;
+  uint32_t *mesh_seg = nullptr, *mesh_pos = nullptr;
   float build_ms = 0.0f;
+  // progressive mode: per-pixel integer sums of the 8-bit frames, three planes (R, G, B) of width*height u32
+  uint32_t* accum = nullptr;
+  size_t accum_capacity = 0;  // pixels allocated
+  uint32_t accum_w = 0, accum_h = 0, accum_frames = 0;
   // frame
   uint8_t* frame = nullptr;
   size_t frame_bytes = 0;
@@ -260,6 +267,41 @@ __global__ void k_gather_tris(const float* __restrict__ pos, const float* __rest
   }
 }
 
+// Progressive mode: the host loop of src/main.cpp:575-582 as one byte-streaming kernel.  Four pixels per thread:
+// the new frame's RGBA8 quad (16 B) is added to the three u32 sum planes (16 B each, read + write) and the quad
+// is overwritten IN PLACE with sum / frames (integer division, alpha 255).  HBM-bound: 4 + 12 + 12 + 4 = 32 B per pixel.
+__global__ void __launch_bounds__(256) k_accum_add(uint32_t* __restrict__ frame, uint32_t* __restrict__ sum_r,
+                                                   uint32_t* __restrict__ sum_g, uint32_t* __restrict__ sum_b,
+                                                   size_t n_pixels, uint32_t frames) {
+  const size_t n_quads = n_pixels / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += stride) {
+    const uint4 px = reinterpret_cast<const uint4*>(frame)[q];
+    uint4 r = reinterpret_cast<uint4*>(sum_r)[q], g = reinterpret_cast<uint4*>(sum_g)[q], b = reinterpret_cast<uint4*>(sum_b)[q];
+    r.x += px.x & 0xffu; g.x += (px.x >> 8) & 0xffu; b.x += (px.x >> 16) & 0xffu;
+    r.y += px.y & 0xffu; g.y += (px.y >> 8) & 0xffu; b.y += (px.y >> 16) & 0xffu;
+    r.z += px.z & 0xffu; g.z += (px.z >> 8) & 0xffu; b.z += (px.z >> 16) & 0xffu;
+    r.w += px.w & 0xffu; g.w += (px.w >> 8) & 0xffu; b.w += (px.w >> 16) & 0xffu;
+    reinterpret_cast<uint4*>(sum_r)[q] = r;
+    reinterpret_cast<uint4*>(sum_g)[q] = g;
+    reinterpret_cast<uint4*>(sum_b)[q] = b;
+    uint4 avg;
+    avg.x = (r.x / frames) | ((g.x / frames) << 8) | ((b.x / frames) << 16) | 0xff000000u;
+    avg.y = (r.y / frames) | ((g.y / frames) << 8) | ((b.y / frames) << 16) | 0xff000000u;
+    avg.z = (r.z / frames) | ((g.z / frames) << 8) | ((b.z / frames) << 16) | 0xff000000u;
+    avg.w = (r.w / frames) | ((g.w / frames) << 8) | ((b.w / frames) << 16) | 0xff000000u;
+    reinterpret_cast<uint4*>(frame)[q] = avg;
+  }
+  // ragged tail (n_pixels % 4 pixels)
+  const size_t i = n_quads * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pixels) {
+    const uint32_t px = frame[i];
+    const uint32_t r = sum_r[i] + (px & 0xffu), g = sum_g[i] + ((px >> 8) & 0xffu), b = sum_b[i] + ((px >> 16) & 0xffu);
+    sum_r[i] = r; sum_g[i] = g; sum_b[i] = b;
+    frame[i] = (r / frames) | ((g / frames) << 8) | ((b / frames) << 16) | 0xff000000u;
+  }
+}
+
 struct IndexedInput {  // host arrays of rr_upload_scene_indexed
   const float* positions = nullptr;
   size_t n_positions = 0;
@@ -272,7 +314,8 @@ static void free_scene(Device& d) {
   cudaSetDevice(d.ordinal);
   dev_free(d.tris); dev_free(d.spheres); dev_free(d.tri_box); dev_free(d.sph_box);
   dev_free(d.tri_geom); dev_free(d.tri_nrm); dev_free(d.sph_geom); dev_free(d.meshes); dev_free(d.materials);
-  dev_free(d.nodes);
+  dev_free(d.nodes); dev_free(d.meshes_in); dev_free(d.mesh_seg); dev_free(d.mesh_pos);
+  d.meshes_in = nullptr; d.mesh_seg = nullptr; d.mesh_pos = nullptr;
   d.tris = nullptr; d.spheres = nullptr; d.tri_box = nullptr; d.sph_box = nullptr;
   d.tri_geom = d.tri_nrm = d.sph_geom = nullptr; d.meshes = nullptr; d.materials = nullptr; d.nodes = nullptr;
   lbvh_free(d.tb);
@@ -305,6 +348,16 @@ static int plan_segments(const rr_mesh_range* ranges, size_t n_meshes, size_t n_
       if (uniq[k].first == ranges[i].firstTriangle && uniq[k].count == ranges[i].numTriangles) { plan.mesh_seg[i] = (uint32_t)k; break; }
   }
   return RR_OK;
+}
+
+// Per-mesh records and the material table from the MeshInfo array on the device (upload and rr_update_meshes).
+static cudaError_t prepare_meshes(Device& d, size_t n_meshes, size_t n_spheres) {
+  if (n_meshes + n_spheres == 0) return cudaSuccess;
+  const int n = (int)(n_meshes + n_spheres);
+  k_prepare_meshes<<<(n + 127) / 128, 128, 0, d.stream>>>(d.meshes_in, d.mesh_seg, (int)n_meshes, d.tb.seg_box, d.tb.seg_sfirst,
+                                                          d.tb.seg_count, d.spheres, (int)n_spheres, d.sb.seg_box, (uint32_t)d.tb.n,
+                                                          d.mesh_pos, d.meshes, d.materials);
+  return cudaGetLastError();
 }
 
 static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput* indexed, size_t n_tris, const rr_mesh* meshes,
@@ -351,15 +404,9 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
   RR_CUDA(dev_malloc(&d.nodes, std::max<uint64_t>(d.tb.n + d.sb.n, 1) * node_bytes));
   if (d.tb.n) RR_CUDA(cudaMemcpyAsync(d.nodes, d.tb.nodes, d.tb.n * node_bytes, cudaMemcpyDeviceToDevice, st));
   if (d.sb.n) RR_CUDA(cudaMemcpyAsync(d.nodes + RR_NODE_QUADS * d.tb.n, d.sb.nodes, d.sb.n * node_bytes, cudaMemcpyDeviceToDevice, st));
-  // mesh + material tables
-  // temporaries of this upload: freed on every exit path
-  struct Temp {
-    rr_mesh* meshes_in = nullptr;
-    uint32_t *mesh_seg = nullptr, *mesh_pos = nullptr;
-    ~Temp() { dev_free(meshes_in); dev_free(mesh_seg); dev_free(mesh_pos); }
-  } tmp;
-  rr_mesh*& d_meshes_in = tmp.meshes_in;
-  uint32_t *&d_mesh_seg = tmp.mesh_seg, *&d_mesh_pos = tmp.mesh_pos;
+  // mesh + material tables (the inputs stay on the device for rr_update_meshes; free_scene releases them)
+  rr_mesh*& d_meshes_in = d.meshes_in;
+  uint32_t *&d_mesh_seg = d.mesh_seg, *&d_mesh_pos = d.mesh_pos;
   // visiting order of the meshes: most primitives first (a hit there prunes the small ones by their world box);
   // equal world distances are resolved by the original index in the kernel, so the order does not change results
   std::vector<uint32_t> mesh_pos(n_meshes + 1, 0);
@@ -380,13 +427,7 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
     RR_CUDA(cudaMemcpyAsync(d_meshes_in, meshes, n_meshes * sizeof(rr_mesh), cudaMemcpyHostToDevice, st));
     RR_CUDA(cudaMemcpyAsync(d_mesh_seg, plan.mesh_seg.data(), n_meshes * 4, cudaMemcpyHostToDevice, st));
   }
-  if (n_meshes + n_spheres) {
-    const int n = (int)(n_meshes + n_spheres);
-    k_prepare_meshes<<<(n + 127) / 128, 128, 0, st>>>(d_meshes_in, d_mesh_seg, (int)n_meshes, d.tb.seg_box, d.tb.seg_sfirst,
-                                                      d.tb.seg_count, d.spheres, (int)n_spheres, d.sb.seg_box, (uint32_t)d.tb.n, d_mesh_pos,
-                                                      d.meshes, d.materials);
-    RR_CUDA(cudaGetLastError());
-  }
+  RR_CUDA(prepare_meshes(d, n_meshes, n_spheres));
   RR_CUDA(cudaEventRecord(d.ev1, st));
   RR_CUDA(cudaStreamSynchronize(st));
   RR_CUDA(cudaEventElapsedTime(&d.build_ms, d.ev0, d.ev1));
@@ -570,7 +611,7 @@ const char* rr_error_string(int status) {
   }
 }
 const char* rr_last_error(void) { return g_last_error.c_str(); }
-int rr_version(void) { return 200; }
+int rr_version(void) { return 300; }
 
 int rr_device_count(int* out) {
   if (!out) return fail(RR_ERR_INVALID_ARGUMENT, "null output");
@@ -648,7 +689,7 @@ void rr_destroy(rr_ctx* ctx) {
       if (d.shared_queue) cudaIpcCloseMemHandle(d.shared_queue);
       if (d.shared_frame) cudaIpcCloseMemHandle(d.shared_frame);
     }
-    cudaFree(d.frame); cudaFree(d.radiance); cudaFree(d.queue); cudaFree(d.counters); cudaFree(d.stack); cudaFree(d.cold);
+    cudaFree(d.frame); cudaFree(d.radiance); cudaFree(d.accum); cudaFree(d.queue); cudaFree(d.counters); cudaFree(d.stack); cudaFree(d.cold);
     dev_trim(d.ordinal);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
@@ -775,6 +816,94 @@ int rr_read_frame(rr_ctx* ctx, uint8_t* rgba_out, size_t bytes) {
   if (!src || bytes > d0.frame_bytes) return fail(RR_ERR_INVALID_ARGUMENT, "no frame of that size has been rendered");
   RR_CUDA(cudaSetDevice(d0.ordinal));
   RR_CUDA(cudaMemcpy(rgba_out, src, bytes, cudaMemcpyDeviceToHost));
+  return RR_OK;
+}
+
+int rr_update_meshes(rr_ctx* ctx, const rr_mesh* meshes, size_t n_meshes) {
+  if (!ctx) return fail(RR_ERR_INVALID_ARGUMENT, "null context");
+  if (!ctx->has_scene) return fail(RR_ERR_NO_SCENE, "rr_upload_scene has not been called");
+  if (n_meshes != ctx->n_meshes) return fail(RR_ERR_INVALID_ARGUMENT, "mesh count differs from the uploaded scene (" + std::to_string(ctx->n_meshes) + ")");
+  if (n_meshes && !meshes) return fail(RR_ERR_INVALID_ARGUMENT, "null mesh array");
+  for (Device& d : ctx->dev) {
+    RR_CUDA(cudaSetDevice(d.ordinal));
+    if (n_meshes) RR_CUDA(cudaMemcpyAsync(d.meshes_in, meshes, n_meshes * sizeof(rr_mesh), cudaMemcpyHostToDevice, d.stream));
+    RR_CUDA(prepare_meshes(d, n_meshes, ctx->n_spheres));
+  }
+  for (Device& d : ctx->dev) {  // the caller's array may go away after the call (CL_MEM_COPY_HOST_PTR semantics)
+    RR_CUDA(cudaSetDevice(d.ordinal));
+    RR_CUDA(cudaStreamSynchronize(d.stream));
+  }
+  return RR_OK;
+}
+
+int rr_accum_reset(rr_ctx* ctx, uint32_t width, uint32_t height) {
+  if (!ctx) return fail(RR_ERR_INVALID_ARGUMENT, "null context");
+  if (width == 0 || height == 0 || (uint64_t)width * height > 0x7fffffffull) return fail(RR_ERR_INVALID_ARGUMENT, "bad image size");
+  Device& d = ctx->dev[0];
+  RR_CUDA(cudaSetDevice(d.ordinal));
+  const size_t n = (size_t)width * height, padded = (n + 3) & ~size_t(3);  // planes stay 16-byte aligned
+  if (padded > d.accum_capacity) {
+    cudaFree(d.accum);
+    d.accum = nullptr; d.accum_capacity = 0;
+    RR_CUDA(cudaMalloc(&d.accum, 3 * padded * sizeof(uint32_t)));
+    d.accum_capacity = padded;
+  }
+  RR_CUDA(cudaMemsetAsync(d.accum, 0, 3 * d.accum_capacity * sizeof(uint32_t), d.stream));
+  RR_CUDA(cudaStreamSynchronize(d.stream));
+  d.accum_w = width; d.accum_h = height; d.accum_frames = 0;
+  return RR_OK;
+}
+
+int rr_accum_frame_count(rr_ctx* ctx, uint32_t* frames_out) {
+  if (!ctx || !frames_out) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
+  *frames_out = ctx->dev[0].accum_frames;
+  return RR_OK;
+}
+
+int rr_accum_add_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
+                       uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, uint8_t* rgba_avg_out,
+                       rr_stats* stats_out) {
+  if (!ctx) return fail(RR_ERR_INVALID_ARGUMENT, "null context");
+  Device& d = ctx->dev[0];
+  if (!d.accum || d.accum_w != width || d.accum_h != height)
+    return fail(RR_ERR_INVALID_ARGUMENT, "rr_accum_reset with this image size has not been called");
+  if (d.accum_frames == 0x00ffffffu) return fail(RR_ERR_UNSUPPORTED, "too many frames for the 32-bit sums");
+  int rc = render_frame(ctx, cam, width, height, spp, max_bounces, frame_index, tile_size, false, false, 0, 0, 1, stats_out);
+  if (rc) return rc;
+  RR_CUDA(cudaSetDevice(d.ordinal));
+  const size_t n = (size_t)width * height;
+  d.accum_frames++;
+  uint32_t* planes = d.accum;
+  const int grid = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)d.sm_count * 8);
+  k_accum_add<<<grid, 256, 0, d.stream>>>(reinterpret_cast<uint32_t*>(d.frame), planes, planes + d.accum_capacity,
+                                          planes + 2 * d.accum_capacity, n, d.accum_frames);
+  RR_CUDA(cudaGetLastError());
+  if (rgba_avg_out) RR_CUDA(cudaMemcpyAsync(rgba_avg_out, d.frame, n * 4, cudaMemcpyDeviceToHost, d.stream));
+  RR_CUDA(cudaStreamSynchronize(d.stream));
+  return RR_OK;
+}
+
+int rr_render_progressive(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
+                          uint32_t max_bounces, int32_t first_frame_index, uint32_t n_frames, uint32_t tile_size,
+                          uint8_t* rgba_out, rr_stats* stats_out) {
+  if (!rgba_out) return fail(RR_ERR_INVALID_ARGUMENT, "null output image");
+  if (n_frames == 0) return fail(RR_ERR_INVALID_ARGUMENT, "n_frames must be positive");
+  int rc = check_render_args(ctx, cam, width, height, spp);
+  if (rc) return rc;
+  rc = rr_accum_reset(ctx, width, height);
+  if (rc) return rc;
+  rr_stats total;
+  memset(&total, 0, sizeof(total));
+  for (uint32_t k = 0; k < n_frames; ++k) {
+    rr_stats st;
+    rc = rr_accum_add_frame(ctx, cam, width, height, spp, max_bounces, (int32_t)((uint32_t)first_frame_index + k), tile_size,
+                            k + 1 == n_frames ? rgba_out : nullptr, &st);
+    if (rc) return rc;
+    total.samples += st.samples; total.rays += st.rays; total.rays_reused += st.rays_reused; total.box_tests += st.box_tests;
+    total.tri_tests += st.tri_tests; total.sphere_tests += st.sphere_tests; total.tiles += st.tiles;
+    total.render_ms += st.render_ms; total.build_ms = st.build_ms;
+  }
+  if (stats_out) *stats_out = total;
   return RR_OK;
 }
 

@@ -348,6 +348,21 @@ void rr_default_camera(rr_camera* cam, uint32_t width, uint32_t height) {
   cam->aspectRatio = (float)width / (float)height;
 }
 
+int rr_video_frame_setup(rr_mesh* meshes, size_t n_meshes, int32_t frame_index, int32_t frame_count) {
+  if (!meshes || n_meshes == 0 || frame_count <= 0) return RR_ERR_INVALID_ARGUMENT;
+  // src/image.hpp:387-390, same float operations in the same order
+  const float anglePerFrame = (3.14159265359f * 2.0f) / (float)frame_count;
+  const float currentRotation = anglePerFrame * (float)frame_index;
+  meshes[n_meshes - 1].yaw = currentRotation + 5.5f;
+  return RR_OK;
+}
+
+int rr_video_frame_path(const char* dir, int32_t frame_number, char* out, size_t out_len) {
+  if (!dir || !out || out_len == 0) return RR_ERR_INVALID_ARGUMENT;
+  const int n = snprintf(out, out_len, "%s/output_%d.bmp", dir, (int)frame_number);  // src/main.cpp:701
+  return (n < 0 || (size_t)n >= out_len) ? RR_ERR_INVALID_ARGUMENT : RR_OK;
+}
+
 int rr_write_bmp(const char* path, const uint8_t* rgba, uint32_t width, uint32_t height) {
   if (!path || !rgba) return RR_ERR_INVALID_ARGUMENT;
   FILE* f = fopen(path, "wb");

@@ -5,9 +5,20 @@
 // output.bmp (src/main.cpp:725).  Nothing of the render path lives here: it is ~150 lines of host glue.
 //
 //   printf '\n\n\n\n\nknight.obj\n' | ./gputest_b200        # empty line = default, as in the reference
+//
+// The reference's compile-time switches FRAME_TOTAL, VIDEO_FRAME_COUNT and VIDEO_FRAME_OUTPUT_DIR
+// (src/settings.hpp:29-31, 52-62) are read from the environment here (RR_FRAME_TOTAL, RR_VIDEO_FRAME_COUNT,
+// RR_VIDEO_FRAME_OUTPUT_DIR; defaults 1, 1, "img"), so that the stdin dialogue stays the reference's.  With
+// RR_VIDEO_FRAME_COUNT > 1 the video loop the reference has commented out (src/main.cpp:686-704) runs: per frame
+// setupNextVideoFrame, a re-pose of the meshes (rr_update_meshes instead of a full generateBuffers), the render
+// and <dir>/output_<n>.bmp (the numbering render.sh feeds to ffmpeg).  RR_FRAME_TOTAL > 1 averages that many
+// differently seeded frames per image (src/main.cpp:575-582).
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <filesystem>
 #include <iostream>
 #include <sstream>
 #include <string>
@@ -42,6 +53,31 @@ bool ask_uint(unsigned int* out) {
 }  // namespace
 
 int main() {
+  int FRAME_TOTAL = 1, VIDEO_FRAME_COUNT = 1;
+  std::string VIDEO_FRAME_OUTPUT_DIR = "img";
+  if (const char* e = std::getenv("RR_FRAME_TOTAL")) FRAME_TOTAL = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("RR_VIDEO_FRAME_COUNT")) VIDEO_FRAME_COUNT = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("RR_VIDEO_FRAME_OUTPUT_DIR")) VIDEO_FRAME_OUTPUT_DIR = e;
+  if (VIDEO_FRAME_COUNT > 1) {  // src/main.cpp:31-50: checked first, before anything is allocated
+    namespace fs = std::filesystem;
+    if (!fs::exists(VIDEO_FRAME_OUTPUT_DIR)) {
+      std::cout << "Output directory for video frames does not exist: " << VIDEO_FRAME_OUTPUT_DIR << std::endl;
+      std::cout << "Should one be made automatically in the current working directory? (y/N)\n> " << std::flush;
+      char response = 'n';
+      std::cin >> response;  // as the reference: the rest of this line then answers the device prompt (empty = default)
+      if (response == 'y' || response == 'Y') {
+        fs::create_directory(VIDEO_FRAME_OUTPUT_DIR);
+      } else {
+        std::cout << "Exiting..." << std::endl;
+        return 1;
+      }
+    } else if (!fs::is_empty(VIDEO_FRAME_OUTPUT_DIR)) {
+      std::cout << "Output directory for video frames is not empty: " << VIDEO_FRAME_OUTPUT_DIR << std::endl;
+      std::cout << "Files will not be overwritten, just in case you have something important in there.\n";
+      std::cout << "Please empty it and try again.\nExiting..." << std::endl;
+      return 1;
+    }
+  }
   int n_dev = 0;
   if (rr_device_count(&n_dev) != RR_OK || n_dev == 0) {
     std::cerr << "Failed to select a usable device on any platform." << std::endl;  // src/main.cpp:186-189
@@ -112,32 +148,58 @@ int main() {
   if (rc) die(rc, "rr_scene_add_cornell");
   rc = rr_scene_add_mesh(scene, &mesh, &range);
   if (rc) die(rc, "rr_scene_add_mesh");
-  rr_scene_mesh(scene, rr_scene_mesh_count(scene) - 1)->yaw = 5.5f;  // setupNextVideoFrame, src/image.hpp:385-390
+  const size_t n_meshes = rr_scene_mesh_count(scene);
+  rr_video_frame_setup(rr_scene_mesh(scene, 0), n_meshes, 0, VIDEO_FRAME_COUNT);  // setupNextVideoFrame(camInfo, 0), src/main.cpp:706
 
   rr_camera cam;  // src/main.cpp:299-304
   rr_default_camera(&cam, WIDTH, HEIGHT);
 
-  std::cout << rr_scene_triangle_count(scene) << " triangles, " << rr_scene_mesh_count(scene) << " meshes" << std::endl;
+  std::cout << rr_scene_triangle_count(scene) << " triangles, " << n_meshes << " meshes" << std::endl;
   rc = rr_scene_upload(ctx, scene);  // generateBuffers, src/main.cpp:709-717
   if (rc) die(rc, "rr_scene_upload");
 
   std::vector<uint8_t> pixels((size_t)WIDTH * HEIGHT * 4);
-  const auto t0 = std::chrono::high_resolution_clock::now();  // src/image.hpp:283
-  rr_stats st;
   // tile_size 0 = library default (8x4 warp tiles): the reference's TILE_SIZE = 512 only bounds the length of
   // one OpenCL launch (src/settings.hpp:44-48) and does not change the image (src/image.hpp:228: seed term 0)
   (void)TILE_SIZE;
-  rc = rr_render_ex(ctx, &cam, WIDTH, HEIGHT, RAYS_PER_PIXEL, MAX_BOUNCE_COUNT, 0, 0, pixels.data(), nullptr, &st, 0);
-  if (rc) die(rc, "rr_render");
-  const auto t1 = std::chrono::high_resolution_clock::now();
-  const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
-  std::cout << "Rendered " << st.tiles << " tiles, " << st.samples << " samples, " << st.rays << " path segments in " << ms
-            << " ms (kernel " << st.render_ms << " ms, LBVH build " << st.build_ms << " ms): "
-            << st.rays / (st.render_ms * 1e3) << " Mrays/s" << std::endl;
-
-  rc = rr_write_bmp("output.bmp", pixels.data(), WIDTH, HEIGHT);  // placeImageDataIntoBMP, src/main.cpp:725
-  if (rc) die(rc, "rr_write_bmp");
-  std::cout << "Wrote output.bmp" << std::endl;
+  // one image: a single frame with seed term 0 (src/image.hpp:228), or FRAME_TOTAL frames seeded 1.. and averaged
+  auto render_image = [&](rr_stats* st) {
+    if (FRAME_TOTAL > 1)
+      return rr_render_progressive(ctx, &cam, WIDTH, HEIGHT, RAYS_PER_PIXEL, MAX_BOUNCE_COUNT, 1, (uint32_t)FRAME_TOTAL, 0, pixels.data(), st);
+    return rr_render_ex(ctx, &cam, WIDTH, HEIGHT, RAYS_PER_PIXEL, MAX_BOUNCE_COUNT, 0, 0, pixels.data(), nullptr, st, 0);
+  };
+  auto report = [&](const rr_stats& st, double ms) {
+    std::cout << "Rendered " << st.tiles << " tiles, " << st.samples << " samples, " << st.rays << " path segments in " << ms
+              << " ms (kernel " << st.render_ms << " ms, LBVH build " << st.build_ms << " ms): "
+              << st.rays / (st.render_ms * 1e3) << " Mrays/s" << std::endl;
+  };
+  if (VIDEO_FRAME_COUNT > 1) {  // the loop of src/main.cpp:686-704
+    for (int videoFrameIdx = 0; videoFrameIdx < VIDEO_FRAME_COUNT;) {
+      rr_video_frame_setup(rr_scene_mesh(scene, 0), n_meshes, videoFrameIdx++, VIDEO_FRAME_COUNT);
+      rc = rr_update_meshes(ctx, rr_scene_meshes(scene), n_meshes);
+      if (rc) die(rc, "rr_update_meshes");
+      std::cout << "Rendering video frame " << videoFrameIdx << " of " << VIDEO_FRAME_COUNT << std::endl;
+      const auto t0 = std::chrono::high_resolution_clock::now();
+      rr_stats st;
+      rc = render_image(&st);
+      if (rc) die(rc, "rr_render");
+      report(st, std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count());
+      char path[4096];
+      rc = rr_video_frame_path(VIDEO_FRAME_OUTPUT_DIR.c_str(), videoFrameIdx, path, sizeof(path));
+      if (!rc) rc = rr_write_bmp(path, pixels.data(), WIDTH, HEIGHT);
+      if (rc) die(rc, "rr_write_bmp");
+    }
+    std::cout << "Wrote " << VIDEO_FRAME_COUNT << " frames to " << VIDEO_FRAME_OUTPUT_DIR << std::endl;
+  } else {
+    const auto t0 = std::chrono::high_resolution_clock::now();  // src/image.hpp:283
+    rr_stats st;
+    rc = render_image(&st);
+    if (rc) die(rc, "rr_render");
+    report(st, std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count());
+    rc = rr_write_bmp("output.bmp", pixels.data(), WIDTH, HEIGHT);  // placeImageDataIntoBMP, src/main.cpp:725
+    if (rc) die(rc, "rr_write_bmp");
+    std::cout << "Wrote output.bmp" << std::endl;
+  }
   rr_scene_destroy(scene);
   rr_destroy(ctx);  // src/main.cpp:728-730
   return 0;

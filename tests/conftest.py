@@ -50,3 +50,9 @@ def renderer():
 def psnr(a, b, peak=255.0):
     mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
     return float("inf") if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+
+
+@pytest.fixture(scope="session")
+def golden_video():
+    """Progressive averages and video poses produced by the reference (tests/golden/make_golden.py progressive_video)."""
+    return dict(np.load(GOLDEN / "progressive_video.npz"))

@@ -70,7 +70,48 @@ def rng_case():
     print("rng", seeds)
 
 
+def progressive_video_case():
+    """Progressive averaging (src/main.cpp:481, 575-582) and the video pose (src/image.hpp:385-390) on the
+    default_small scene: the reference kernel renders frame k with kernel arg 7 = k (1-based), the 8-bit frames
+    are summed in integers and divided by the frame count; setupNextVideoFrame is the reference's own text with
+    VIDEO_FRAME_COUNT bound to a variable (oracle/ref_shim/ref_driver.cpp)."""
+    ref = Reference("strict")
+    g = dict(np.load(OUT / "default_small.npz"))
+    W, H = int(g["W"]), int(g["H"])
+    ref.scene_set(g["tris"], g["meshes"], g["gpunodes"])
+    data = {}
+    spp, bounces, frames = 2, 8, 5
+    sums = np.zeros((H, W, 3), np.uint32)
+    for k in range(1, frames + 1):
+        rgba, _ = ref.render(g["cam"], W, H, spp, bounces, frame_index=k)
+        sums += rgba[..., :3]
+        data[f"avg_after_{k}"] = (sums // k).astype(np.uint8)
+        if k == 1:
+            data["frame_1"] = rgba
+    data["prog_spp"], data["prog_bounces"], data["prog_frames"] = spp, bounces, frames
+    count = 6
+    yaws, images = [], []
+    for idx in range(count):
+        meshes = ref.video_frame_setup(idx, count)
+        yaws.append(meshes["yaw"][-1])
+        if idx in (0, 2, 5):
+            rgba, _ = ref.render(g["cam"], W, H, 2, 8, frame_index=0)
+            images.append(rgba)
+    data["video_count"] = count
+    data["video_yaw"] = np.array(yaws, np.float32)
+    data["video_rgba_idx"] = np.array([0, 2, 5])
+    data["video_rgba"] = np.array(images)
+    data["video_yaw_count1"] = np.array([ref.video_frame_setup(i, 1)["yaw"][-1] for i in range(4)], np.float32)
+    data["video_yaw_count360"] = np.array([ref.video_frame_setup(i, 360)["yaw"][-1] for i in (0, 1, 7, 180, 359)], np.float32)
+    np.savez_compressed(OUT / "progressive_video.npz", **data)
+    print("progressive_video", {k: getattr(v, "shape", v) for k, v in data.items()})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "progressive_video":  # added later: leaves the older fixtures untouched
+        progressive_video_case()
+        sys.exit(0)
     default_scene_case("default_small", 16, 8, 64, 64, [(1, 1), (1, 8), (4, 50), (16, 50)])
     default_scene_case("default_wide", 24, 12, 96, 54, [(1, 1), (2, 50)])
     rng_case()
+    progressive_video_case()

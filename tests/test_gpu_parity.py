@@ -512,3 +512,112 @@ def test_indexed_upload_assembles_the_same_triangles_on_the_device(knight_obj):
     assert np.array_equal(got, want) and np.array_equal(bits(grad), bits(wrad))
     for key in ("codes", "order", "left", "right", "bounds"):
         assert np.array_equal(gb[key], wb[key]), key
+
+
+# ------------------------------------------- progressive / video --
+def test_progressive_average_matches_reference_golden(renderer, golden_small, golden_video):
+    """rr_accum_* / rr_render_progressive == the reference's averaging loop (src/main.cpp:481, 575-582) run on the
+    reference's own kernel text: frame k seeded with k, integer sums, integer division -- byte for byte."""
+    g, v = golden_small, golden_video
+    W, H = int(g["W"]), int(g["H"])
+    spp, bounces, frames = int(v["prog_spp"]), int(v["prog_bounces"]), int(v["prog_frames"])
+    renderer.upload_arrays(g["tris"], g["meshes"], g["ranges"])
+    one, _, _ = renderer.render(g["cam"], W, H, spp, bounces, frame_index=1)
+    assert np.array_equal(one, v["frame_1"])
+    renderer.accum_reset(W, H)
+    assert renderer.accum_frame_count() == 0
+    for k in range(1, frames + 1):
+        avg, st = renderer.accum_add_frame(g["cam"], W, H, spp, bounces, frame_index=k)
+        assert renderer.accum_frame_count() == k
+        assert np.array_equal(avg[..., :3], v[f"avg_after_{k}"]), k
+        assert (avg[..., 3] == 255).all() and st["samples"] == W * H * spp
+    final, st = renderer.render_progressive(g["cam"], W, H, spp, bounces, frames)
+    assert np.array_equal(final[..., :3], v[f"avg_after_{frames}"])
+    assert st["samples"] == W * H * spp * frames
+    with pytest.raises(_abi.RRError):  # size differs from the reset
+        renderer.accum_add_frame(g["cam"], W + 1, H, spp, bounces, frame_index=1)
+
+
+def test_progressive_ragged_sizes_vs_oracle(renderer, golden_small):
+    """The accumulation kernel handles four pixels per thread; sizes with W*H % 4 != 0 exercise its tail."""
+    g = golden_small
+    o = Oracle(g["tris"], g["meshes"], g["ranges"])
+    renderer.upload_arrays(g["tris"], g["meshes"], g["ranges"])
+    for W, H in [(7, 5), (1, 1), (33, 3), (2, 1)]:
+        cam = g["cam"].copy()
+        cam["aspectRatio"] = np.float32(W) / np.float32(H)
+        sums = np.zeros((H, W, 3), np.uint32)
+        for k in range(1, 4):
+            sums += o.render(cam, W, H, 1, 6, frame_index=k)[0][..., :3]
+        got, _ = renderer.render_progressive(cam, W, H, 1, 6, 3)
+        assert np.array_equal(got[..., :3], (sums // 3).astype(np.uint8)), (W, H)
+
+
+def test_update_meshes_reposes_without_rebuild(renderer, golden_small, golden_video):
+    """The video loop (src/main.cpp:686-704): setupNextVideoFrame + rr_update_meshes instead of a full
+    generateBuffers.  Images equal the reference's for the same pose and equal a fresh upload; the LBVH is untouched."""
+    g, v = golden_small, golden_video
+    W, H = int(g["W"]), int(g["H"])
+    renderer.upload_arrays(g["tris"], g["meshes"], g["ranges"])
+    bvh0 = renderer.bvh(0)
+    count = int(v["video_count"])
+    for idx, want in zip(v["video_rgba_idx"], v["video_rgba"]):
+        m = g["meshes"].copy()
+        rr.video_frame_setup(m, int(idx), count)
+        renderer.update_meshes(m)
+        got, _, _ = renderer.render(g["cam"], W, H, 2, 8)
+        assert np.array_equal(got, want), int(idx)
+    bvh1 = renderer.bvh(0)
+    assert all(np.array_equal(bvh0[k], bvh1[k]) for k in bvh0)
+    # materials, position and scale are re-read too: compare with a fresh upload of the edited meshes
+    m = g["meshes"].copy()
+    m["pos"][-1, :3] += (15.0, 5.0, -20.0)
+    m["scale"][-1] = 0.75
+    m["roll"][-1] = 0.4
+    m["material"]["type"][-1] = _abi.MATERIAL_GLASSY
+    m["material"]["ior"][-1] = 1.4
+    m["material"]["color"][3, :3] = (0.9, 0.1, 0.9)
+    renderer.update_meshes(m)
+    got, grad, _ = renderer.render(g["cam"], W, H, 3, 12, radiance=True)
+    fresh = rr.Renderer()
+    fresh.upload_arrays(g["tris"], m, g["ranges"])
+    want, wrad, _ = fresh.render(g["cam"], W, H, 3, 12, radiance=True)
+    fresh.close()
+    assert np.array_equal(got, want) and np.array_equal(bits(grad), bits(wrad))
+    orad = Oracle(g["tris"], m, g["ranges"]).render(g["cam"], W, H, 3, 12, radiance=True)[1]
+    assert np.array_equal(bits(grad), bits(orad))
+    with pytest.raises(_abi.RRError):
+        renderer.update_meshes(m[:-1])
+
+
+def test_command_line_driver_video_and_progressive(knight_obj, tmp_path):
+    """gputest_b200 with RR_VIDEO_FRAME_COUNT / RR_FRAME_TOTAL: img/output_<n>.bmp per video frame, each the
+    average of FRAME_TOTAL seeded frames -- byte-identical to the library path."""
+    import os
+    import subprocess
+    from pathlib import Path
+
+    exe = Path(_abi.PKG_DIR) / "csrc" / "gputest_b200"
+    if not exe.exists():
+        pytest.skip("gputest_b200 not built")
+    W, H, spp, bounces, count, total = 80, 48, 2, 6, 3, 2
+    # first answer: create the img directory (src/main.cpp:34-38).  The reference reads it with `cin >> char`, so the
+    # rest of that line is what the device prompt's getline sees (empty = default device), and so does gputest_b200.
+    answers = f"y\n{W}\n{H}\n{spp}\n{bounces}\n{knight_obj}\n"
+    env = dict(os.environ, RR_VIDEO_FRAME_COUNT=str(count), RR_FRAME_TOTAL=str(total))
+    p = subprocess.run([str(exe)], input=answers, text=True, capture_output=True, cwd=tmp_path, timeout=120, env=env)
+    assert p.returncode == 0, p.stderr + p.stdout
+    s = rr.default_scene(knight_obj)
+    r = rr.Renderer()
+    r.upload(s)
+    m = s.arrays()[1]
+    for idx in range(count):
+        rr.video_frame_setup(m, idx, count)
+        r.update_meshes(m)
+        img, _ = r.render_progressive(rr.default_camera(W, H), W, H, spp, bounces, total)
+        rr.write_bmp(tmp_path / "want.bmp", img)
+        assert (tmp_path / rr.video_frame_path("img", idx + 1)).read_bytes() == (tmp_path / "want.bmp").read_bytes(), idx
+    r.close()
+    # a non-empty output directory is refused, as in the reference (src/main.cpp:44-49)
+    p = subprocess.run([str(exe)], input=answers[2:], text=True, capture_output=True, cwd=tmp_path, timeout=120, env=env)
+    assert p.returncode == 1 and "not empty" in p.stdout

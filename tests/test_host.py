@@ -145,3 +145,30 @@ def test_indexed_obj_loader_lifts_the_reference_limits(tmp_path):
     assert cor[4].tolist() == [0, 1, 2, 0, 0, 0]
     with pytest.raises(_abi.RRError):
         rr.load_obj_indexed(tmp_path / "missing.obj")
+
+
+def test_video_frame_setup_matches_reference(golden_video):
+    """setupNextVideoFrame (src/image.hpp:385-390): yaw of the LAST mesh, float for float."""
+    g = golden_video
+    for count, idxs, want in [(int(g["video_count"]), range(int(g["video_count"])), g["video_yaw"]),
+                              (1, range(4), g["video_yaw_count1"]), (360, (0, 1, 7, 180, 359), g["video_yaw_count360"])]:
+        for idx, w in zip(idxs, want):
+            m = np.zeros(3, _abi.MESH)
+            m["yaw"] = 0.25
+            rr.video_frame_setup(m, idx, count)
+            assert m["yaw"][2].view(np.uint32) == np.float32(w).view(np.uint32), (count, idx)
+            assert m["yaw"][0] == np.float32(0.25) and m["yaw"][1] == np.float32(0.25)  # only meshList.back() moves
+    if Reference.available():
+        ref = Reference("strict")
+        ref.scene_set(np.zeros(0, _abi.TRIANGLE), np.zeros(2, _abi.MESH), np.zeros(0, _abi.GPU_NODE))
+        for idx, count in [(3, 7), (59, 60), (0, 1)]:
+            m = np.zeros(2, _abi.MESH)
+            rr.video_frame_setup(m, idx, count)
+            assert m["yaw"].tobytes() == ref.video_frame_setup(idx, count)["yaw"].tobytes()
+    with pytest.raises(_abi.RRError):
+        rr.video_frame_setup(np.zeros(1, _abi.MESH), 0, 0)
+
+
+def test_video_frame_path():
+    assert rr.video_frame_path("img", 1) == "img/output_1.bmp"      # src/main.cpp:701, render.sh:12
+    assert rr.video_frame_path("/tmp/x", 120) == "/tmp/x/output_120.bmp"

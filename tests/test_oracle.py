@@ -194,3 +194,31 @@ def test_hierarchy_only_culls_brute_force_defines_the_result(golden_wide, knight
         bi, br, bst = brute.render(cam, W, H, 2, 12, radiance=True)
         assert np.array_equal(wi, bi) and np.array_equal(wr.view(np.uint32), br.view(np.uint32))
         assert wst["rays"] == bst["rays"] and wst["tri_tests"] < bst["tri_tests"]
+
+
+def test_oracle_frame_seed_and_progressive_average_vs_reference_golden(golden_small, golden_video):
+    """Kernel arg 7 (frameIndex, src/Trace.cl:172,632) through the restatement, and the integer averaging loop of
+    src/main.cpp:575-582 in numpy: equal to what the reference's own kernel text produced."""
+    g, v = golden_small, golden_video
+    W, H = int(g["W"]), int(g["H"])
+    o = Oracle(g["tris"], g["meshes"], g["ranges"])
+    spp, bounces, frames = int(v["prog_spp"]), int(v["prog_bounces"]), int(v["prog_frames"])
+    sums = np.zeros((H, W, 3), np.uint32)
+    for k in range(1, frames + 1):
+        rgba, _, _ = o.render(g["cam"], W, H, spp, bounces, frame_index=k)
+        if k == 1:
+            assert np.array_equal(rgba, v["frame_1"])
+        sums += rgba[..., :3]
+        assert np.array_equal((sums // k).astype(np.uint8), v[f"avg_after_{k}"]), k
+    # a different seed term gives a different image (the reference's live path always passes 0, src/image.hpp:228)
+    assert not np.array_equal(v["frame_1"], g["rgba_s4_b50"])
+
+
+def test_oracle_video_pose_vs_reference_golden(golden_small, golden_video):
+    g, v = golden_small, golden_video
+    W, H = int(g["W"]), int(g["H"])
+    for idx, want in zip(v["video_rgba_idx"], v["video_rgba"]):
+        m = g["meshes"].copy()
+        m["yaw"][-1] = v["video_yaw"][idx]
+        rgba, _, _ = Oracle(g["tris"], m, g["ranges"]).render(g["cam"], W, H, 2, 8)
+        assert np.array_equal(rgba, want), int(idx)
