@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
+#include <cstddef>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -119,6 +121,10 @@ struct Device {
   // inputs of k_prepare_meshes, kept so that rr_update_meshes can re-pose the scene without a rebuild
   rr_mesh* meshes_in = nullptr;
   uint32_t *mesh_seg = nullptr, *mesh_pos = nullptr;
+  std::vector<uint64_t> entry_count;  // host: primitives of every mesh (+ the sphere set), for the visiting order
+  float4* tlas_blocks = nullptr;      // > 32 meshes: the implicit top-level tree, one allocation: block boxes ...
+  float4* tlas = nullptr;             // ... then the chunk level and the levels above it (RenderParams::tlas)
+  uint32_t* tlas_levels = nullptr;    // device: level count, first box of every level (RenderParams::tlas_levels)
   float build_ms = 0.0f;
   // progressive mode: per-pixel integer sums of the 8-bit frames, three planes (R, G, B) of width*height u32
   uint32_t* accum = nullptr;
@@ -314,8 +320,8 @@ static void free_scene(Device& d) {
   cudaSetDevice(d.ordinal);
   dev_free(d.tris); dev_free(d.spheres); dev_free(d.tri_box); dev_free(d.sph_box);
   dev_free(d.tri_geom); dev_free(d.tri_nrm); dev_free(d.sph_geom); dev_free(d.meshes); dev_free(d.materials);
-  dev_free(d.nodes); dev_free(d.meshes_in); dev_free(d.mesh_seg); dev_free(d.mesh_pos);
-  d.meshes_in = nullptr; d.mesh_seg = nullptr; d.mesh_pos = nullptr;
+  dev_free(d.nodes); dev_free(d.meshes_in); dev_free(d.mesh_seg); dev_free(d.mesh_pos); dev_free(d.tlas_blocks); dev_free(d.tlas_levels);
+  d.meshes_in = nullptr; d.mesh_seg = nullptr; d.mesh_pos = nullptr; d.tlas_blocks = nullptr; d.tlas = nullptr; d.tlas_levels = nullptr;
   d.tris = nullptr; d.spheres = nullptr; d.tri_box = nullptr; d.sph_box = nullptr;
   d.tri_geom = d.tri_nrm = d.sph_geom = nullptr; d.meshes = nullptr; d.materials = nullptr; d.nodes = nullptr;
   lbvh_free(d.tb);
@@ -350,14 +356,140 @@ static int plan_segments(const rr_mesh_range* ranges, size_t n_meshes, size_t n_
   return RR_OK;
 }
 
-// Per-mesh records and the material table from the MeshInfo array on the device (upload and rr_update_meshes).
-static cudaError_t prepare_meshes(Device& d, size_t n_meshes, size_t n_spheres) {
-  if (n_meshes + n_spheres == 0) return cudaSuccess;
+// World boxes of the implicit top-level tree (RenderParams::tlas_blocks / tlas): output box w is the union of `fan`
+// consecutive input boxes -- mesh world boxes (skipped meshes excluded) for the blocks, boxes of the level below
+// otherwise.  An empty union is stored as a NaN box, which no ray enters.  A few thousand boxes at most per launch.
+__global__ void k_tlas_boxes(const DMesh* __restrict__ meshes, const float4* __restrict__ in_boxes, int n_in, int fan,
+                             float4* __restrict__ out, int n_out) {
+  const int w = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (w >= n_out) return;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = fan * w; i < min(fan * w + fan, n_in); ++i) {
+    float4 a, b;
+    bool use;
+    if (meshes) {
+      a = meshes[i].wmin; b = meshes[i].wmax;
+      use = !(__float_as_uint(a.w) & RR_MF_SKIP);
+    } else {
+      a = in_boxes[2 * i]; b = in_boxes[2 * i + 1];
+      use = a.x == a.x;  // not an empty (NaN) box
+    }
+    if (use) {
+      lo[0] = fminf(lo[0], a.x); lo[1] = fminf(lo[1], a.y); lo[2] = fminf(lo[2], a.z);
+      hi[0] = fmaxf(hi[0], b.x); hi[1] = fmaxf(hi[1], b.y); hi[2] = fmaxf(hi[2], b.z);
+    }
+  }
+  const bool empty = lo[0] > hi[0];
+  const float q = __int_as_float(0x7fc00000);
+  out[2 * w] = empty ? make_float4(q, q, q, 0.0f) : make_float4(lo[0], lo[1], lo[2], 0.0f);
+  out[2 * w + 1] = empty ? make_float4(q, q, q, 0.0f) : make_float4(hi[0], hi[1], hi[2], 0.0f);
+}
+
+static inline uint64_t spread21(uint64_t v) {  // 21 bits -> every third bit
+  v &= 0x1fffffull;
+  v = (v | v << 32) & 0x1f00000000ffffull;
+  v = (v | v << 16) & 0x1f0000ff0000ffull;
+  v = (v | v << 8) & 0x100f00f00f00f00full;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+  v = (v | v << 2) & 0x1249249249249249ull;
+  return v;
+}
+
+// Per-mesh records and the material table from the MeshInfo array on the device (upload and rr_update_meshes), in
+// the order the kernel visits them.  Up to 32 entries (meshes + the sphere set): one chunk, most primitives first (a
+// hit there prunes the small ones by their world box).  More: Morton order of the world-box centres, so that the
+// 32-mesh chunks are compact and the top level (k_tlas_boxes) can cull them; inside a chunk, most primitives first.
+// Equal world distances are resolved by the original mesh index in the kernel: the order never changes a result.
+static int prepare_meshes(Device& d, size_t n_meshes, size_t n_spheres) {
+  const size_t n_entries = n_meshes + (n_spheres ? 1 : 0);
+  if (n_meshes + n_spheres == 0) return RR_OK;
+  cudaStream_t st = d.stream;
   const int n = (int)(n_meshes + n_spheres);
-  k_prepare_meshes<<<(n + 127) / 128, 128, 0, d.stream>>>(d.meshes_in, d.mesh_seg, (int)n_meshes, d.tb.seg_box, d.tb.seg_sfirst,
-                                                          d.tb.seg_count, d.spheres, (int)n_spheres, d.sb.seg_box, (uint32_t)d.tb.n,
-                                                          d.mesh_pos, d.meshes, d.materials);
-  return cudaGetLastError();
+  auto launch = [&]() -> cudaError_t {
+    k_prepare_meshes<<<(n + 127) / 128, 128, 0, st>>>(d.meshes_in, d.mesh_seg, (int)n_meshes, d.tb.seg_box, d.tb.seg_sfirst,
+                                                      d.tb.seg_count, d.spheres, (int)n_spheres, d.sb.seg_box, (uint32_t)d.tb.n,
+                                                      d.mesh_pos, d.meshes, d.materials);
+    return cudaGetLastError();
+  };
+  std::vector<uint32_t> pos(n_meshes + 1, 0);
+  std::vector<uint32_t> order(n_entries);  // order[k] = entry at position k
+  for (size_t k = 0; k < n_entries; ++k) order[k] = (uint32_t)k;
+  auto by_count = [&](uint32_t a, uint32_t b) { return d.entry_count[a] > d.entry_count[b]; };
+  if (n_entries <= 32) {
+    std::stable_sort(order.begin(), order.end(), by_count);
+  } else {
+    // pass 1 in upload order, to learn the world boxes
+    for (size_t k = 0; k <= n_meshes; ++k) pos[k] = (uint32_t)k;
+    RR_CUDA(cudaMemcpyAsync(d.mesh_pos, pos.data(), (n_meshes + 1) * 4, cudaMemcpyHostToDevice, st));
+    RR_CUDA(launch());
+    std::vector<float> wb(n_entries * 8);
+    RR_CUDA(cudaMemcpy2DAsync(wb.data(), 32, reinterpret_cast<const char*>(d.meshes) + offsetof(DMesh, wmin), sizeof(DMesh), 32,
+                              n_entries, cudaMemcpyDeviceToHost, st));
+    RR_CUDA(cudaStreamSynchronize(st));
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    std::vector<char> skip(n_entries);
+    for (size_t k = 0; k < n_entries; ++k) {
+      uint32_t flags;
+      memcpy(&flags, &wb[8 * k + 3], 4);
+      skip[k] = (flags & RR_MF_SKIP) != 0;
+      if (skip[k]) continue;
+      for (int a = 0; a < 3; ++a) {
+        const float c = 0.5f * (wb[8 * k + a] + wb[8 * k + 4 + a]);
+        if (c == c && std::fabs(c) < 3.0e38f) { lo[a] = std::min(lo[a], c); hi[a] = std::max(hi[a], c); }
+      }
+    }
+    std::vector<uint64_t> key(n_entries, ~0ull);  // skipped meshes go last
+    for (size_t k = 0; k < n_entries; ++k) {
+      if (skip[k]) continue;
+      uint64_t code = 0;
+      for (int a = 0; a < 3; ++a) {
+        const float c = 0.5f * (wb[8 * k + a] + wb[8 * k + 4 + a]);
+        const float ext = hi[a] - lo[a];
+        double u = (ext > 0.0f && c == c) ? ((double)c - lo[a]) / ext : 0.0;
+        u = std::min(std::max(u, 0.0), 1.0);
+        code |= spread21((uint64_t)(u * 2097151.0)) << (2 - a);
+      }
+      key[k] = code;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+    for (size_t c = 0; c < n_entries; c += 8) std::stable_sort(order.begin() + c, order.begin() + std::min(c + 8, n_entries), by_count);
+  }
+  for (size_t k = 0; k < n_entries; ++k) pos[order[k]] = (uint32_t)k;
+  RR_CUDA(cudaMemcpyAsync(d.mesh_pos, pos.data(), (n_meshes + 1) * 4, cudaMemcpyHostToDevice, st));
+  RR_CUDA(launch());
+  uint32_t level_info[1 + RR_TLAS_MAX_LEVELS] = {0};
+  if (n_entries > 32) {
+    // blocks of 8 meshes, chunks of 4 blocks, then 4 boxes per box until one box is left
+    const int n_blocks = (int)((n_entries + 7) / 8);
+    std::vector<int> count;  // boxes per level of RenderParams::tlas
+    for (int n = (n_blocks + 3) / 4;; n = (n + 3) / 4) {
+      count.push_back(n);
+      if (n == 1 || (int)count.size() == RR_TLAS_MAX_LEVELS) break;
+    }
+    size_t total = (size_t)n_blocks;
+    for (int c : count) total += (size_t)c;
+    if (!d.tlas_blocks) RR_CUDA(dev_malloc(&d.tlas_blocks, total * 2 * sizeof(float4)));
+    d.tlas = d.tlas_blocks + 2 * (size_t)n_blocks;
+    k_tlas_boxes<<<(n_blocks + 127) / 128, 128, 0, st>>>(d.meshes, nullptr, (int)n_entries, 8, d.tlas_blocks, n_blocks);
+    RR_CUDA(cudaGetLastError());
+    const float4* in = d.tlas_blocks;
+    int n_in = n_blocks;
+    uint32_t off = 0;
+    for (size_t l = 0; l < count.size(); ++l) {
+      float4* out = d.tlas + 2 * (size_t)off;
+      k_tlas_boxes<<<(count[l] + 127) / 128, 128, 0, st>>>(nullptr, in, n_in, 4, out, count[l]);
+      RR_CUDA(cudaGetLastError());
+      level_info[1 + l] = off;
+      off += (uint32_t)count[l];
+      in = out;
+      n_in = count[l];
+    }
+    level_info[0] = (uint32_t)count.size();
+    if (!d.tlas_levels) RR_CUDA(dev_malloc(&d.tlas_levels, sizeof(level_info)));
+    RR_CUDA(cudaMemcpyAsync(d.tlas_levels, level_info, sizeof(level_info), cudaMemcpyHostToDevice, st));
+  }
+  RR_CUDA(cudaStreamSynchronize(st));  // `pos` is pageable host memory read by the copies above
+  return RR_OK;
 }
 
 static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput* indexed, size_t n_tris, const rr_mesh* meshes,
@@ -407,18 +539,10 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
   // mesh + material tables (the inputs stay on the device for rr_update_meshes; free_scene releases them)
   rr_mesh*& d_meshes_in = d.meshes_in;
   uint32_t *&d_mesh_seg = d.mesh_seg, *&d_mesh_pos = d.mesh_pos;
-  // visiting order of the meshes: most primitives first (a hit there prunes the small ones by their world box);
-  // equal world distances are resolved by the original index in the kernel, so the order does not change results
-  std::vector<uint32_t> mesh_pos(n_meshes + 1, 0);
-  {
-    std::vector<std::pair<uint64_t, uint32_t>> byCount;
-    for (size_t i = 0; i < n_meshes; ++i) byCount.push_back({plan.count[plan.mesh_seg[i]], (uint32_t)i});
-    if (n_spheres) byCount.push_back({n_spheres, (uint32_t)n_meshes});
-    std::stable_sort(byCount.begin(), byCount.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
-    for (size_t k = 0; k < byCount.size(); ++k) mesh_pos[byCount[k].second] = (uint32_t)k;
-  }
+  d.entry_count.assign(n_meshes + (n_spheres ? 1 : 0), 0);
+  for (size_t i = 0; i < n_meshes; ++i) d.entry_count[i] = plan.count[plan.mesh_seg[i]];
+  if (n_spheres) d.entry_count[n_meshes] = n_spheres;
   RR_CUDA(dev_malloc(&d_mesh_pos, (n_meshes + 1) * 4));
-  RR_CUDA(cudaMemcpyAsync(d_mesh_pos, mesh_pos.data(), (n_meshes + 1) * 4, cudaMemcpyHostToDevice, st));
   RR_CUDA(dev_malloc(&d_meshes_in, std::max<size_t>(n_meshes, 1) * sizeof(rr_mesh)));
   RR_CUDA(dev_malloc(&d_mesh_seg, std::max<size_t>(n_meshes, 1) * 4));
   RR_CUDA(dev_malloc(&d.meshes, (n_meshes + 1) * sizeof(DMesh)));
@@ -427,7 +551,10 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
     RR_CUDA(cudaMemcpyAsync(d_meshes_in, meshes, n_meshes * sizeof(rr_mesh), cudaMemcpyHostToDevice, st));
     RR_CUDA(cudaMemcpyAsync(d_mesh_seg, plan.mesh_seg.data(), n_meshes * 4, cudaMemcpyHostToDevice, st));
   }
-  RR_CUDA(prepare_meshes(d, n_meshes, n_spheres));
+  {
+    const int rc = prepare_meshes(d, n_meshes, n_spheres);
+    if (rc) return rc;
+  }
   RR_CUDA(cudaEventRecord(d.ev1, st));
   RR_CUDA(cudaStreamSynchronize(st));
   RR_CUDA(cudaEventElapsedTime(&d.build_ms, d.ev0, d.ev1));
@@ -437,10 +564,12 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
   {  // traversal stacks sized for THIS scene: a wide node pushes at most 3 children per level
     const uint32_t need = 3u * std::max(d.tb.wide_levels, d.sb.wide_levels) + 4u;
     if (need > d.stack_entries || !d.stack) {
-      cudaFree(d.stack);
-      d.stack = nullptr;
+      cudaFree(d.cold);  // one block: cold slot words of every warp, then the stacks
+      d.cold = nullptr; d.stack = nullptr;
       d.stack_entries = 0;
-      RR_CUDA(cudaMalloc(&d.stack, (size_t)d.stack_warps * render_stack_bytes_per_warp(need)));
+      const size_t cold_bytes = (size_t)d.stack_warps * render_cold_bytes_per_warp();
+      RR_CUDA(cudaMalloc(&d.cold, cold_bytes + (size_t)d.stack_warps * render_stack_bytes_per_warp(need)));
+      d.stack = reinterpret_cast<uint2*>(reinterpret_cast<char*>(d.cold) + cold_bytes);
       d.stack_entries = need;
     }
   }
@@ -480,6 +609,11 @@ static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam
   p.tri_nrm = d.tri_nrm;
   p.n_spheres = (int32_t)ctx->n_spheres;
   p.last_mesh = (int32_t)ctx->n_meshes - 1 + (ctx->n_spheres ? 1 : 0);
+  if (p.last_mesh >= 32 && !(ctx->tune.speculate & 4u)) {  // tuning bit 2: linear mesh scan (A/B)
+    p.tlas_blocks = d.tlas_blocks;
+    p.tlas = d.tlas;
+    p.tlas_levels = d.tlas_levels;
+  }
   p.sph_geom = d.sph_geom;
   p.sph_order = d.sb.order;
   p.tune = ctx->tune;
@@ -658,7 +792,7 @@ int rr_create(const int* cuda_ordinals, int n, rr_ctx** out) {
     if (e == cudaSuccess) e = cudaMalloc(&d.counters, sizeof(Counters));
     if (e == cudaSuccess) {
       d.stack_warps = (uint32_t)(prop.multiProcessorCount * render_max_warps_per_sm());
-      e = cudaMalloc(&d.cold, (size_t)d.stack_warps * render_cold_bytes_per_warp());
+      // the scratch block itself is sized at upload time (its stack part depends on the scene)
     }
     if (e != cudaSuccess) { rr_destroy(ctx); return cuda_fail(e, "rr_create"); }
     d.sm_count = prop.multiProcessorCount;
@@ -689,7 +823,7 @@ void rr_destroy(rr_ctx* ctx) {
       if (d.shared_queue) cudaIpcCloseMemHandle(d.shared_queue);
       if (d.shared_frame) cudaIpcCloseMemHandle(d.shared_frame);
     }
-    cudaFree(d.frame); cudaFree(d.radiance); cudaFree(d.accum); cudaFree(d.queue); cudaFree(d.counters); cudaFree(d.stack); cudaFree(d.cold);
+    cudaFree(d.frame); cudaFree(d.radiance); cudaFree(d.accum); cudaFree(d.queue); cudaFree(d.counters); cudaFree(d.cold);
     dev_trim(d.ordinal);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
@@ -827,11 +961,8 @@ int rr_update_meshes(rr_ctx* ctx, const rr_mesh* meshes, size_t n_meshes) {
   for (Device& d : ctx->dev) {
     RR_CUDA(cudaSetDevice(d.ordinal));
     if (n_meshes) RR_CUDA(cudaMemcpyAsync(d.meshes_in, meshes, n_meshes * sizeof(rr_mesh), cudaMemcpyHostToDevice, d.stream));
-    RR_CUDA(prepare_meshes(d, n_meshes, ctx->n_spheres));
-  }
-  for (Device& d : ctx->dev) {  // the caller's array may go away after the call (CL_MEM_COPY_HOST_PTR semantics)
-    RR_CUDA(cudaSetDevice(d.ordinal));
-    RR_CUDA(cudaStreamSynchronize(d.stream));
+    const int rc = prepare_meshes(d, n_meshes, ctx->n_spheres);  // synchronises: the caller's array may go away
+    if (rc) return rc;
   }
   return RR_OK;
 }

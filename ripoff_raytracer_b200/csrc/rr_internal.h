@@ -97,6 +97,8 @@ struct Tuning {
   uint32_t ctas_per_sm; // persistent CTAs per SM (0 = default)
 };
 
+#define RR_TLAS_MAX_LEVELS 14  // 4^13 chunks of 32 meshes: more than the 31-bit mesh index allows
+
 // Everything a render kernel needs (passed by value).
 struct RenderParams {
   // scene
@@ -109,6 +111,10 @@ struct RenderParams {
   // spheres (one segment, world space)
   int32_t n_spheres;
   int32_t last_mesh;         // n_meshes - 1, or n_meshes when the sphere pseudo-mesh exists
+  // more than 32 meshes: implicit tree of world boxes (lo, hi pairs) over the Morton-ordered meshes; nullptr otherwise
+  const float4* tlas_blocks; // one box per block of 8 meshes
+  const float4* tlas;        // level 0: one box per chunk of 32 meshes; level l: one box per 4^l chunks
+  const uint32_t* tlas_levels; // number of levels in `tlas`, then the index of the first box of every level
   const float4* sph_geom;    // (center, radius) per slot
   const uint32_t* sph_order; // slot -> sphere index
   Tuning tune;

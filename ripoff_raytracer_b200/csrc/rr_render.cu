@@ -313,18 +313,54 @@ __device__ __forceinline__ uint32_t ref_slot(int32_t r) { return (uint32_t)(-r) 
 
 // World-box tests of the meshes [base, base + 32): bit k set = the ray enters mesh base + k's box before `tmax`.
 // Every lane walks the whole chunk, so the loop is convergent.  Out of line: one copy serves shade, pixel and setup.
-__device__ __noinline__ uint32_t scan_meshes_fn(const DMesh* __restrict__ meshes, int32_t base, int32_t last_mesh, V3 winv,
-                                                V3 wnoi, float tmax) {
+// With a top level (`blocks` != nullptr, more than 32 meshes) the chunk is four blocks of eight meshes and a block
+// whose box the ray misses is skipped.
+__device__ __noinline__ uint32_t scan_meshes_fn(const DMesh* __restrict__ meshes, const float4* __restrict__ blocks, int32_t base,
+                                                int32_t last_mesh, V3 winv, V3 wnoi, float tmax, unsigned* tests) {
   uint32_t mask = 0;
   const int32_t end = min(base + 32, last_mesh + 1);
-  for (int32_t k = base; k < end; ++k) {
-    const DMesh* M = meshes + k;
-    const float4 wlo = __ldg(&M->wmin), whi = __ldg(&M->wmax);
+  for (int32_t k0 = base; k0 < end; k0 += 8) {
     float tn;
-    const bool hit = box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, tmax, tn);
-    if (hit && !(__float_as_uint(wlo.w) & RR_MF_SKIP)) mask |= 1u << (k - base);
+    if (blocks) {
+      const float4 blo = __ldg(blocks + 2 * (k0 >> 3)), bhi = __ldg(blocks + 2 * (k0 >> 3) + 1);
+      if (tests) ++*tests;
+      if (!box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, winv, wnoi, tmax, tn)) continue;
+    }
+    const int32_t e = min(k0 + 8, end);
+    if (tests) *tests += (unsigned)(e - k0);
+    for (int32_t k = k0; k < e; ++k) {
+      const DMesh* M = meshes + k;
+      const float4 wlo = __ldg(&M->wmin), whi = __ldg(&M->wmax);
+      const bool hit = box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, tmax, tn);
+      if (hit && !(__float_as_uint(wlo.w) & RR_MF_SKIP)) mask |= 1u << (k - base);
+    }
   }
   return mask;
+}
+
+// Top level over the meshes (replaces the linear mesh loop of src/Trace.cl:444-482 for scenes
+// with many instances).  The meshes are stored in Morton order of their world boxes and carry an implicit tree of
+// world boxes (rr_api.cu prepare_meshes): blocks of 8 meshes, chunks of 32, then every level groups 4 boxes of the
+// level below (128, 512, 2048 ... meshes).  The walk needs no stack and no per-ray state: from chunk `c` onwards, at
+// every level whose span starts at c (top level first) a box the ray misses skips its whole span; returns the first
+// chunk the ray enters before `tmax`, or a value > last_chunk.  Out of line: scenes with at most 32 meshes never come here.
+__device__ __noinline__ int32_t next_chunk_fn(const float4* __restrict__ tlas, const uint32_t* __restrict__ lv, int32_t c,
+                                              int32_t last_chunk, V3 winv, V3 wnoi, float tmax, unsigned* tests) {
+  const int levels = (int)__ldg(lv);  // lv: level count, then the first box of every level
+  while (c <= last_chunk) {
+    bool skipped = false;
+    float tn;
+    for (int l = levels - 1; l >= 0; --l) {  // level l: boxes over 4^l chunks (l = 0: the chunks themselves)
+      const int32_t span = 1 << (2 * l);
+      if (c & (span - 1)) continue;
+      const float4* b = tlas + 2 * ((size_t)__ldg(lv + 1 + l) + (size_t)(c >> (2 * l)));
+      const float4 lo = __ldg(b), hi = __ldg(b + 1);
+      if (tests) ++*tests;
+      if (!box_cull(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, winv, wnoi, tmax, tn)) { c += span; skipped = true; break; }
+    }
+    if (!skipped) break;
+  }
+  return c;
 }
 
 template <bool COUNT, bool PRIMARY>
@@ -413,8 +449,10 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   };
 
   auto scan_meshes = [&](int32_t base, const V3& winv, const V3& wnoi, float tmax) -> uint32_t {
-    if (COUNT) c_box += (unsigned)max(min(base + 32, p.last_mesh + 1) - base, 0);
-    return scan_meshes_fn(p.meshes, base, p.last_mesh, winv, wnoi, tmax);
+    unsigned tests = 0;
+    const uint32_t mask = scan_meshes_fn(p.meshes, p.tlas_blocks, base, p.last_mesh, winv, wnoi, tmax, COUNT ? &tests : nullptr);
+    if (COUNT) c_box += tests;
+    return mask;
   };
   // The mesh just traversed has a closest hit (local space): LocalToWorldHit and the keep-min of
   // src/Trace.cl:465-481.  Meshes are visited in our own order, so equal distances are resolved by the
@@ -454,14 +492,21 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   };
   // Enters the next candidate mesh (src/Trace.cl:444-463): world box against the closest hit so far,
   // WorldToLocalRay, root box.  Returns the slot's new key (traversal started, or K_H: no candidate left).
-  auto enter_next_mesh = [&](const V3& winv, const V3& wnoi) -> uint32_t {
-    for (;;) {
+  // One step of the search: false = look at the next candidate, true = done (`key` set).
+  auto enter_step = [&](const V3& winv, const V3& wnoi, uint32_t& key) -> bool {
+    {
       if (cand == 0) {
-        const int32_t base = (m & ~31) + 32;
-        if (base > p.last_mesh) return K_H;
+        int32_t base = (m & ~31) + 32;
+        if (base > p.last_mesh) { key = K_H; return true; }
+        if (p.tlas) {  // skip the chunks (and groups of chunks) the ray does not enter before the closest hit so far
+          unsigned tests = 0;
+          base = next_chunk_fn(p.tlas, p.tlas_levels, base >> 5, p.last_mesh >> 5, winv, wnoi, best_dst, COUNT ? &tests : nullptr) << 5;
+          if (COUNT) c_box += tests;
+          if (base > p.last_mesh) { key = K_H; return true; }
+        }
         m = base;
         cand = scan_meshes(base, winv, wnoi, best_dst);
-        continue;
+        return false;
       }
       const int k = __ffs((int)cand) - 1;
       cand &= cand - 1u;
@@ -471,7 +516,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       if (best_dst < INFINITY) {  // a hit exists: the box may now lie behind it
         const float4 wlo = __ldg(&M->wmin), whi = __ldg(&M->wmax);
         if (COUNT) c_box++;
-        if (!box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, best_dst, tn)) continue;
+        if (!box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, best_dst, tn)) return false;
       }
       mflags = __float_as_uint(__ldg(&M->wmin.w));
       if (mflags & RR_MF_SPHERES) {
@@ -497,7 +542,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       }
       const float4 blo = __ldg(&M->bmin), bhi = __ldg(&M->bmax);
       if (COUNT) c_box++;
-      if (!box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, linv, lnoi, INFINITY, tn)) continue;
+      if (!box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, linv, lnoi, INFINITY, tn)) return false;
       const uint32_t first = __float_as_uint(blo.w), count = __float_as_uint(bhi.w);
       lt = INFINITY; lprim = NO_PRIM; lback = false;
       sp = 0;
@@ -509,8 +554,14 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         pend_cnt = 0;
         cur = (int32_t)first;  // root node
       }
-      return trav_key();
+      key = trav_key();
+      return true;
     }
+  };
+  auto enter_next_mesh = [&](const V3& winv, const V3& wnoi) -> uint32_t {
+    uint32_t key = 0;
+    while (!enter_step(winv, wnoi, key)) {}
+    return key;
   };
   // what setup and shade write back after finish_mesh / enter_next_mesh
   auto store_ray_state = [&](uint32_t key) {

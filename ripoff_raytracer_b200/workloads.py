@@ -118,4 +118,41 @@ def c5_mesh10m(width=7680, height=4320, spp=1024, bounces=50, seed=5) -> Workloa
     return w
 
 
-WORKLOADS = {"c1": c1_default, "c2": c2_spheres, "c3": c3_mesh100k, "c4": c4_mixed1m, "c5": c5_mesh10m}
+def instances(width=1920, height=1080, spp=8, bounces=16, count=1024, subdiv=3, seed=9) -> Workload:
+    """many instances of ONE mesh (a displaced icosphere of 20*4^subdiv triangles, one triangle
+    range shared by every MeshInfo -- the reference's meshList allows that, src/readobj.hpp:75-81) with random pose,
+    scale and material, in a room of six walls and a ceiling light.  Exercises the top level over the mesh boxes."""
+    rng = np.random.default_rng(seed)
+    s = Scene()
+    v, n, f = scenes.displaced_icosphere(subdiv, radius=10.0, center=(0.0, 0.0, 0.0), seed=seed)
+    blob = s.add_triangles(scenes.mesh_triangles(v, n, f))
+    side = 40.0 * max(count, 8) ** (1.0 / 3.0) + 60.0  # room edge grows with the instance count (constant density)
+    h = 0.6 * side
+    s.add_quad((-side, 0, -side), (side, 0, -side), (side, 0, side), (-side, 0, side), (0, 1, 0), (0.6, 0.6, 0.6))
+    s.add_quad((-side, h, -side), (side, h, -side), (side, h, side), (-side, h, side), (0, -1, 0), (0.9, 0.9, 0.9))
+    s.add_quad((-side, 0, -side), (side, 0, -side), (side, h, -side), (-side, h, -side), (0, 0, 1), (0.2, 0.7, 0.2))
+    s.add_quad((-side, 0, -side), (-side, 0, side), (-side, h, side), (-side, h, -side), (1, 0, 0), (0.2, 0.2, 0.9))
+    s.add_quad((side, 0, -side), (side, 0, side), (side, h, side), (side, h, -side), (-1, 0, 0), (0.9, 0.2, 0.2))
+    s.add_quad((-0.5 * side, h - 1, -0.5 * side), (0.5 * side, h - 1, -0.5 * side), (0.5 * side, h - 1, 0.5 * side),
+               (-0.5 * side, h - 1, 0.5 * side), (0, -1, 0), (1, 1, 1))
+    lm = s.mesh(s.n_meshes - 1)["material"]
+    lm["emissionColor"][0, :3] = 1.0
+    lm["emissionStrength"] = 6.0
+    m = np.zeros(count, _abi.MESH)
+    m["pos"][:, :3] = rng.uniform((-0.9 * side, 12.0, -0.9 * side), (0.9 * side, 0.9 * h, 0.9 * side), size=(count, 3))
+    m["pitch"], m["yaw"], m["roll"] = rng.uniform(-3.1, 3.1, size=(3, count)).astype(np.float32)
+    m["scale"] = rng.choice(np.array([0.5, 0.8, 1.0, 1.3, 2.0], np.float32), size=count)
+    mm = m["material"]
+    mm["type"] = rng.choice(np.array([_abi.MATERIAL_SOLID] * 6 + [_abi.MATERIAL_GLASSY, _abi.MATERIAL_ONESIDED]), size=count)
+    mm["ior"] = 1.45
+    mm["color"][:, :3] = rng.uniform(0.25, 0.95, size=(count, 3))
+    mm["specularProbability"] = rng.uniform(0.0, 0.6, size=count)
+    mm["reflectiveness"] = rng.uniform(0.0, 0.9, size=count)
+    for k in range(count):
+        s.add_mesh(m[k:k + 1], blob)
+    cam = _camera(width, height, (0.0, 0.55 * h, 0.95 * side), pitch=0.12, yaw=3.14159, fov=80.0)
+    return Workload(f"instances_{count}", f"{count} instances of a {len(f)}-triangle mesh + 6 wall quads", s, cam, width, height,
+                    spp, bounces)
+
+
+WORKLOADS = {"instances": instances, "c1": c1_default, "c2": c2_spheres, "c3": c3_mesh100k, "c4": c4_mixed1m, "c5": c5_mesh10m}

@@ -621,3 +621,45 @@ def test_command_line_driver_video_and_progressive(knight_obj, tmp_path):
     # a non-empty output directory is refused, as in the reference (src/main.cpp:44-49)
     p = subprocess.run([str(exe)], input=answers[2:], text=True, capture_output=True, cwd=tmp_path, timeout=120, env=env)
     assert p.returncode == 1 and "not empty" in p.stdout
+
+
+# --------------------------------------------- top level over the meshes --
+@pytest.mark.parametrize("count", [40, 1500])
+def test_many_instances_top_level_is_bit_exact(count):
+    """More than 32 meshes: Morton-ordered 32-mesh chunks with chunk / group boxes (rr_api.cu prepare_meshes,
+    rr_render.cu next_chunk_fn) instead of the reference's linear mesh loop (src/Trace.cl:444-482).  The boxes only
+    cull: primary hits, ray counts and every float of the radiance equal the oracle's in-order loop over ALL meshes,
+    and equal the linear scan of the same kernel (tuning bit 2)."""
+    from ripoff_raytracer_b200 import workloads
+
+    W, H = (160, 90) if count > 1000 else (200, 120)
+    wl = workloads.instances(width=W, height=H, spp=3, bounces=10, count=count, subdiv=1)
+    t, m, r, sp = wl.scene.arrays()
+    assert len(m) == count + 6
+    ren = rr.Renderer()
+    ren.upload(wl.scene)
+    o = Oracle(t, m, r, sp)
+    mesh, prim, dst = ren.primary_hits(wl.cam, W, H)
+    om, op, od = o.primary(wl.cam, W, H, threads=16)
+    assert np.array_equal(mesh, om) and np.array_equal(prim, op) and np.array_equal(bits(dst), bits(od))
+    assert len(np.unique(mesh)) > 20
+    got, grad, st = ren.render(wl.cam, W, H, wl.spp, wl.bounces, radiance=True, count_tests=True)
+    want, wrad, ost = o.render(wl.cam, W, H, wl.spp, wl.bounces, radiance=True, threads=16)
+    assert st["rays"] == ost["rays"]
+    assert np.array_equal(bits(grad), bits(wrad))
+    assert_images_equal(got, want, f"{count} instances")
+    ren.set_tuning([4, 4, 4, 4, 4, 20, 1 | 4])  # same kernel, linear scan over every chunk
+    lin, lrad, lst = ren.render(wl.cam, W, H, wl.spp, wl.bounces, radiance=True, count_tests=True)
+    assert np.array_equal(bits(lrad), bits(grad)) and lst["rays"] == st["rays"]
+    if count > 1000:
+        assert st["box_tests"] < 0.5 * lst["box_tests"]  # the top level removes most of the mesh-box tests
+    # re-posing re-sorts the chunks and rebuilds their boxes
+    m2 = m.copy()
+    m2["pos"][6:, 0] = -m2["pos"][6:, 0]
+    m2["yaw"][6:] += 0.5
+    ren.set_tuning(None)
+    ren.update_meshes(m2)
+    got2, grad2, _ = ren.render(wl.cam, W, H, 2, 6, radiance=True)
+    ren.close()
+    wrad2 = Oracle(t, m2, r, sp).render(wl.cam, W, H, 2, 6, radiance=True, threads=16)[1]
+    assert np.array_equal(bits(grad2), bits(wrad2))
