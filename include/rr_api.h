@@ -261,6 +261,8 @@ int rr_accum_add_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32
                        rr_stats* stats_out);
 /* Frames added since the last reset. */
 int rr_accum_frame_count(rr_ctx* ctx, uint32_t* frames_out);
+/* Device time (CUDA events) of the accumulation kernel of the last rr_accum_add_frame: 32 B of HBM traffic per pixel. */
+int rr_accum_last_ms(rr_ctx* ctx, float* ms_out);
 /* reset + n_frames x add_frame with frame_index = first_frame_index + k (the reference counts from 1);
  * rgba_out is the final average.  stats_out sums the frames (render_ms: total kernel time). */
 int rr_render_progressive(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,

@@ -131,6 +131,7 @@ SYMBOLS = {
     "rr_accum_reset": (C.c_int, [_vp, _u32, _u32]),
     "rr_accum_add_frame": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, _vp, C.POINTER(Stats)]),
     "rr_accum_frame_count": (C.c_int, [_vp, C.POINTER(_u32)]),
+    "rr_accum_last_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rr_render_progressive": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, _u32, _vp, C.POINTER(Stats)]),
     "rr_primary_hits": (C.c_int, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "rr_bvh_size": (C.c_int, [_vp, C.c_int, C.POINTER(_u64)]),

@@ -263,6 +263,11 @@ class Renderer:
               "rr_accum_add_frame")
         return avg, st.as_dict()
 
+    def accum_last_ms(self) -> float:
+        ms = C.c_float()
+        check(lib().rr_accum_last_ms(self.h, C.byref(ms)), "rr_accum_last_ms")
+        return float(ms.value)
+
     def accum_frame_count(self) -> int:
         n = C.c_uint32()
         check(lib().rr_accum_frame_count(self.h, C.byref(n)), "rr_accum_frame_count")

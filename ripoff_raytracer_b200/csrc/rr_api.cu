@@ -130,6 +130,7 @@ struct Device {
   uint32_t* accum = nullptr;
   size_t accum_capacity = 0;  // pixels allocated
   uint32_t accum_w = 0, accum_h = 0, accum_frames = 0;
+  float accum_ms = 0.0f;      // device time of the last k_accum_add
   // frame
   uint8_t* frame = nullptr;
   size_t frame_bytes = 0;
@@ -985,6 +986,12 @@ int rr_accum_reset(rr_ctx* ctx, uint32_t width, uint32_t height) {
   return RR_OK;
 }
 
+int rr_accum_last_ms(rr_ctx* ctx, float* ms_out) {
+  if (!ctx || !ms_out) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
+  *ms_out = ctx->dev[0].accum_ms;
+  return RR_OK;
+}
+
 int rr_accum_frame_count(rr_ctx* ctx, uint32_t* frames_out) {
   if (!ctx || !frames_out) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
   *frames_out = ctx->dev[0].accum_frames;
@@ -1006,11 +1013,14 @@ int rr_accum_add_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32
   d.accum_frames++;
   uint32_t* planes = d.accum;
   const int grid = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)d.sm_count * 8);
+  RR_CUDA(cudaEventRecord(d.ev0, d.stream));
   k_accum_add<<<grid, 256, 0, d.stream>>>(reinterpret_cast<uint32_t*>(d.frame), planes, planes + d.accum_capacity,
                                           planes + 2 * d.accum_capacity, n, d.accum_frames);
   RR_CUDA(cudaGetLastError());
+  RR_CUDA(cudaEventRecord(d.ev1, d.stream));
   if (rgba_avg_out) RR_CUDA(cudaMemcpyAsync(rgba_avg_out, d.frame, n * 4, cudaMemcpyDeviceToHost, d.stream));
   RR_CUDA(cudaStreamSynchronize(d.stream));
+  RR_CUDA(cudaEventElapsedTime(&d.accum_ms, d.ev0, d.ev1));
   return RR_OK;
 }
 

@@ -6,11 +6,14 @@
 // Pure C++; no CUDA in this file.
 #include <algorithm>
 #include <cfloat>
+#include <charconv>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rr_api.h"
@@ -52,24 +55,243 @@ rr_mesh default_mesh() {
   return m;
 }
 
-// One face corner: "v/vt/vn" or "v//vn".  Returns chars consumed, 0 on failure.
-bool parse_corner(const char*& p, long& v, long& n) {
-  char* end;
-  while (*p == ' ' || *p == '\t') ++p;
-  v = strtol(p, &end, 10);
-  if (end == p || *end != '/') return false;
-  p = end + 1;
-  if (*p == '/') {
-    ++p;
-  } else {
-    strtol(p, &end, 10);  // texture index, unused
-    if (end == p || *end != '/') return false;
-    p = end + 1;
+// ---- OBJ text -> indexed arrays, in parallel ---------------------------------------------------------------
+// The file is read once and cut into one chunk per thread at line boundaries.  Pass 1 (parallel) parses the `v` /
+// `vn` lines of a chunk into chunk-local arrays and notes where its `f` lines are, together with how many `v` / `vn`
+// lines precede each of them inside the chunk; a prefix sum over the chunks then gives every face line the number of
+// vertices / normals defined BEFORE it in the file -- what 1-based, relative (negative) and out-of-range indices are
+// resolved against, exactly as a sequential reader does.  Pass 2 (parallel) parses the faces against the merged
+// vertex array.  Two dialects:
+//   strict     the reference loader's (src/readobj.hpp:289-344): `v `, `vn `, `f a/b/c` or `f a//c`, first three
+//              corners only, normals mandatory, no negative indices;
+//   permissive polygons (fan), `f a` / `f a/b` (face normals generated), negative indices, tabs.
+struct ObjFace { size_t offset; uint32_t lv, ln; };  // line start in the file; `v` / `vn` lines before it in its chunk
+struct ObjChunk {
+  size_t begin = 0, end = 0;
+  std::vector<float> pos, nrm, gen;  // gen: face normals generated for faces without `vn`
+  std::vector<ObjFace> faces;
+  std::vector<uint32_t> corners;     // v0 v1 v2 n0 n1 n2; generated normals flagged with bit 30 (chunk-local index)
+  size_t base_v = 0, base_n = 0, base_gen = 0, base_tri = 0;
+};
+
+inline bool is_blank(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
+
+// "%f" of sscanf on [p, end): optional blanks, then a float; correctly rounded like strtof.  Anything from_chars does
+// not take (a leading '+', hex floats, out-of-range values) goes through strtof on a bounded copy.
+bool parse_float(const char*& p, const char* end, float& out) {
+  while (p < end && is_blank(*p)) ++p;
+  if (p >= end) return false;
+  const char* d = (*p == '-') ? p + 1 : p;
+  const bool hex = end - d >= 2 && d[0] == '0' && (d[1] == 'x' || d[1] == 'X');  // "%f" reads hex floats, from_chars would stop at the x
+  if (!hex) {
+    const auto r = std::from_chars(p, end, out);
+    if (r.ec == std::errc()) { p = r.ptr; return true; }
   }
-  n = strtol(p, &end, 10);
-  if (end == p) return false;
-  p = end;
+  char buf[96];
+  const size_t n = std::min<size_t>((size_t)(end - p), sizeof(buf) - 1);
+  memcpy(buf, p, n);
+  buf[n] = 0;
+  char* e;
+  out = strtof(buf, &e);
+  if (e == buf) return false;
+  p += e - buf;
   return true;
+}
+bool parse_float3(const char* p, const char* end, float* xyz) {
+  return parse_float(p, end, xyz[0]) && parse_float(p, end, xyz[1]) && parse_float(p, end, xyz[2]);
+}
+// strtol(p, &end, 10) on [p, end): blanks, optional sign, digits.  false when no digit was read (p unchanged).
+bool parse_long(const char*& p, const char* end, long& out) {
+  const char* q = p;
+  while (q < end && is_blank(*q)) ++q;
+  bool neg = false;
+  if (q < end && (*q == '-' || *q == '+')) { neg = *q == '-'; ++q; }
+  if (q >= end || *q < '0' || *q > '9') return false;
+  long v = 0;
+  while (q < end && *q >= '0' && *q <= '9') { v = v * 10 + (*q - '0'); if (v > (1L << 40)) v = 1L << 40; ++q; }
+  out = neg ? -v : v;
+  p = q;
+  return true;
+}
+
+void obj_pass1(const char* data, ObjChunk& c, bool strict) {
+  const char* p = data + c.begin;
+  const char* const stop = data + c.end;
+  uint32_t lv = 0, ln = 0;
+  while (p < stop) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(stop - p));
+    const char* e = nl ? nl : stop;
+    if (e - p >= 2) {
+      const bool sep1 = p[1] == ' ' || (!strict && p[1] == '\t');
+      if (p[0] == 'v' && sep1) {
+        float f[3];
+        if (parse_float3(p + 1, e, f)) { c.pos.insert(c.pos.end(), f, f + 3); ++lv; }
+      } else if (p[0] == 'v' && p[1] == 'n' && e - p >= 3 && (p[2] == ' ' || (!strict && p[2] == '\t'))) {
+        float f[3];
+        if (parse_float3(p + 2, e, f)) { c.nrm.insert(c.nrm.end(), f, f + 3); ++ln; }
+      } else if (p[0] == 'f' && sep1) {
+        c.faces.push_back({(size_t)(p - data), lv, ln});
+      }
+    }
+    p = nl ? nl + 1 : stop;
+  }
+}
+
+void obj_pass2(const char* data, size_t size, ObjChunk& c, bool strict, const std::vector<float>& positions) {
+  std::vector<long> fv, fn;
+  for (const ObjFace& face : c.faces) {
+    const char* p = data + face.offset;
+    const char* nl = (const char*)memchr(p, '\n', size - face.offset);
+    const char* e = nl ? nl : data + size;
+    const long nv = (long)(c.base_v + face.lv), nn = (long)(c.base_n + face.ln);  // defined before this line
+    if (strict) {
+      // three corners `v/vt/vn` or `v//vn` (src/readobj.hpp:307-312); a 4th corner is ignored
+      p += 2;
+      long v[3], n[3];
+      bool ok = true;
+      for (int k = 0; k < 3 && ok; ++k) {
+        long vt;
+        ok = parse_long(p, e, v[k]) && p < e && *p == '/';
+        if (!ok) break;
+        ++p;
+        if (p < e && *p == '/') ++p;
+        else { ok = parse_long(p, e, vt) && p < e && *p == '/'; if (!ok) break; ++p; }
+        ok = parse_long(p, e, n[k]);
+      }
+      if (!ok) continue;
+      for (int k = 0; k < 3; ++k) {
+        v[k] -= 1; n[k] -= 1;
+        if (v[k] < 0 || v[k] >= nv || n[k] < 0 || n[k] >= nn) ok = false;
+      }
+      if (!ok) continue;
+      for (int k = 0; k < 3; ++k) c.corners.push_back((uint32_t)v[k]);
+      for (int k = 0; k < 3; ++k) c.corners.push_back((uint32_t)n[k]);
+      continue;
+    }
+    fv.clear(); fn.clear();
+    ++p;
+    bool ok = true;
+    for (;;) {  // corners: v, v/vt, v//vn, v/vt/vn
+      while (p < e && is_blank(*p)) ++p;
+      if (p >= e) break;
+      long v, n = 0, vt;
+      if (!parse_long(p, e, v)) { ok = false; break; }
+      if (p < e && *p == '/') {
+        ++p;
+        if (!(p < e && *p == '/')) parse_long(p, e, vt);  // texture index, unused
+        if (p < e && *p == '/') {
+          ++p;
+          if (!parse_long(p, e, n)) { ok = false; break; }
+        }
+      }
+      v = v < 0 ? nv + v : v - 1;  // negative indices count from the end
+      n = n < 0 ? nn + n : n - 1;  // n == 0 (absent) becomes -1
+      if (v < 0 || v >= nv || n >= nn) { ok = false; break; }
+      fv.push_back(v);
+      fn.push_back(n);
+    }
+    if (!ok || fv.size() < 3) continue;
+    for (size_t k = 1; k + 1 < fv.size(); ++k) {  // fan triangulation; a triangle is a fan of one
+      const long v3[3] = {fv[0], fv[k], fv[k + 1]};
+      long n3[3] = {fn[0], fn[k], fn[k + 1]};
+      if (n3[0] < 0 || n3[1] < 0 || n3[2] < 0) {  // no normals: one face normal for the triangle
+        const float* A = &positions[3 * v3[0]];
+        const float* B = &positions[3 * v3[1]];
+        const float* C = &positions[3 * v3[2]];
+        const float e1[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, e2[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+        float nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
+        const float len = std::sqrt(nx * nx + ny * ny + nz * nz);
+        if (len > 0.0f) { nx /= len; ny /= len; nz /= len; } else { nx = 0.0f; ny = 1.0f; nz = 0.0f; }
+        const long idx = (long)(c.gen.size() / 3);
+        c.gen.push_back(nx); c.gen.push_back(ny); c.gen.push_back(nz);
+        n3[0] = n3[1] = n3[2] = idx | 0x40000000L;
+      }
+      for (int q = 0; q < 3; ++q) c.corners.push_back((uint32_t)v3[q]);
+      for (int q = 0; q < 3; ++q) c.corners.push_back((uint32_t)n3[q]);
+    }
+  }
+}
+
+template <class F>
+void parallel_chunks(size_t n, F&& body) {
+  std::vector<std::thread> pool;
+  for (size_t k = 1; k < n; ++k) pool.emplace_back([&body, k] { body(k); });
+  body(0);
+  for (auto& t : pool) t.join();
+}
+
+int obj_parse(const char* path, bool strict, rr_obj* o) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return RR_ERR_IO;
+  std::string text;
+  {
+    fseek(f, 0, SEEK_END);
+    const long size = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (size < 0) { fclose(f); return RR_ERR_IO; }
+    text.resize((size_t)size);
+    const size_t got = size ? fread(&text[0], 1, (size_t)size, f) : 0;
+    fclose(f);
+    if (got != (size_t)size) return RR_ERR_IO;
+  }
+  const char* data = text.data();
+  const size_t size = text.size();
+  const bool dbg = getenv("RR_OBJ_DEBUG") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tl = now();
+  auto lap = [&](const char* what) { if (dbg) { const double t = now(); fprintf(stderr, "[obj] %s %.1f ms\n", what, (t - tl) * 1e3); tl = t; } };
+  size_t threads = std::max(1u, std::thread::hardware_concurrency());
+  if (const char* e = getenv("RR_OBJ_THREADS")) threads = (size_t)std::max(1, atoi(e));
+  size_t min_chunk = 1u << 20;  // at least 1 MiB of text per thread
+  if (const char* e = getenv("RR_OBJ_MIN_CHUNK")) min_chunk = (size_t)std::max(1, atoi(e));
+  threads = std::min(threads, std::max<size_t>(1, size / min_chunk));
+  std::vector<ObjChunk> chunks(threads);
+  size_t at = 0;
+  for (size_t k = 0; k < threads; ++k) {  // cut at line boundaries
+    chunks[k].begin = at;
+    size_t want = k + 1 == threads ? size : std::max(at, size / threads * (k + 1));
+    if (want < size) {
+      const char* nl = (const char*)memchr(data + want, '\n', size - want);
+      want = nl ? (size_t)(nl - data) + 1 : size;
+    }
+    chunks[k].end = at = want;
+  }
+  lap("read+cut");
+  parallel_chunks(threads, [&](size_t k) { obj_pass1(data, chunks[k], strict); });
+  lap("pass1");
+  size_t nv = 0, nn = 0;
+  for (ObjChunk& c : chunks) { c.base_v = nv; c.base_n = nn; nv += c.pos.size() / 3; nn += c.nrm.size() / 3; }
+  if (nv >= 0x3fffffffull || nn >= 0x3fffffffull) return RR_ERR_UNSUPPORTED;
+  o->positions.resize(3 * nv);
+  o->normals.resize(3 * nn);
+  parallel_chunks(threads, [&](size_t k) {
+    ObjChunk& c = chunks[k];
+    if (!c.pos.empty()) memcpy(&o->positions[3 * c.base_v], c.pos.data(), c.pos.size() * sizeof(float));
+    if (!c.nrm.empty()) memcpy(&o->normals[3 * c.base_n], c.nrm.data(), c.nrm.size() * sizeof(float));
+    std::vector<float>().swap(c.pos);
+    std::vector<float>().swap(c.nrm);
+  });
+  lap("merge v/vn");
+  parallel_chunks(threads, [&](size_t k) { obj_pass2(data, size, chunks[k], strict, o->positions); });
+  lap("pass2");
+  size_t ngen = 0, ntri = 0;
+  for (ObjChunk& c : chunks) { c.base_gen = ngen; c.base_tri = ntri; ngen += c.gen.size() / 3; ntri += c.corners.size() / 6; }
+  if (ntri >= 0x7fffffffull || nn + ngen >= 0x3fffffffull) return RR_ERR_UNSUPPORTED;
+  // generated face normals go behind the file's normals, so that they never shift the file's own normal indices
+  o->normals.resize(3 * (nn + ngen));
+  o->corners.resize(6 * ntri);
+  parallel_chunks(threads, [&](size_t k) {
+    ObjChunk& c = chunks[k];
+    if (!c.gen.empty()) memcpy(&o->normals[3 * (nn + c.base_gen)], c.gen.data(), c.gen.size() * sizeof(float));
+    uint32_t* dst = o->corners.data() + 6 * c.base_tri;
+    const uint32_t gen0 = (uint32_t)(nn + c.base_gen);
+    for (size_t i = 0; i < c.corners.size(); ++i) {
+      const uint32_t v = c.corners[i];
+      dst[i] = (i % 6 >= 3 && (v & 0x40000000u)) ? gen0 + (v & 0x3fffffffu) : v;
+    }
+  });
+  lap("merge faces");
+  return RR_OK;
 }
 
 }  // namespace
@@ -80,76 +302,9 @@ extern "C" {
 int rr_obj_load(const char* path, rr_obj** out) {
   if (!path || !out) return RR_ERR_INVALID_ARGUMENT;
   *out = nullptr;
-  std::ifstream file(path);
-  if (!file) return RR_ERR_IO;
   rr_obj* o = new rr_obj();
-  std::string line;
-  std::vector<long> fv, fn;
-  std::vector<float> generated;  // face normals of faces without `vn`: appended behind the file's normals at the end,
-                                 // so that they never shift the file's own (possibly relative) normal indices
-  while (std::getline(file, line)) {
-    if (line.size() < 2) continue;
-    const char* c = line.c_str();
-    if (c[0] == 'v' && (c[1] == ' ' || c[1] == '\t')) {
-      float x, y, z;
-      if (sscanf(c + 1, "%f %f %f", &x, &y, &z) == 3) { o->positions.push_back(x); o->positions.push_back(y); o->positions.push_back(z); }
-    } else if (c[0] == 'v' && c[1] == 'n' && (c[2] == ' ' || c[2] == '\t')) {
-      float x, y, z;
-      if (sscanf(c + 2, "%f %f %f", &x, &y, &z) == 3) { o->normals.push_back(x); o->normals.push_back(y); o->normals.push_back(z); }
-    } else if (c[0] == 'f' && (c[1] == ' ' || c[1] == '\t')) {
-      fv.clear(); fn.clear();
-      const char* p = c + 1;
-      bool ok = true;
-      for (;;) {  // corners: v, v/vt, v//vn, v/vt/vn
-        while (*p == ' ' || *p == '\t' || *p == '\r') ++p;
-        if (!*p) break;
-        char* end;
-        long v = strtol(p, &end, 10), n = 0;
-        if (end == p) { ok = false; break; }
-        p = end;
-        if (*p == '/') {
-          ++p;
-          if (*p != '/') { strtol(p, &end, 10); p = end; }  // texture index, unused
-          if (*p == '/') {
-            ++p;
-            n = strtol(p, &end, 10);
-            if (end == p) { ok = false; break; }
-            p = end;
-          }
-        }
-        const long nv = (long)(o->positions.size() / 3), nn = (long)(o->normals.size() / 3);
-        v = v < 0 ? nv + v : v - 1;  // negative indices count from the end
-        n = n < 0 ? nn + n : n - 1;  // n == 0 (absent) becomes -1
-        if (v < 0 || v >= nv || n >= nn) { ok = false; break; }
-        fv.push_back(v);
-        fn.push_back(n);
-      }
-      if (!ok || fv.size() < 3) continue;
-      for (size_t k = 1; k + 1 < fv.size(); ++k) {  // fan triangulation; a triangle is a fan of one
-        const long v3[3] = {fv[0], fv[k], fv[k + 1]};
-        long n3[3] = {fn[0], fn[k], fn[k + 1]};
-        if (n3[0] < 0 || n3[1] < 0 || n3[2] < 0) {  // no normals: one face normal for the triangle
-          const float* A = &o->positions[3 * v3[0]];
-          const float* B = &o->positions[3 * v3[1]];
-          const float* C = &o->positions[3 * v3[2]];
-          const float e1[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, e2[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
-          float nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
-          const float len = std::sqrt(nx * nx + ny * ny + nz * nz);
-          if (len > 0.0f) { nx /= len; ny /= len; nz /= len; } else { nx = 0.0f; ny = 1.0f; nz = 0.0f; }
-          const long idx = (long)(generated.size() / 3);
-          generated.push_back(nx); generated.push_back(ny); generated.push_back(nz);
-          n3[0] = n3[1] = n3[2] = idx | 0x40000000L;
-        }
-        for (int q = 0; q < 3; ++q) o->corners.push_back((uint32_t)v3[q]);
-        for (int q = 0; q < 3; ++q) o->corners.push_back((uint32_t)n3[q]);
-      }
-    }
-  }
-  const uint32_t n_file = (uint32_t)(o->normals.size() / 3);
-  for (size_t i = 0; i < o->corners.size(); i += 6)
-    for (int q = 3; q < 6; ++q)
-      if (o->corners[i + q] & 0x40000000u) o->corners[i + q] = n_file + (o->corners[i + q] & 0x3fffffffu);
-  o->normals.insert(o->normals.end(), generated.begin(), generated.end());
+  const int rc = obj_parse(path, false, o);
+  if (rc) { delete o; return rc; }
   *out = o;
   return RR_OK;
 }
@@ -184,40 +339,26 @@ int rr_scene_add_triangles(rr_scene* s, const rr_triangle* tris, size_t n, rr_me
 // triCount before validating, src/readobj.hpp:305,346).
 int rr_scene_load_obj(rr_scene* s, const char* path, rr_mesh* mesh_out, rr_mesh_range* range_out) {
   if (!s || !path) return RR_ERR_INVALID_ARGUMENT;
-  std::ifstream file(path);
-  if (!file) return RR_ERR_IO;
-  std::vector<rr_float3> verts, normals;
-  const size_t first = s->tris.size();
-  std::string line;
-  while (std::getline(file, line)) {
-    if (line.size() < 2) continue;
-    const char* c = line.c_str();
-    if (c[0] == 'v' && c[1] == ' ') {
-      float x, y, z;
-      if (sscanf(c, "v %f %f %f", &x, &y, &z) == 3) verts.push_back(f3(x, y, z));
-    } else if (c[0] == 'v' && c[1] == 'n' && c[2] == ' ') {
-      float x, y, z;
-      if (sscanf(c, "vn %f %f %f", &x, &y, &z) == 3) normals.push_back(f3(x, y, z));
-    } else if (c[0] == 'f' && c[1] == ' ') {
-      const char* p = c + 2;
-      long v[3], n[3];
-      bool ok = true;
-      for (int k = 0; k < 3 && ok; ++k) ok = parse_corner(p, v[k], n[k]);
-      if (!ok) continue;
-      for (int k = 0; k < 3; ++k) {
-        v[k] -= 1;
-        n[k] -= 1;
-        if (v[k] < 0 || (size_t)v[k] >= verts.size() || n[k] < 0 || (size_t)n[k] >= normals.size()) ok = false;
+  rr_obj o;
+  const int rc = obj_parse(path, true, &o);
+  if (rc) return rc;
+  const size_t first = s->tris.size(), n = o.corners.size() / 6;
+  s->tris.resize(first + n);
+  // the 96-byte Triangle records of src/readobj.hpp:313-343, expanded in parallel
+  const size_t threads = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>(1, n >> 16));
+  parallel_chunks(threads, [&](size_t k) {
+    for (size_t i = n * k / threads; i < n * (k + 1) / threads; ++i) {
+      const uint32_t* c = &o.corners[6 * i];
+      rr_triangle& t = s->tris[first + i];
+      rr_float3* dst[6] = {&t.posA, &t.posB, &t.posC, &t.normalA, &t.normalB, &t.normalC};
+      for (int q = 0; q < 6; ++q) {
+        const float* src = q < 3 ? &o.positions[3 * (size_t)c[q]] : &o.normals[3 * (size_t)c[q]];
+        *dst[q] = f3(src[0], src[1], src[2]);
       }
-      if (!ok) continue;
-      rr_triangle t;
-      t.posA = verts[v[0]]; t.posB = verts[v[1]]; t.posC = verts[v[2]];
-      t.normalA = normals[n[0]]; t.normalB = normals[n[1]]; t.normalC = normals[n[2]];
-      s->tris.push_back(t);
     }
-  }
+  });
   if (mesh_out) *mesh_out = default_mesh();  // src/readobj.hpp:369-375
-  if (range_out) { range_out->firstTriangle = first; range_out->numTriangles = s->tris.size() - first; }
+  if (range_out) { range_out->firstTriangle = first; range_out->numTriangles = n; }
   return RR_OK;
 }
 

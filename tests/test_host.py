@@ -172,3 +172,46 @@ def test_video_frame_setup_matches_reference(golden_video):
 def test_video_frame_path():
     assert rr.video_frame_path("img", 1) == "img/output_1.bmp"      # src/main.cpp:701, render.sh:12
     assert rr.video_frame_path("/tmp/x", 120) == "/tmp/x/output_120.bmp"
+
+
+def test_parallel_obj_parse_is_independent_of_the_chunking(tmp_path, monkeypatch):
+    """The loader cuts the text into one chunk per thread; indices (1-based, relative, out of range) are resolved
+    against the `v` / `vn` lines BEFORE a face in the whole file, whatever chunk they are in."""
+    rng = np.random.default_rng(3)
+    lines = ["# interleaved blocks of vertices, normals and faces"]
+    nv = nn = 0
+    for block in range(40):
+        k = int(rng.integers(3, 9))
+        for _ in range(k):
+            x, y, z = rng.normal(size=3) * 10
+            lines.append(f"v {x:.7g} {y:.7g} {z:.7g}" + ("\r" if block % 7 == 0 else ""))
+        nv += k
+        for _ in range(int(rng.integers(0, 3))):
+            lines.append("vn 0 %.6f %.6f" % tuple(rng.normal(size=2)))
+            nn += 1
+        for _ in range(int(rng.integers(2, 7))):
+            c = rng.integers(1, nv + 1, size=int(rng.integers(3, 6)))
+            kind = int(rng.integers(0, 5))
+            if kind == 0 or nn == 0:
+                lines.append("f " + " ".join(str(i) for i in c))                         # no normals -> generated
+            elif kind == 1:
+                lines.append("f " + " ".join(f"{i}//{int(rng.integers(1, nn + 1))}" for i in c))
+            elif kind == 2:
+                lines.append("f " + " ".join(f"{i}/1/{int(rng.integers(1, nn + 1))}" for i in c))
+            elif kind == 3:
+                lines.append("f " + " ".join(f"{-int(rng.integers(1, nv + 1))}//-1" for _ in c))  # relative
+            else:
+                lines.append(f"f {nv + 5}//1 1//1 2//1")                                  # forward reference: skipped
+    p = tmp_path / "mixed.obj"
+    p.write_text("\n".join(lines))  # no trailing newline
+    monkeypatch.setenv("RR_OBJ_MIN_CHUNK", "64")
+    results = []
+    for threads in (1, 2, 7, 16):
+        monkeypatch.setenv("RR_OBJ_THREADS", str(threads))
+        pos, nrm, cor = rr.load_obj_indexed(p)
+        s = rr.Scene()
+        s.load_obj(p)
+        results.append((pos.tobytes(), nrm.tobytes(), cor.tobytes(), s.arrays()[0].tobytes()))
+    assert len(cor) > 100 and all(r == results[0] for r in results[1:])
+    # the forward references were skipped and every index is in range
+    assert cor[:, :3].max() < len(pos) and cor[:, 3:].max() < len(nrm)
