@@ -190,6 +190,8 @@ def lib() -> C.CDLL:
             )
         l = C.CDLL(str(path))
         for name, (res, args) in SYMBOLS.items():
+            if "RR_B200_LIB" in os.environ and not hasattr(l, name):
+                continue  # an older build loaded for an A/B run (tools/ab.py)
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args

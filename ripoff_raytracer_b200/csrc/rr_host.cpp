@@ -12,15 +12,45 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <iterator>
 #include <string>
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "../../include/rr_api.h"
 
+// Output array whose pages are first touched by the threads that fill it (std::vector::resize would zero -- and
+// page-fault -- every byte on the calling thread, which costs more than the parse itself at 16 threads).
+template <class T>
+struct RawArray {
+  T* p = nullptr;
+  size_t n = 0;
+  RawArray() = default;
+  RawArray(const RawArray&) = delete;
+  RawArray& operator=(const RawArray&) = delete;
+  ~RawArray() { free(p); }
+  bool resize_keep(size_t count) {  // contents up to min(n, count) are kept
+    if (count == 0) { free(p); p = nullptr; n = 0; return true; }  // realloc(p, 0) is not portable
+    T* q = static_cast<T*>(realloc(p, count * sizeof(T)));
+    if (!q) return false;
+    p = q; n = count;
+    return true;
+  }
+  size_t size() const { return n; }
+  T* data() { return p; }
+  const T* data() const { return p; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+};
+
 struct rr_obj {
-  std::vector<float> positions, normals;  // x,y,z triples
-  std::vector<uint32_t> corners;          // v0 v1 v2 n0 n1 n2 per triangle, 0-based
+  RawArray<float> positions, normals;  // x,y,z triples
+  RawArray<uint32_t> corners;          // v0 v1 v2 n0 n1 n2 per triangle, 0-based
 };
 
 struct rr_scene {
@@ -137,7 +167,7 @@ void obj_pass1(const char* data, ObjChunk& c, bool strict) {
   }
 }
 
-void obj_pass2(const char* data, size_t size, ObjChunk& c, bool strict, const std::vector<float>& positions) {
+void obj_pass2(const char* data, size_t size, ObjChunk& c, bool strict, const float* positions) {
   std::vector<long> fv, fn;
   for (const ObjFace& face : c.faces) {
     const char* p = data + face.offset;
@@ -220,22 +250,42 @@ void parallel_chunks(size_t n, F&& body) {
   for (auto& t : pool) t.join();
 }
 
-int obj_parse(const char* path, bool strict, rr_obj* o) {
-  FILE* f = fopen(path, "rb");
-  if (!f) return RR_ERR_IO;
-  std::string text;
-  {
-    fseek(f, 0, SEEK_END);
-    const long size = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    if (size < 0) { fclose(f); return RR_ERR_IO; }
-    text.resize((size_t)size);
-    const size_t got = size ? fread(&text[0], 1, (size_t)size, f) : 0;
-    fclose(f);
-    if (got != (size_t)size) return RR_ERR_IO;
+// The file's bytes, mapped (no copy of the page cache); an empty or unmappable file falls back to read().
+struct FileText {
+  const char* data = nullptr;
+  size_t size = 0;
+  void* map = nullptr;
+  std::string fallback;
+  ~FileText() { if (map) munmap(map, size); }
+  bool open(const char* path) {
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { ::close(fd); return read_all(path); }
+    size = (size_t)st.st_size;
+    if (size == 0) { ::close(fd); data = ""; return true; }
+    void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    ::close(fd);
+    if (m == MAP_FAILED) return read_all(path);
+    map = m;
+    data = static_cast<const char*>(m);
+    return true;
   }
-  const char* data = text.data();
-  const size_t size = text.size();
+  bool read_all(const char* path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    fallback.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    data = fallback.data();
+    size = fallback.size();
+    return true;
+  }
+};
+
+int obj_parse(const char* path, bool strict, rr_obj* o) {
+  FileText text;
+  if (!text.open(path)) return RR_ERR_IO;
+  const char* data = text.data;
+  const size_t size = text.size;
   const bool dbg = getenv("RR_OBJ_DEBUG") != nullptr;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double tl = now();
@@ -262,8 +312,7 @@ int obj_parse(const char* path, bool strict, rr_obj* o) {
   size_t nv = 0, nn = 0;
   for (ObjChunk& c : chunks) { c.base_v = nv; c.base_n = nn; nv += c.pos.size() / 3; nn += c.nrm.size() / 3; }
   if (nv >= 0x3fffffffull || nn >= 0x3fffffffull) return RR_ERR_UNSUPPORTED;
-  o->positions.resize(3 * nv);
-  o->normals.resize(3 * nn);
+  if (!o->positions.resize_keep(3 * nv) || !o->normals.resize_keep(3 * nn)) return RR_ERR_OUT_OF_MEMORY;
   parallel_chunks(threads, [&](size_t k) {
     ObjChunk& c = chunks[k];
     if (!c.pos.empty()) memcpy(&o->positions[3 * c.base_v], c.pos.data(), c.pos.size() * sizeof(float));
@@ -272,14 +321,13 @@ int obj_parse(const char* path, bool strict, rr_obj* o) {
     std::vector<float>().swap(c.nrm);
   });
   lap("merge v/vn");
-  parallel_chunks(threads, [&](size_t k) { obj_pass2(data, size, chunks[k], strict, o->positions); });
+  parallel_chunks(threads, [&](size_t k) { obj_pass2(data, size, chunks[k], strict, o->positions.data()); });
   lap("pass2");
   size_t ngen = 0, ntri = 0;
   for (ObjChunk& c : chunks) { c.base_gen = ngen; c.base_tri = ntri; ngen += c.gen.size() / 3; ntri += c.corners.size() / 6; }
   if (ntri >= 0x7fffffffull || nn + ngen >= 0x3fffffffull) return RR_ERR_UNSUPPORTED;
   // generated face normals go behind the file's normals, so that they never shift the file's own normal indices
-  o->normals.resize(3 * (nn + ngen));
-  o->corners.resize(6 * ntri);
+  if (!o->normals.resize_keep(3 * (nn + ngen)) || !o->corners.resize_keep(6 * ntri)) return RR_ERR_OUT_OF_MEMORY;
   parallel_chunks(threads, [&](size_t k) {
     ObjChunk& c = chunks[k];
     if (!c.gen.empty()) memcpy(&o->normals[3 * (nn + c.base_gen)], c.gen.data(), c.gen.size() * sizeof(float));

@@ -51,6 +51,16 @@ with tempfile.TemporaryDirectory() as td:
     scenes.write_obj(obj, v, n, f)
     for th in [int(x) for x in a.threads.split(",")]:
         subprocess.run([sys.executable, __file__, "--child", str(th), "--obj", str(obj)], check=True)
+    # the same call from C (no Python-side copies of the result), with the loader's own phase timing on stderr
+    exe = Path(td) / "bench_obj_c"
+    lib = ROOT / "ripoff_raytracer_b200" / "csrc"
+    subprocess.run(["g++", "-O2", "-o", str(exe), str(ROOT / "tools" / "bench_obj_c.cpp"), f"-L{lib}", "-lrr_b200", f"-Wl,-rpath,{lib}"], check=True)
+    for th in [int(x) for x in a.threads.split(",")]:
+        out = subprocess.run([str(exe), str(obj)], env=dict(os.environ, RR_OBJ_THREADS=str(th), RR_OBJ_DEBUG="1"), capture_output=True, text=True)
+        best = min(float(l.split()[-2]) for l in out.stdout.splitlines() if l.startswith("rc=0"))
+        laps = [l for l in out.stderr.splitlines() if l.startswith("[obj]")][-5:]
+        print(json.dumps({"threads": th, "c_api_rr_obj_load_ms": round(best * 1e3, 1), "mb_s": round(os.path.getsize(obj) / 1e6 / best, 1),
+                          "phases_last_run": "; ".join(l[6:] for l in laps)}), flush=True)
     # file -> device: parse + indexed upload + LBVH build
     try:
         ren = rr.Renderer()
