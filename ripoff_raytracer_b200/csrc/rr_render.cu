@@ -619,9 +619,9 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   for (;;) {
     // ---- vote: one REDUX over the byte-packed keys counts the ready slots of every phase ----
     __syncwarp();  // the slots written by the previous phase are visible to every lane
-    uint32_t ksum = 0;
+    uint32_t ksum = 0, keys[ROUNDS];
 #pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) ksum += PW(W_KEY, lane + 32 * r);
+    for (int r = 0; r < ROUNDS; ++r) { keys[r] = PW(W_KEY, lane + 32 * r); ksum += keys[r]; }
     const uint32_t counts = __reduce_add_sync(full, ksum);
     const bool more_pixels = !(queue_empty && tile_next >= tile_pixels);
     const uint32_t nP = more_pixels ? n_need : 0u;
@@ -635,12 +635,23 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     if (nH * wH > best) { best = nH * wH; phase = PH_SHADE; }
     if (min(nP, 32u) * wP > best) { best = min(nP, 32u) * wP; phase = PH_PIXEL; }
     round++;
+    // ---- gather: up to 32 slots that are ready for the chosen phase go to the lanes (ONE copy of this code for all
+    // phases: the phases a warp cycles through have to share a 32 KB instruction cache) ----
+    int n_sel;
+    {
+      bool ready[ROUNDS];
+      if (phase == PH_PIXEL) {
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) ready[r] = (int32_t)PW(W_PIX, lane + 32 * r) == PIX_NEED;
+      } else {
+        const uint32_t km = phase == PH_TRAV ? K_T : phase == PH_LEAF ? K_L : phase == PH_SETUP ? K_S : K_H;
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) ready[r] = (keys[r] & km) != 0u;
+      }
+      n_sel = select(ready);
+    }
     if (phase == PH_TRAV) {
       // ================= node steps =================
-      bool ready[ROUNDS];
-#pragma unroll
-      for (int r = 0; r < ROUNDS; ++r) ready[r] = (PW(W_KEY, lane + 32 * r) & K_T) != 0u;
-      select(ready);
       const bool mine = s >= 0;
       if (mine) {
         cur = (int32_t)PW(W_CUR, s);
@@ -757,10 +768,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       }
     } else if (phase == PH_LEAF) {
       // ================= leaf tests =================
-      bool ready[ROUNDS];
-#pragma unroll
-      for (int r = 0; r < ROUNDS; ++r) ready[r] = (PW(W_KEY, lane + 32 * r) & K_L) != 0u;
-      const int n_sel = select(ready);
       if (COUNT) { ph_runs[PH_LEAF]++; ph_lanes[PH_LEAF] += n_sel; }
       if (s >= 0) {
         cur = (int32_t)PW(W_CUR, s);
@@ -864,10 +871,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       }
     } else if (phase == PH_SETUP) {
       // ================= finish the current mesh, enter the next candidate (src/Trace.cl:444-482) =================
-      bool ready[ROUNDS];
-#pragma unroll
-      for (int r = 0; r < ROUNDS; ++r) ready[r] = (PW(W_KEY, lane + 32 * r) & K_S) != 0u;
-      const int n_sel = select(ready);
       if (COUNT) { ph_runs[PH_SETUP]++; ph_lanes[PH_SETUP] += n_sel; }
       if (s >= 0) {
         origin = PLD3(W_OX, s);
@@ -882,10 +885,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       }
     } else if (phase == PH_SHADE) {
       // ================= one bounce of Trace() (src/Trace.cl:497-591) and the sample loop (:639-642) =================
-      bool ready[ROUNDS];
-#pragma unroll
-      for (int r = 0; r < ROUNDS; ++r) ready[r] = (PW(W_KEY, lane + 32 * r) & K_H) != 0u;
-      const int n_sel = select(ready);
       if (COUNT) { ph_runs[PH_SHADE]++; ph_lanes[PH_SHADE] += n_sel; }
       bool pixel_done = false;
       if (s >= 0) {
@@ -956,10 +955,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       n_need += __popc(__ballot_sync(full, pixel_done));
     } else {
       // ================= hand a pixel to every slot that needs one =================
-      bool ready[ROUNDS];
-#pragma unroll
-      for (int r = 0; r < ROUNDS; ++r) ready[r] = (int32_t)PW(W_PIX, lane + 32 * r) == PIX_NEED;
-      const int n_sel = select(ready);
       if (COUNT) { ph_runs[PH_PIXEL]++; ph_lanes[PH_PIXEL] += n_sel; }
       bool need = s >= 0;
       while (__any_sync(full, need)) {
