@@ -417,7 +417,7 @@ def device_step_e2e(r, rr, wl, mode, rank, world, barrier, frame_host):
         st = r.render_shared(wl.cam, W, H, wl.spp, wl.bounces)
         barrier()
         if rank == 0:
-            frame_host[...] = r.read_frame(W, H)
+            r.read_frame(W, H, out=frame_host)  # D2H straight into the pinned host frame
         return st
     import torch
     import torch.distributed as dist

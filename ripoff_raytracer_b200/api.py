@@ -314,8 +314,8 @@ class Renderer:
               "rr_render_device")
         return st.as_dict()
 
-    def read_frame(self, width, height):
-        rgba = np.zeros((height, width, 4), np.uint8)
+    def read_frame(self, width, height, out=None):
+        rgba = out if out is not None else np.empty((height, width, 4), np.uint8)
         check(lib().rr_read_frame(self.h, ptr(rgba), rgba.nbytes), "rr_read_frame")
         return rgba
 

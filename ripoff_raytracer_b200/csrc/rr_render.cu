@@ -399,7 +399,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
                  wT = p.tune.weight[PH_TRAV], wL = p.tune.weight[PH_LEAF];
   const uint32_t trav_keep = p.tune.trav_keep;
   const bool speculate = (p.tune.speculate & 1u) != 0;
-  const bool prefetch = (p.tune.speculate & 2u) != 0;  // parked slots prefetch the line they will need next
 
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
@@ -699,7 +698,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         const bool step = mine && cur >= REF_POP && (speculate || pend_cnt == 0);
         if (COUNT) { ph_runs[PH_TRAV]++; ph_lanes[PH_TRAV] += __popc(__ballot_sync(full, step)); }
         if (step) {
-          if (cur == REF_POP) resolve(REF_POP);
+          int32_t next = REF_POP;  // cur == REF_POP (the slot comes from the leaf phase): only take the next stack entry
           if (cur >= 0) {
             // one 128-byte node: the boxes of up to four children (SoA) and their references.  The quads holding the
             // planes the ray ENTERS / LEAVES through are picked by the sign of its direction (qn*/qf*, set up
@@ -742,15 +741,16 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             // misses sort last, so the children to push are a suffix of the hits: farthest first, the nearest of
             // them ends up as the (register-resident) top; the previous top is spilled once
             if (hits >= 2 && sp + hits - 1 <= (int)p.stack_entries) {
-              if (sp > 0) stk[(sp - 1) * POOL] = top;
-              if (hits == 4) { stk[sp * POOL] = make_uint2((uint32_t)r3, k3 & ~3u); sp++; }
-              if (hits >= 3) { stk[sp * POOL] = make_uint2((uint32_t)r2, k2 & ~3u); sp++; }
+              uint2* const w = stk + sp * POOL;  // one address; the stores below use constant offsets from it
+              if (sp > 0) w[-POOL] = top;
+              if (hits >= 3) w[0] = hits == 4 ? make_uint2((uint32_t)r3, k3 & ~3u) : make_uint2((uint32_t)r2, k2 & ~3u);
+              if (hits == 4) w[POOL] = make_uint2((uint32_t)r2, k2 & ~3u);
               top = make_uint2((uint32_t)r1, k1 & ~3u);
-              sp++;
+              sp += hits - 1;
             }
-            const int32_t next = hits > 0 ? r0 : REF_POP;
-            resolve(next);
+            if (hits > 0) next = r0;
           }
+          resolve(next);  // the one copy of the pop / postpone logic
         }
         active = __popc(__ballot_sync(full, mine && cur >= REF_POP && (speculate || pend_cnt == 0)));
       } while (active >= trav_keep);
@@ -761,10 +761,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         PW(W_TOPN, s) = top.x;
         PW(W_TOPD, s) = top.y;
         PW(W_KEY, s) = trav_key();
-        if (prefetch) {  // the slot now waits for a later round: start fetching what that round will read
-          if (cur >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.nodes + RR_NODE_QUADS * (size_t)cur));
-          if (pend_cnt) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.tri_geom + 3 * (size_t)pend_slot));
-        }
       }
     } else if (phase == PH_LEAF) {
       // ================= leaf tests =================
