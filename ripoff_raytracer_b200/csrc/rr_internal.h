@@ -18,8 +18,11 @@
 #ifndef RR_POOL
 #define RR_POOL 96        // path slots per warp of the render kernel (rr_render.cu)
 #endif
+#ifndef RR_NT
+#define RR_NT 128         // threads per CTA of the render kernel
+#endif
 #ifndef RR_MIN_CTAS
-#define RR_MIN_CTAS 5     // resident 128-thread CTAs per SM the render kernel is compiled for
+#define RR_MIN_CTAS 5     // resident CTAs per SM the render kernel is compiled for
 #endif
 #define RR_POOL_WORDS 28  // 32-bit words of one slot in shared memory
 #define RR_COLD_WORDS 25  // ... and in the per-warp global scratch

@@ -275,7 +275,7 @@ __device__ __forceinline__ bool pop_tile(const RenderParams& p, uint32_t& tile) 
   return t < (unsigned long long)p.tiles_x * p.tiles_y;
 }
 
-constexpr int NT = 128;          // threads per CTA (warps are independent: no block-level barrier in the loop)
+constexpr int NT = RR_NT;        // threads per CTA (warps are independent: no block-level barrier in the loop)
 constexpr int WARPS = NT / 32;
 constexpr int POOL = RR_POOL;    // path slots per warp (rr_internal.h)
 constexpr int ROUNDS = POOL / 32;
