@@ -386,6 +386,79 @@ __global__ void k_tlas_boxes(const DMesh* __restrict__ meshes, const float4* __r
   out[2 * w + 1] = empty ? make_float4(q, q, q, 0.0f) : make_float4(hi[0], hi[1], hi[2], 0.0f);
 }
 
+// Tight world boxes of ROTATED meshes.  The world box k_prepare_meshes derives from the eight corners of the local root
+// box is exact for an axis-aligned mesh but up to sqrt(3) too wide per axis for a rotated one, and every ray that
+// enters it pays a mesh entry (transform, root test, finish).  Here the vertices themselves go through
+// LocalToWorldHit (src/Trace.cl:139-147): grid.x = mesh, grid.y = 1024-triangle chunk of its range, block-reduced
+// min / max into ordered-int atomics.  The hierarchy and the result arithmetic are untouched: the box only culls.
+__device__ __forceinline__ int wb_f2ord(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float wb_ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void k_world_box_init(int* __restrict__ box_ord, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 6 * n) box_ord[i] = (i % 6) < 3 ? wb_f2ord(INFINITY) : wb_f2ord(-INFINITY);
+}
+
+__global__ void __launch_bounds__(256) k_world_box_accum(const rr_triangle* __restrict__ tris, const rr_mesh* __restrict__ meshes,
+                                                         const uint32_t* __restrict__ mesh_seg, const uint32_t* __restrict__ seg_first,
+                                                         const uint32_t* __restrict__ seg_count, const uint32_t* __restrict__ mesh_pos,
+                                                         const DMesh* __restrict__ dm, int* __restrict__ box_ord) {
+  const uint32_t i = blockIdx.x;
+  const DMesh& d = dm[mesh_pos[i]];
+  const float4 r0 = d.r0, r1 = d.r1, r2 = d.r2;
+  if (__float_as_uint(d.wmin.w) & RR_MF_SKIP) return;
+  if (r0.x == 1.0f && r0.y == 0.0f && r0.z == 0.0f && r1.x == 0.0f && r1.y == 1.0f && r1.z == 0.0f && r2.x == 0.0f && r2.y == 0.0f &&
+      r2.z == 1.0f)
+    return;  // axis-aligned: the corner box is exact
+  const float scale = meshes[i].scale;
+  const float px = d.ri0.w, py = d.ri1.w, pz = d.ri2.w;
+  const uint32_t first = seg_first[mesh_seg[i]], count = seg_count[mesh_seg[i]];
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (uint32_t base = blockIdx.y * 1024u; base < count; base += gridDim.y * 1024u) {
+    for (uint32_t t = base + threadIdx.x; t < min(base + 1024u, count); t += 256u) {
+      const rr_triangle& tr = tris[first + t];
+      const rr_float3* v[3] = {&tr.posA, &tr.posB, &tr.posC};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float lx = v[k]->s[0] * scale, ly = v[k]->s[1] * scale, lz = v[k]->s[2] * scale;
+        const float w[3] = {r0.x * lx + r0.y * ly + r0.z * lz + px, r1.x * lx + r1.y * ly + r1.z * lz + py,
+                            r2.x * lx + r2.y * ly + r2.z * lz + pz};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], w[a]); hi[a] = fmaxf(hi[a], w[a]); }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], off));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], off));
+    }
+  if ((threadIdx.x & 31) == 0 && lo[0] <= hi[0]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      atomicMin(box_ord + 6 * i + a, wb_f2ord(lo[a]));
+      atomicMax(box_ord + 6 * i + 3 + a, wb_f2ord(hi[a]));
+    }
+  }
+}
+
+// The tight box (with the same slack as the corner box) replaces the corner box where it is smaller.
+__global__ void k_world_box_apply(const int* __restrict__ box_ord, const uint32_t* __restrict__ mesh_pos, int n_meshes, DMesh* __restrict__ dm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_meshes) return;
+  float lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) { lo[a] = wb_ord2f(box_ord[6 * i + a]); hi[a] = wb_ord2f(box_ord[6 * i + 3 + a]); }
+  if (!(lo[0] <= hi[0])) return;  // not a rotated mesh (or no triangles)
+  float mabs = 0.0f;
+  for (int a = 0; a < 3; ++a) mabs = fmaxf(mabs, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
+  const float e = mabs * 1.220703125e-4f + 1.0e-6f;  // 2^-13 relative, as in k_prepare_meshes
+  DMesh& d = dm[mesh_pos[i]];
+  d.wmin.x = fmaxf(d.wmin.x, lo[0] - e); d.wmin.y = fmaxf(d.wmin.y, lo[1] - e); d.wmin.z = fmaxf(d.wmin.z, lo[2] - e);
+  d.wmax.x = fminf(d.wmax.x, hi[0] + e); d.wmax.y = fminf(d.wmax.y, hi[1] + e); d.wmax.z = fminf(d.wmax.z, hi[2] + e);
+}
+
 static inline uint64_t spread21(uint64_t v) {  // 21 bits -> every third bit
   v &= 0x1fffffull;
   v = (v | v << 32) & 0x1f00000000ffffull;
@@ -412,6 +485,26 @@ static int prepare_meshes(Device& d, size_t n_meshes, size_t n_spheres) {
                                                       d.mesh_pos, d.meshes, d.materials);
     return cudaGetLastError();
   };
+  // tight world boxes of the rotated meshes: accumulated once (they do not depend on the visiting order), applied
+  // after every k_prepare_meshes launch
+  struct Tmp { int* p = nullptr; ~Tmp() { dev_free(p); } } box_ord;
+  bool have_tight = false;
+  auto tighten = [&]() -> cudaError_t {
+    if (n_meshes == 0 || getenv("RR_NO_TIGHT_BOXES")) return cudaSuccess;
+    if (!have_tight) {
+      cudaError_t e = dev_malloc(&box_ord.p, n_meshes * 6 * sizeof(int));
+      if (e != cudaSuccess) return e;
+      k_world_box_init<<<(unsigned)((6 * n_meshes + 255) / 256), 256, 0, st>>>(box_ord.p, (int)n_meshes);
+      uint64_t max_count = 0;
+      for (size_t k = 0; k < n_meshes; ++k) max_count = std::max(max_count, d.entry_count[k]);
+      const dim3 grid((unsigned)n_meshes, (unsigned)std::min<uint64_t>(std::max<uint64_t>((max_count + 1023) / 1024, 1), 65535));
+      k_world_box_accum<<<grid, 256, 0, st>>>(d.tris, d.meshes_in, d.mesh_seg, d.tb.seg_first, d.tb.seg_count, d.mesh_pos, d.meshes,
+                                              box_ord.p);
+      have_tight = true;
+    }
+    k_world_box_apply<<<(unsigned)((n_meshes + 127) / 128), 128, 0, st>>>(box_ord.p, d.mesh_pos, (int)n_meshes, d.meshes);
+    return cudaGetLastError();
+  };
   std::vector<uint32_t> pos(n_meshes + 1, 0);
   std::vector<uint32_t> order(n_entries);  // order[k] = entry at position k
   for (size_t k = 0; k < n_entries; ++k) order[k] = (uint32_t)k;
@@ -423,6 +516,7 @@ static int prepare_meshes(Device& d, size_t n_meshes, size_t n_spheres) {
     for (size_t k = 0; k <= n_meshes; ++k) pos[k] = (uint32_t)k;
     RR_CUDA(cudaMemcpyAsync(d.mesh_pos, pos.data(), (n_meshes + 1) * 4, cudaMemcpyHostToDevice, st));
     RR_CUDA(launch());
+    RR_CUDA(tighten());
     std::vector<float> wb(n_entries * 8);
     RR_CUDA(cudaMemcpy2DAsync(wb.data(), 32, reinterpret_cast<const char*>(d.meshes) + offsetof(DMesh, wmin), sizeof(DMesh), 32,
                               n_entries, cudaMemcpyDeviceToHost, st));
@@ -458,6 +552,7 @@ static int prepare_meshes(Device& d, size_t n_meshes, size_t n_spheres) {
   for (size_t k = 0; k < n_entries; ++k) pos[order[k]] = (uint32_t)k;
   RR_CUDA(cudaMemcpyAsync(d.mesh_pos, pos.data(), (n_meshes + 1) * 4, cudaMemcpyHostToDevice, st));
   RR_CUDA(launch());
+  RR_CUDA(tighten());
   uint32_t level_info[1 + RR_TLAS_MAX_LEVELS] = {0};
   if (n_entries > 32) {
     // blocks of 8 meshes, chunks of 4 blocks, then 4 boxes per box until one box is left
