@@ -138,6 +138,8 @@ __device__ __forceinline__ bool box_cull(float lox, float loy, float loz, float 
 }
 
 constexpr int32_t NO_PRIM = 0x7fffffff;
+// flags kept with the mesh number in the slot word W_M, so that the leaf phase needs no look-up in the mesh table
+constexpr uint32_t WM_BACK = 1u << 31, WM_SPHERES = 1u << 30, WM_CULL = 1u << 29, WM_MESH = WM_CULL - 1u;
 
 struct SceneHit {  // HitInfo of src/Trace.cl:67-74 as the shade phase sees it
   bool did;
@@ -290,7 +292,7 @@ enum {
   W_KEY = 0, W_PIX,
   W_OX, W_OY, W_OZ, W_DX, W_DY, W_DZ,           // world ray
   W_BDST, W_BMAT,                               // closest hit so far: distance, material | back << 31 (mesh = min(material, n_meshes))
-  W_CAND, W_M,                                  // candidate meshes of the chunk; (current mesh + 1, 0 = new ray) | lback << 31
+  W_CAND, W_M,                                  // candidate meshes of the chunk; (current mesh + 1, 0 = new ray) | WM_* flags
   W_LOX, W_LOY, W_LOZ, W_LDX, W_LDY, W_LDZ, W_LIX, W_LIY, W_LIZ,  // mesh-local ray and its reciprocal direction
   W_LT, W_LPRIM,                                // closest hit inside the current mesh (its normal: C_LNX)
   W_CUR, W_SPC, W_PSLOT,                        // traversal: node ref, stack pointer | postponed count << 8, postponed slot
@@ -568,7 +570,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     PW(W_BMAT, s) = (uint32_t)best_mat | (best_back ? 0x80000000u : 0u);
     if (PRIMARY) CW(C_BPRIM, s) = (uint32_t)best_prim;
     PW(W_CAND, s) = cand;
-    PW(W_M, s) = (uint32_t)(m + 1) | (lback ? 0x80000000u : 0u);
+    PW(W_M, s) = (uint32_t)(m + 1) | (lback ? WM_BACK : 0u) | ((mflags & RR_MF_SPHERES) ? WM_SPHERES : 0u) |
+                 ((mflags & RR_MF_CULL) ? WM_CULL : 0u);
     PST3(W_LOX, s, lo);
     PST3(W_LDX, s, ld);
     PST3(W_LIX, s, linv);
@@ -595,8 +598,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   };
   auto load_mesh_word = [&]() {  // W_M -> m (-1: new ray), lback
     const uint32_t mw = PW(W_M, s);
-    m = (int)(mw & 0x7fffffffu) - 1;
-    lback = (mw >> 31) != 0u;
+    m = (int)(mw & WM_MESH) - 1;
+    lback = (mw & WM_BACK) != 0u;
   };
   // shade / pixel start the next segment: reset the closest hit (src/Trace.cl:437-444), collect the candidate
   // meshes (convergent here: every lane of these phases does it) and hand the slot to the setup phase
@@ -775,14 +778,13 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         lprim = (int32_t)PW(W_LPRIM, s);
         lo = PLD3(W_LOX, s);
         ld = PLD3(W_LDX, s);
-        load_mesh_word();
-        mflags = __float_as_uint(__ldg(&p.meshes[m].wmin.w));
+        const uint32_t mw = PW(W_M, s);
         const uint32_t slot = pend_slot;
         pend_slot++;
         pend_cnt--;
         bool accepted = false;
         V3 n3 = mk(0, 0, 0);
-        if (mflags & RR_MF_SPHERES) {
+        if (mw & WM_SPHERES) {
           // EXTENSION (the reference kernel has no sphere primitive): semantics of oracle/rr_oracle.c ray_sphere
           if (COUNT) c_sph++;
           const float4 cr = __ldg(p.sph_geom + slot);
@@ -836,7 +838,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
                   bool back = false;
                   bool ok = true;
                   if (dot(ld, n3) > RR_EPSILON) {
-                    if (mflags & RR_MF_CULL) ok = false;
+                    if (mw & WM_CULL) ok = false;
                     back = true;
                     n3 = -n3;
                   }
@@ -852,7 +854,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         if (accepted) {
           PSF(W_LT, s, lt);
           PW(W_LPRIM, s) = (uint32_t)lprim;
-          PW(W_M, s) = (uint32_t)(m + 1) | (lback ? 0x80000000u : 0u);
+          PW(W_M, s) = (mw & ~WM_BACK) | (lback ? WM_BACK : 0u);
           CST3(C_LNX, s, n3);
         }
         if (pend_cnt == 0 && ref_is_leaf(cur)) {  // the leaf this slot was waiting on becomes the postponed one
