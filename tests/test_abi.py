@@ -61,3 +61,22 @@ def test_default_camera_matches_settings():
     cam = rr.default_camera(512, 512)
     assert cam["position"][0, :3].tolist() == [0.0, 150.0, 250.0]
     assert cam["yaw"][0] == np.float32(3.14) and cam["fov"][0] == 90.0 and cam["aspectRatio"][0] == 1.0
+
+
+def test_new_entry_points_reject_bad_arguments_without_a_device():
+    """Argument checks of the progressive / video entry points run before any CUDA call."""
+    l = _abi.lib()
+    cam = np.zeros(1, _abi.CAMERA)
+    img = np.zeros((2, 2, 4), np.uint8)
+    assert l.rr_update_meshes(None, None, 0) == 1
+    assert l.rr_accum_reset(None, 4, 4) == 1
+    assert l.rr_accum_add_frame(None, _abi.ptr(cam), 2, 2, 1, 1, 1, 0, _abi.ptr(img), None) == 1
+    assert l.rr_accum_frame_count(None, None) == 1
+    assert l.rr_accum_last_ms(None, None) == 1
+    assert l.rr_render_progressive(None, _abi.ptr(cam), 2, 2, 1, 1, 1, 1, 0, None, None) == 1       # null output image
+    assert l.rr_render_progressive(None, _abi.ptr(cam), 2, 2, 1, 1, 1, 0, 0, _abi.ptr(img), None) == 1  # zero frames
+    assert l.rr_render_progressive(None, _abi.ptr(cam), 2, 2, 1, 1, 1, 2, 0, _abi.ptr(img), None) == 1  # null context
+    assert l.rr_video_frame_setup(None, 0, 0, 1) == 1
+    buf = C.create_string_buffer(8)
+    assert l.rr_video_frame_path(b"a_long_directory_name", 1, buf, len(buf)) == 1                    # does not fit
+    assert b"argument" in l.rr_error_string(1)
