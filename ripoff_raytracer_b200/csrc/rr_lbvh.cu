@@ -178,7 +178,8 @@ __global__ void k_morton(const float* __restrict__ box, uint64_t n_total, const 
 }
 
 // ---- stable LSD radix sort, 8 bits per pass ---------------------------------
-// One pass = histogram per tile, exclusive scan over (digit, tile), stable scatter.
+// One pass = histogram per tile, exclusive scan over (digit, tile) -- per digit value across the tiles, then across the
+// digit values inside the scatter kernel --, stable scatter.
 // A tile is processed by 8 warps; warp w owns the w-th contiguous eighth of the
 // tile, walks it 32 consecutive items at a time and ranks equal digits with
 // __match_any_sync, so equal keys keep their input order.
@@ -209,52 +210,58 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint64_t* __re
   hist[(uint64_t)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of `m` counters in place, one block of 1024 threads
-__global__ void __launch_bounds__(1024) k_scan(uint32_t* data, uint64_t m) {
+// Exclusive scan of the per-tile counters of ONE digit value per block (256 blocks run side by side), in place; the
+// total of every digit value goes to totals[digit].  The scan ACROSS the 256 digit values is done by the scatter
+// kernel itself (256 numbers, one block-wide scan), so a radix pass is three launches and none of them is serial.
+__global__ void __launch_bounds__(1024) k_scan_bins(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t* __restrict__ totals) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
+  uint32_t* data = hist + (uint64_t)blockIdx.x * n_tiles;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (uint64_t base = 0; base < m; base += 1024) {
-    uint64_t i = base + threadIdx.x;
-    uint32_t v = i < m ? data[i] : 0u;
+  for (uint32_t base = 0; base < n_tiles; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < n_tiles ? data[i] : 0u;
     uint32_t x = v;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
       if (lane >= (unsigned)off) x += y;
     }
     if (lane == 31) warp_sums[wid] = x;
     __syncthreads();
     if (wid == 0) {
-      uint32_t w = warp_sums[lane];
+      const uint32_t w = warp_sums[lane];
       uint32_t ws = w;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, ws, off);
+        const uint32_t y = __shfl_up_sync(0xffffffffu, ws, off);
         if (lane >= (unsigned)off) ws += y;
       }
       warp_sums[lane] = ws - w;  // exclusive
     }
     __syncthreads();
-    uint32_t carry = carry_s;
-    uint32_t excl = carry + warp_sums[wid] + (x - v);
-    if (i < m) data[i] = excl;
+    const uint32_t carry = carry_s;
+    if (i < n_tiles) data[i] = carry + warp_sums[wid] + (x - v);
     __syncthreads();
     if (threadIdx.x == 1023) carry_s = carry + warp_sums[wid] + x;
     __syncthreads();
   }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry_s;
 }
 
 template <bool SEG_DIGIT>
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                                const uint32_t* __restrict__ seg_id, uint64_t n, int shift,
-                                                               const uint32_t* __restrict__ offsets, uint32_t n_tiles) {
+                                                               const uint32_t* __restrict__ offsets, uint32_t n_tiles,
+                                                               const uint32_t* __restrict__ totals) {
   constexpr int WARPS = SORT_THREADS / 32;
   constexpr int ROUNDS = SORT_TILE / WARPS / 32;
+  static_assert(SORT_THREADS == 256, "one thread per digit value");
   __shared__ uint32_t wh[WARPS][256];
+  __shared__ uint32_t digit_base_warp[WARPS];
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int k = threadIdx.x; k < WARPS * 256; k += SORT_THREADS) (&wh[0][0])[k] = 0;
   __syncthreads();
@@ -275,10 +282,26 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint64_t* _
       dig[r] = 0x100u + lane;  // matches nobody
     }
   }
-  __syncthreads();
+  // first output position of every digit value: exclusive scan of the 256 totals (thread = digit value)
+  uint32_t digit_base;
+  {
+    const uint32_t tot = totals[threadIdx.x];
+    uint32_t x = tot;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= (unsigned)off) x += y;
+    }
+    if (lane == 31) digit_base_warp[w] = x;
+    __syncthreads();  // (also orders the per-warp histograms above)
+    uint32_t before = 0;
+#pragma unroll
+    for (int ww = 0; ww < WARPS; ++ww) before += ww < (int)w ? digit_base_warp[ww] : 0u;
+    digit_base = before + x - tot;
+  }
   {
     const unsigned bin = threadIdx.x;
-    uint32_t running = offsets[(uint64_t)bin * n_tiles + blockIdx.x];
+    uint32_t running = digit_base + offsets[(uint64_t)bin * n_tiles + blockIdx.x];
 #pragma unroll
     for (int ww = 0; ww < WARPS; ++ww) {
       uint32_t c = wh[ww][bin];
@@ -581,7 +604,7 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
   RR_TRY(dalloc(&vals_a, n_total));
   RR_TRY(dalloc(&vals_b, n_total));
   RR_TRY(dalloc(&seg_id, n_total));
-  RR_TRY(dalloc(&hist, (uint64_t)256 * (n_tiles ? n_tiles : 1)));
+  RR_TRY(dalloc(&hist, (uint64_t)256 * (n_tiles ? n_tiles : 1) + 256));  // per-(digit, tile) counters + 256 digit totals
   RR_TRY(dalloc(&seg_box_ord, (uint64_t)(n_segs ? n_segs : 1) * 6));
   RR_TRY(dalloc(&leaf_parent, n));
   RR_TRY(dalloc(&flags, n));
@@ -608,8 +631,9 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
     uint32_t *vin = vals_a, *vout = vals_b;
     for (int pass = 0; pass < 8; ++pass) {
       k_sort_hist<false><<<n_tiles, SORT_THREADS, 0, st>>>(kin, vin, seg_id, n_total, pass * 8, hist, n_tiles);
-      k_scan<<<1, 1024, 0, st>>>(hist, (uint64_t)256 * n_tiles);
-      k_sort_scatter<false><<<n_tiles, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, seg_id, n_total, pass * 8, hist, n_tiles);
+      k_scan_bins<<<256, 1024, 0, st>>>(hist, n_tiles, hist + (uint64_t)256 * n_tiles);
+      k_sort_scatter<false><<<n_tiles, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, seg_id, n_total, pass * 8, hist, n_tiles,
+                                                              hist + (uint64_t)256 * n_tiles);
       uint64_t* tk = kin; kin = kout; kout = tk;
       uint32_t* tv = vin; vin = vout; vout = tv;
     }
@@ -617,8 +641,9 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
     if (!one_full_segment) {
       for (int shift = 0; (n_segs >> shift) != 0; shift += 8) {
         k_sort_hist<true><<<n_tiles, SORT_THREADS, 0, st>>>(kin, vin, seg_id, n_total, shift, hist, n_tiles);
-        k_scan<<<1, 1024, 0, st>>>(hist, (uint64_t)256 * n_tiles);
-        k_sort_scatter<true><<<n_tiles, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, seg_id, n_total, shift, hist, n_tiles);
+        k_scan_bins<<<256, 1024, 0, st>>>(hist, n_tiles, hist + (uint64_t)256 * n_tiles);
+        k_sort_scatter<true><<<n_tiles, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, seg_id, n_total, shift, hist, n_tiles,
+                                                               hist + (uint64_t)256 * n_tiles);
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
       }
