@@ -779,11 +779,14 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         lo = PLD3(W_LOX, s);
         ld = PLD3(W_LDX, s);
         const uint32_t mw = PW(W_M, s);
+        bool accepted = false;
+        V3 n3 = mk(0, 0, 0), nbest = n3;  // normal of the primitive under test / of the closest accepted hit
+        // One primitive per round for a leaf of a hierarchy; the 2 - 4 primitives of a hierarchy-less mesh (the Cornell
+        // quads) are tested back to back: a round trip through the vote per triangle costs more than the idle lanes.
+        do {
         const uint32_t slot = pend_slot;
         pend_slot++;
         pend_cnt--;
-        bool accepted = false;
-        V3 n3 = mk(0, 0, 0);
         if (mw & WM_SPHERES) {
           // EXTENSION (the reference kernel has no sphere primitive): semantics of oracle/rr_oracle.c ray_sphere
           if (COUNT) c_sph++;
@@ -808,6 +811,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
                 n3 = (hp - c) / r;
                 if (back) n3 = -n3;
                 lt = t; lprim = prim; lback = back;
+                nbest = n3;
                 accepted = true;
               }
             }
@@ -844,6 +848,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
                   }
                   if (ok) {
                     lt = t; lprim = prim; lback = back;
+                    nbest = n3;
                     accepted = true;
                   }
                 }
@@ -851,11 +856,12 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             }
           }
         }
+        } while (pend_cnt > 0);
         if (accepted) {
           PSF(W_LT, s, lt);
           PW(W_LPRIM, s) = (uint32_t)lprim;
           PW(W_M, s) = (mw & ~WM_BACK) | (lback ? WM_BACK : 0u);
-          CST3(C_LNX, s, n3);
+          CST3(C_LNX, s, nbest);
         }
         if (pend_cnt == 0 && ref_is_leaf(cur)) {  // the leaf this slot was waiting on becomes the postponed one
           pend_slot = ref_slot(cur);
