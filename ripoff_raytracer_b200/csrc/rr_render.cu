@@ -677,6 +677,10 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       // with the node fetch that follows instead of preceding it.
       uint2 top = make_uint2(0u, 0u);
       if (mine && sp > 0) top = make_uint2(PW(W_TOPN, s), PW(W_TOPD, s));
+      // ... and a register copy of entry sp-2 (`below`), fetched one pop ahead: when a popped entry turns out to lie
+      // behind the closest hit, the next one is already here instead of an L2 round trip away.
+      uint2 below = make_uint2(0u, 0u);
+      if (mine && sp > 1) below = stk[(sp - 2) * POOL];
       // Pops the stack / postpones leaves until `cur` is an inner node, a leaf the slot must wait for, or REF_END.
       auto resolve = [&](int32_t next) {
         for (;;) {
@@ -685,7 +689,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             while (sp > 0) {
               const uint2 e = top;
               --sp;
-              if (sp > 0) top = stk[(sp - 1) * POOL];
+              top = below;
+              if (sp > 1) below = stk[(sp - 2) * POOL];
               if (__uint_as_float(e.y) <= lt) { next = (int32_t)e.x; found = true; break; }
             }
             if (!found) { cur = REF_END; break; }
@@ -748,6 +753,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
               if (sp > 0) w[-POOL] = top;
               if (hits >= 3) w[0] = hits == 4 ? make_uint2((uint32_t)r3, k3 & ~3u) : make_uint2((uint32_t)r2, k2 & ~3u);
               if (hits == 4) w[POOL] = make_uint2((uint32_t)r2, k2 & ~3u);
+              below = hits >= 3 ? make_uint2((uint32_t)r2, k2 & ~3u) : top;  // the entry under the new top
               top = make_uint2((uint32_t)r1, k1 & ~3u);
               sp += hits - 1;
             }
