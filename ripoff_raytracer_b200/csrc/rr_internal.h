@@ -82,6 +82,8 @@ struct DMaterial {
   float pad;
 };
 
+static_assert(sizeof(DMaterial) == 48, "the shade phase reads a material as three float4: (type, ior, emissionStrength, reflectiveness) (color, specularProbability) (emissionColor, pad)");
+
 struct DCamera {
   float pos[3];
   float pitch, yaw, roll, fov, aspect;

@@ -182,7 +182,10 @@ __device__ __forceinline__ bool shade(const RenderParams& p, const SceneHit& hit
                                       V3& incoming, uint32_t& bounce, uint32_t& passes, uint32_t& rng) {
   if (!hit.did) return false;
   const DMaterial* M = p.materials + hit.material;
-  const int32_t type = __ldg(&M->type);
+  // the 48-byte material record in three 16-byte loads, all requested before the first use
+  const float4 m0 = __ldg(reinterpret_cast<const float4*>(M)), m1 = __ldg(reinterpret_cast<const float4*>(M) + 1),
+               m2 = __ldg(reinterpret_cast<const float4*>(M) + 2);
+  const int32_t type = __float_as_int(m0.x);
   if (type == RR_MATERIAL_INVISIBLE) {
     // `continue` without counting a bounce (:502-506).  Guard: when hit.point + dir*1e-6 rounds back
     // to hit.point the reference loops forever; the path is ended after RR_MAX_INVISIBLE_PASSES.
@@ -190,11 +193,11 @@ __device__ __forceinline__ bool shade(const RenderParams& p, const SceneHit& hit
     origin = hit.point + dir * RR_EPSILON;
     return true;
   }
-  V3 color = ld3(M->color);
-  const V3 emissionColor = ld3(M->emissionColor);
-  float emissionStrength = __ldg(&M->emissionStrength);
-  const float specProb = __ldg(&M->specularProbability);
-  const float reflectiveness = __ldg(&M->reflectiveness);
+  V3 color = mk(m1.x, m1.y, m1.z);
+  const V3 emissionColor = mk(m2.x, m2.y, m2.z);
+  float emissionStrength = m0.z;
+  const float specProb = m1.w;
+  const float reflectiveness = m0.w;
   if (type == RR_MATERIAL_CHECKER) {  // :509-533
     const float size = emissionStrength;
     const int xi = (int)floorf(hit.point.x / size);
@@ -209,7 +212,7 @@ __device__ __forceinline__ bool shade(const RenderParams& p, const SceneHit& hit
     const V3 specularDir = reflect3(dir, hit.normal);
     dir = normalize(lerp3(diffuseDir, specularDir, reflectiveness * (isSpec ? 1.0f : 0.0f)));
   } else if (type == RR_MATERIAL_GLASSY) {  // :534-558
-    const float ior = __ldg(&M->ior);
+    const float ior = m0.y;
     const float iorCur = hit.back ? ior : 1.0f;
     const float iorNext = hit.back ? 1.0f : ior;
     const V3 reflectDir = reflect3(dir, hit.normal);
@@ -513,18 +516,20 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       cand &= cand - 1u;
       m = (m & ~31) + k;
       const DMesh* M = p.meshes + m;
+      // the whole mesh record is requested at once (one L1 round trip instead of three dependent ones)
+      const float4 wlo = __ldg(&M->wmin), whi = __ldg(&M->wmax);
+      const float4 i0 = __ldg(&M->ri0), i1 = __ldg(&M->ri1), i2 = __ldg(&M->ri2);
+      const float4 blo = __ldg(&M->bmin), bhi = __ldg(&M->bmax);
       float tn;
       if (best_dst < INFINITY) {  // a hit exists: the box may now lie behind it
-        const float4 wlo = __ldg(&M->wmin), whi = __ldg(&M->wmax);
         if (COUNT) c_box++;
         if (!box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, best_dst, tn)) return false;
       }
-      mflags = __float_as_uint(__ldg(&M->wmin.w));
+      mflags = __float_as_uint(wlo.w);
       if (mflags & RR_MF_SPHERES) {
         lo = origin; ld = dir; linv = winv; lnoi = wnoi;
       } else {
         // WorldToLocalRay, src/Trace.cl:118-137
-        const float4 i0 = __ldg(&M->ri0), i1 = __ldg(&M->ri1), i2 = __ldg(&M->ri2);
         const V3 rel = origin - mk(i0.w, i1.w, i2.w);
         lo = mk(dot(xyz(i0), rel), dot(xyz(i1), rel), dot(xyz(i2), rel));
         ld = mk(dot(xyz(i0), dir), dot(xyz(i1), dir), dot(xyz(i2), dir));
@@ -541,7 +546,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         linv = mk(rcp_approx(ld.x), rcp_approx(ld.y), rcp_approx(ld.z));
         lnoi = mk(-(lo.x * linv.x), -(lo.y * linv.y), -(lo.z * linv.z));
       }
-      const float4 blo = __ldg(&M->bmin), bhi = __ldg(&M->bmax);
       if (COUNT) c_box++;
       if (!box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, linv, lnoi, INFINITY, tn)) return false;
       const uint32_t first = __float_as_uint(blo.w), count = __float_as_uint(bhi.w);
