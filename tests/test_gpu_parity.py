@@ -634,8 +634,10 @@ def test_many_instances_top_level_is_bit_exact(count):
 
     W, H = (160, 90) if count > 1000 else (200, 120)
     wl = workloads.instances(width=W, height=H, spp=3, bounces=10, count=count, subdiv=1)
+    if count < 1000:  # the sphere set is one more entry of the top level (its pseudo-mesh has the highest index)
+        wl.scene.add_spheres(scenes.random_spheres(24, seed=5, box=(250.0, 90.0, 250.0), radius=(4.0, 12.0)))
     t, m, r, sp = wl.scene.arrays()
-    assert len(m) == count + 6
+    assert len(m) == count + 6 and len(sp) == (24 if count < 1000 else 0)
     ren = rr.Renderer()
     ren.upload(wl.scene)
     o = Oracle(t, m, r, sp)
