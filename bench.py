@@ -339,10 +339,21 @@ def main():
             barrier()
             e_dt = total(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
         e_rays = total(e_rays)
+        # "frame time to output.bmp" (BASELINE.json metric): the e2e step plus placeImageDataIntoBMP of the frame it left
+        # in host memory (src/main.cpp:725); written once, outside the timed region, by rank 0
+        bmp_ms = None
+        if rank == 0:
+            import tempfile
+            with tempfile.TemporaryDirectory() as td:
+                t0 = time.perf_counter()
+                rr.write_bmp(Path(td) / "output.bmp", frame_host)
+                bmp_ms = (time.perf_counter() - t0) * 1e3
         e2e = {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e_dt / e2e_steps * 1e3, "steps": e2e_steps, "kernel_ms_per_step": e_kernel_ms / e2e_steps,
                "clocks": e_clocks.summary(),
-               "includes": "rr_upload_scene (H2D from pinned memory + LBVH build) + rr_render (kernel + frame D2H)"}
+               "includes": "rr_upload_scene (H2D from pinned memory + LBVH build) + rr_render (kernel + frame D2H)",
+               "bmp_write_ms": bmp_ms,
+               "frame_time_to_bmp_ms": (e_dt / e2e_steps * 1e3 + bmp_ms) if bmp_ms is not None else None}
 
     if rank != 0:
         if world > 1:
