@@ -549,7 +549,10 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       if (COUNT) c_box++;
       if (!box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, linv, lnoi, INFINITY, tn)) return false;
       const uint32_t first = __float_as_uint(blo.w), count = __float_as_uint(bhi.w);
-      lt = INFINITY; lprim = NO_PRIM; lback = false;
+      // The sphere set lives in world space and is the last entry in the tie order (highest mesh index): a sphere at or
+      // beyond the closest hit so far can never win, so its walk starts with that distance as the bound.
+      lt = (mflags & RR_MF_SPHERES) ? best_dst : INFINITY;
+      lprim = NO_PRIM; lback = false;
       sp = 0;
       if (count <= RR_DIRECT_MAX) {  // no hierarchy: the primitives are tested one by one in the leaf phase
         pend_slot = (mflags & RR_MF_SPHERES) ? 0u : first;
