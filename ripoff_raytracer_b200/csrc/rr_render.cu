@@ -375,8 +375,9 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   const unsigned warp = threadIdx.x >> 5;
   const unsigned full = 0xffffffffu;
   const unsigned lanes_below = (1u << lane) - 1u;
-  uint32_t* const pool = pool_all + warp * (NW * POOL + 32);
+  uint32_t* const pool = pool_all + warp * (NW * POOL + 32 + 8);
   uint32_t* const sel = pool + NW * POOL;  // slot picked for each lane in the current phase
+  uint32_t* const tstate = sel + 32;       // the warp's current tile (only the pixel phase touches it): x0, y0, w, next, pixels
   uint2* const stack = p.stack + (size_t)(blockIdx.x * WARPS + warp) * ((size_t)p.stack_entries * POOL);  // [depth][slot]
   uint32_t* const cold = p.cold + (size_t)(blockIdx.x * WARPS + warp) * (NC * POOL);
 #define CW(w, s) cold[(w) * POOL + (s)]
@@ -391,12 +392,11 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
 #define PST3(w, s, v) do { PSF(w, s, (v).x); PSF((w) + 1, s, (v).y); PSF((w) + 2, s, (v).z); } while (0)
   const V3 cam_pos = mk(p.cam.pos[0], p.cam.pos[1], p.cam.pos[2]);
   // warp-uniform state
-  bool queue_empty = false;
-  uint32_t tile_x0 = 0, tile_y0 = 0, tile_w = 1, tile_next = 0, tile_pixels = 0;
+  bool more_pixels = true;  // the tile queue or the warp's current tile still holds pixels
+  if (lane < 8) tstate[lane] = lane == 2 ? 1u : 0u;
   uint32_t n_need = POOL;  // slots waiting for a pixel
-  uint32_t round = 0;
   // statistics
-  unsigned long long n_rays = 0, n_tiles = 0;
+  uint32_t n_rays = 0, n_tiles = 0;  // per lane / per warp: far below 2^32 even for an 8K, 1024-spp frame on one GPU
   unsigned c_box = 0, c_tri = 0, c_sph = 0;
   unsigned ph_runs[5] = {0, 0, 0, 0, 0}, ph_lanes[5] = {0, 0, 0, 0, 0};
 
@@ -632,7 +632,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) { keys[r] = PW(W_KEY, lane + 32 * r); ksum += keys[r]; }
     const uint32_t counts = __reduce_add_sync(full, ksum);
-    const bool more_pixels = !(queue_empty && tile_next >= tile_pixels);
     const uint32_t nP = more_pixels ? n_need : 0u;
     if (counts == 0 && nP == 0) break;
     const uint32_t nT = min(counts & 0xffu, 32u), nL = min((counts >> 8) & 0xffu, 32u), nS = min((counts >> 16) & 0xffu, 32u),
@@ -643,7 +642,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     if (nS * wS > best) { best = nS * wS; phase = PH_SETUP; }
     if (nH * wH > best) { best = nH * wH; phase = PH_SHADE; }
     if (min(nP, 32u) * wP > best) { best = min(nP, 32u) * wP; phase = PH_PIXEL; }
-    round++;
     // ---- gather: up to 32 slots that are ready for the chosen phase go to the lanes (ONE copy of this code for all
     // phases: the phases a warp cycles through have to share a 32 KB instruction cache) ----
     int n_sel;
@@ -974,6 +972,9 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       // ================= hand a pixel to every slot that needs one =================
       if (COUNT) { ph_runs[PH_PIXEL]++; ph_lanes[PH_PIXEL] += n_sel; }
       bool need = s >= 0;
+      // the tile state lives in shared memory between two runs of this (rare) phase, not in six registers
+      uint32_t tile_x0 = tstate[0], tile_y0 = tstate[1], tile_w = tstate[2], tile_next = tstate[3], tile_pixels = tstate[4];
+      bool queue_empty = false;
       while (__any_sync(full, need)) {
         if (tile_next >= tile_pixels) {
           if (queue_empty) break;
@@ -1013,6 +1014,9 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         }
         tile_next += __popc(mb);
       }
+      more_pixels = !(queue_empty && tile_next >= tile_pixels);
+      __syncwarp();
+      if (lane == 0) { tstate[0] = tile_x0; tstate[1] = tile_y0; tstate[2] = tile_w; tstate[3] = tile_next; tstate[4] = tile_pixels; }
       const bool got = s >= 0 && !need;
       n_need -= __popc(__ballot_sync(full, got));
       if (need) PW(W_PIX, s) = (uint32_t)PIX_IDLE;  // the queue is empty
@@ -1029,12 +1033,12 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
 #undef PLD3
 #undef PST3
   // counters: one atomic per warp
-  unsigned long long r = n_rays;
+  unsigned long long r = n_rays;  // summed over the warp in 64 bits
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) r += __shfl_xor_sync(full, r, off);
   if (lane == 0) {
     atomicAdd(&p.counters->rays, r);
-    atomicAdd(&p.counters->tiles, n_tiles);
+    atomicAdd(&p.counters->tiles, (unsigned long long)n_tiles);
   }
   if (COUNT) {
     unsigned long long b = c_box, t = c_tri, sq = c_sph;
@@ -1063,7 +1067,7 @@ void default_tuning(Tuning& t) {
   t.ctas_per_sm = 0;
 }
 
-constexpr size_t RENDER_SMEM = (size_t)WARPS * (NW * POOL + 32) * sizeof(uint32_t);
+constexpr size_t RENDER_SMEM = (size_t)WARPS * (NW * POOL + 32 + 8) * sizeof(uint32_t);
 
 template <class K>
 static cudaError_t launch_persistent(K kernel, const RenderParams& p, int sm_count, cudaStream_t s) {
