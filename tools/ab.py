@@ -42,8 +42,10 @@ def child(workloads_csv, spp):
         r.upload(wl.scene)
         r.render_device(wl.cam, wl.width, wl.height, 2, wl.bounces)
         best = min((r.render_device(wl.cam, wl.width, wl.height, wl.spp, wl.bounces) for _ in range(3)), key=lambda s: s["render_ms"])
+        import zlib
+        crc = zlib.crc32(r.read_frame(wl.width, wl.height).tobytes())  # same image <=> same checksum across variants
         print(json.dumps({"variant": os.environ.get("RR_AB_LABEL", "?"), "workload": wl.name, "ms": round(best["render_ms"], 3),
-                          "mrays_s": round(best["rays"] / best["render_ms"] / 1e3, 1), "rays": best["rays"]}), flush=True)
+                          "mrays_s": round(best["rays"] / best["render_ms"] / 1e3, 1), "rays": best["rays"], "frame_crc32": crc}), flush=True)
         r.close()
 
 
