@@ -14,16 +14,7 @@
 #define RR_DIRECT_MAX 4               // segments this small are tested without a hierarchy
 #define RR_TILE_W 8                   // default work tile: 8 x 4 pixels = one warp
 #define RR_TILE_H 4
-// EXPERIMENT (prepared at the end of round 1, not yet measured): -DRR_QNODES packs a 4-wide node
-// into 64 bytes -- child boxes as 16-bit grid coordinates inside the (delta-inflated) root box of their mesh, rounded
-// outwards by RR_QMARGIN grid steps -- so that a node visit costs four 16-byte loads instead of seven.
-#ifdef RR_QNODES
-#define RR_NODE_QUADS 4   // 16-byte quads per traversal node: 3 of packed planes + 1 of child references
-#define RR_QSTEPS 65530.0f  // grid steps across the root box (the outward margin must still fit 16 bits)
-#define RR_QMARGIN 2        // outward rounding, in grid steps (covers the decode's rounding: see rr_render.cu)
-#else
 #define RR_NODE_QUADS 8   // float4 per traversal node (4-wide node, 128 bytes)
-#endif
 #ifndef RR_POOL
 #define RR_POOL 96        // path slots per warp of the render kernel (rr_render.cu)
 #endif

@@ -497,38 +497,6 @@ __global__ void k_pack_wide(const int32_t* __restrict__ frontier, unsigned int n
     }
   }
   float4* o = nodes + RR_NODE_QUADS * (uint64_t)g;
-#ifdef RR_QNODES
-  // Grid of the mesh: origin = the delta-inflated root box's low corner (what k_prepare_meshes stores as DMesh::bmin),
-  // step = its extent / RR_QSTEPS -- the SAME float expressions as the kernel uses to rebuild the grid from bmin / bmax.
-  // A low plane is rounded down and a high plane up, RR_QMARGIN steps further out; an unused child gets an inverted box
-  // and the reference REF_END (0x80000000), which the kernel treats as a miss.
-  uint32_t qlo[3][4], qhi[3][4];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const float org = sb[a] - d, top = sb[3 + a] + d;
-    const float step = (top - org) * (1.0f / RR_QSTEPS);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (k < cnt && step > 0.0f) {
-        const float fl = floorf((lo[a][k] - org) / step) - (float)RR_QMARGIN, fh = ceilf((hi[a][k] - org) / step) + (float)RR_QMARGIN;
-        qlo[a][k] = (uint32_t)fminf(fmaxf(fl, 0.0f), 65535.0f);
-        qhi[a][k] = (uint32_t)fminf(fmaxf(fh, 0.0f), 65535.0f);
-      } else if (k < cnt) {  // flat mesh on this axis: every plane is the origin plane
-        qlo[a][k] = 0u; qhi[a][k] = 65535u;
-      } else {
-        qlo[a][k] = 65535u; qhi[a][k] = 0u;
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (k >= cnt) ref[k] = (int32_t)0x80000000;
-  auto pk = [](uint32_t a, uint32_t b) { return __uint_as_float(a | (b << 16)); };
-  o[0] = make_float4(pk(qlo[0][0], qlo[0][1]), pk(qlo[0][2], qlo[0][3]), pk(qlo[1][0], qlo[1][1]), pk(qlo[1][2], qlo[1][3]));
-  o[1] = make_float4(pk(qlo[2][0], qlo[2][1]), pk(qlo[2][2], qlo[2][3]), pk(qhi[0][0], qhi[0][1]), pk(qhi[0][2], qhi[0][3]));
-  o[2] = make_float4(pk(qhi[1][0], qhi[1][1]), pk(qhi[1][2], qhi[1][3]), pk(qhi[2][0], qhi[2][1]), pk(qhi[2][2], qhi[2][3]));
-  o[3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
-#else
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     o[a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
@@ -536,7 +504,6 @@ __global__ void k_pack_wide(const int32_t* __restrict__ frontier, unsigned int n
   }
   o[6] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
   o[7] = make_float4(__int_as_float(cnt), 0.0f, 0.0f, 0.0f);
-#endif
 }
 
 // Sorted triangle arrays.  geom: (A, prim) (B-A) (C-A) -- the edge vectors are

@@ -673,27 +673,9 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       } else {
         cur = REF_END; sp = 0; pend_cnt = 0;
       }
-#ifdef RR_QNODES
-      // Decode of a 16-bit plane coordinate q of this mesh's grid (origin = DMesh::bmin, step = extent / RR_QSTEPS, the
-      // expressions k_pack_wide used): t = (origin + q * step) * inv - o * inv = q * qa + (origin * inv + noi).  q goes
-      // into the mantissa of 2^23 (one PRMT; 2^23 + q is exact), so t = (2^23 + q) * qa + qb with qb reduced by
-      // 2^23 * qa: one rounding of at most half an ulp of 2^23 * qa = half a grid step, inside the RR_QMARGIN steps
-      // the packed planes were moved outwards; everything else rounds as the unquantised test does (covered by delta).
-      V3 qa = mk(0, 0, 0), qb = mk(0, 0, 0);
-      if (mine) {
-        const DMesh* M = p.meshes + ((int)(PW(W_M, s) & WM_MESH) - 1);
-        const float4 glo = __ldg(&M->bmin), ghi = __ldg(&M->bmax);
-        qa = mk((ghi.x - glo.x) * (1.0f / RR_QSTEPS) * linv.x, (ghi.y - glo.y) * (1.0f / RR_QSTEPS) * linv.y,
-                (ghi.z - glo.z) * (1.0f / RR_QSTEPS) * linv.z);
-        qb = mk(__fmaf_rn(glo.x, linv.x, lnoi.x) - 8388608.0f * qa.x, __fmaf_rn(glo.y, linv.y, lnoi.y) - 8388608.0f * qa.y,
-                __fmaf_rn(glo.z, linv.z, lnoi.z) - 8388608.0f * qa.z);
-      }
-      const bool negx = linv.x < 0.0f, negy = linv.y < 0.0f, negz = linv.z < 0.0f;
-#else
       // which quad of a node holds the entry / exit plane of each axis (node layout: min.x min.y min.z max.x max.y max.z)
       const int qnx = linv.x < 0.0f ? 3 : 0, qny = linv.y < 0.0f ? 4 : 1, qnz = linv.z < 0.0f ? 5 : 2;
       const int qfx = 3 - qnx, qfy = 5 - qny, qfz = 7 - qnz;
-#endif
       uint2* const stk = stack + (mine ? s : 0);
       // Entry sp-1 (the top) is kept in registers / shared memory, entries 0..sp-2 in the global scratch.  A pop
       // hands out the top at once and only ISSUES the load of the next entry, so that its L2 latency overlaps
@@ -735,29 +717,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             // planes the ray ENTERS / LEAVES through are picked by the sign of its direction (qn*/qf*, set up
             // once per run), so no per-child min/max is needed to order the two planes of a slab.
             const float4* nd = p.nodes + RR_NODE_QUADS * (size_t)cur;
-#ifdef RR_QNODES
-            // 64-byte node: (lo.x lo.y) (lo.z hi.x) (hi.y hi.z) as pairs of packed words [children 0|1, children 2|3], refs
-            const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(nd)), q1 = __ldg(reinterpret_cast<const uint4*>(nd) + 1),
-                        q2 = __ldg(reinterpret_cast<const uint4*>(nd) + 2);
-            const float4 rf = __ldg(nd + 3);
-            const uint32_t nxa = negx ? q1.z : q0.x, nxb = negx ? q1.w : q0.y, fxa = negx ? q0.x : q1.z, fxb = negx ? q0.y : q1.w;
-            const uint32_t nya = negy ? q2.x : q0.z, nyb = negy ? q2.y : q0.w, fya = negy ? q0.z : q2.x, fyb = negy ? q0.w : q2.y;
-            const uint32_t nza = negz ? q2.z : q1.x, nzb = negz ? q2.w : q1.y, fza = negz ? q1.x : q2.z, fzb = negz ? q1.y : q2.w;
-            if (COUNT) c_box += (unsigned)((__float_as_int(rf.x) != REF_END) + (__float_as_int(rf.y) != REF_END) +
-                                           (__float_as_int(rf.z) != REF_END) + (__float_as_int(rf.w) != REF_END));
-            auto lo16 = [](uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); };  // 2^23 + low half
-            auto hi16 = [](uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); };  // 2^23 + high half
-            auto child_key = [&](float pnx, float pny, float pnz, float pfx, float pfy, float pfz, float ref, uint32_t c) -> uint32_t {
-              const float tn = fmaxf(fmaxf(__fmaf_rn(pnx, qa.x, qb.x), __fmaf_rn(pny, qa.y, qb.y)), __fmaf_rn(pnz, qa.z, qb.z));
-              const float tf = fminf(fminf(__fmaf_rn(pfx, qa.x, qb.x), __fmaf_rn(pfy, qa.y, qb.y)), __fmaf_rn(pfz, qa.z, qb.z));
-              const float t0 = fmaxf(tn, 0.0f);
-              return (tf >= t0 && tn <= lt && __float_as_int(ref) != REF_END) ? ((__float_as_uint(t0) & ~3u) | c) : 0xffffffffu;
-            };
-            uint32_t k0 = child_key(lo16(nxa), lo16(nya), lo16(nza), lo16(fxa), lo16(fya), lo16(fza), rf.x, 0u),
-                     k1 = child_key(hi16(nxa), hi16(nya), hi16(nza), hi16(fxa), hi16(fya), hi16(fza), rf.y, 1u),
-                     k2 = child_key(lo16(nxb), lo16(nyb), lo16(nzb), lo16(fxb), lo16(fyb), lo16(fzb), rf.z, 2u),
-                     k3 = child_key(hi16(nxb), hi16(nyb), hi16(nzb), hi16(fxb), hi16(fyb), hi16(fzb), rf.w, 3u);
-#else
             const float4 nx = __ldg(nd + qnx), ny = __ldg(nd + qny), nz = __ldg(nd + qnz), fx = __ldg(nd + qfx),
                          fy = __ldg(nd + qfy), fz = __ldg(nd + qfz), rf = __ldg(nd + 6);
             if (COUNT) c_box += (unsigned)__float_as_int(__ldg(&nd[7].x));
@@ -771,7 +730,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             };
             uint32_t k0 = child_key(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, 0u), k1 = child_key(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, 1u),
                      k2 = child_key(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, 2u), k3 = child_key(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, 3u);
-#endif
             {  // 5-comparator sorting network, ascending
               uint32_t t;
               t = min(k0, k1); k1 = max(k0, k1); k0 = t;
