@@ -132,11 +132,13 @@ def cpu_reference_run(wl, steps, warmup, budget_s=20.0):
         # the reference kernel has no sphere primitive: its arm renders the triangle part of the scene
         ref = Reference("fast")
         t0 = time.perf_counter()
-        rt, rm, _ = ref.scene_from_arrays(t, m, r)
+        rt, rm, rn = ref.scene_from_arrays(t, m, r)
         build_s = time.perf_counter() - t0
         counter = Oracle(rt, rm, r)                      # strict restatement: counts the segments of the same sample
         render = lambda spp: ref.render(cam, W, H, spp, wl.bounces, threads=cores)
+        sah_counter = Oracle(rt, rm, r, ref_gpunodes=rn)  # the same restatement walking the REFERENCE's own SAH nodes
     else:
+        sah_counter = None
         t0 = time.perf_counter()
         counter = Oracle(t, m, r, sp)
         build_s = time.perf_counter() - t0
@@ -154,7 +156,17 @@ def cpu_reference_run(wl, steps, warmup, budget_s=20.0):
     for _ in range(steps):
         render(spp)
     dt = (time.perf_counter() - t0) / max(steps, 1)
+    sah = None
+    if sah_counter is not None:  # test counts of the reference's own hierarchy on the same rays (1 spp: the counts are per ray)
+        _, _, s1 = sah_counter.render(cam, W, H, 1, wl.bounces, threads=cores)
+        _, _, l1 = counter.render(cam, W, H, 1, wl.bounces, threads=cores)
+        sah = {"box_tests_per_ray": s1["box_tests"] / max(s1["rays"], 1), "tri_tests_per_ray": s1["tri_tests"] / max(s1["rays"], 1),
+               "lbvh_binary_walk_box_tests_per_ray": l1["box_tests"] / max(l1["rays"], 1),
+               "lbvh_binary_walk_tri_tests_per_ray": l1["tri_tests"] / max(l1["rays"], 1),
+               "what": "oracle restatement of src/Trace.cl:319-397 on the node list the reference's SplitBVH (src/readobj.hpp:206-267) "
+                       "built for this scene, triangles only, same rays; beside it the oracle's binary in-order walk of our LBVH"}
     return {
+        "reference_sah": sah,
         "mrays_s": rays / dt / 1e6, "msamples_s": W * H * spp / dt / 1e6, "ms_per_step": dt * 1e3, "cores": cores,
         "kind": kind, "build_s": build_s,
         "sample": f"{wl.name} scene ({len(t)} tris{'' if kind == 'port' else ', triangles only: the reference kernel has no spheres'}) "
@@ -176,7 +188,8 @@ def run_reference_arm(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(wl, args.gpus),
         "msamples_per_s": res["msamples_s"],
-        "cpu_baseline": {"value": res["mrays_s"], "unit": "Mrays/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
+        "cpu_baseline": {"value": res["mrays_s"], "unit": "Mrays/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"],
+                         "reference_sah": res["reference_sah"]},
         "e2e": {"value": res["mrays_s"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -266,10 +279,7 @@ def main():
         if mode == "local":
             return r.render_device(wl.cam, W, H, spp, bounces)
         if mode == "shared":
-            if rank == 0:
-                r.queue_reset()
-            barrier()
-            return r.render_shared(wl.cam, W, H, spp, bounces)
+            return shared_frame(r, wl.cam, W, H, spp, bounces, rank, barrier)
         st = r.render_strided(wl.cam, W, H, spp, bounces, rank, world)
         return st
 
@@ -299,7 +309,7 @@ def main():
         t0 = time.perf_counter()
         for _ in range(args.steps):
             st = device_step()
-            rays_total += st["rays"] + st["rays_reused"]
+            rays_total += st["rays"]
             rays_traced += st["rays"]
             kernel_ms.append(st["render_ms"])  # CUDA events on the library's own stream, around the render kernel
         barrier()
@@ -334,7 +344,7 @@ def main():
                     _, _, st = r.render(wl.cam, W, H, spp, bounces, out=frame_host)              # render + D2H
                 else:
                     st = device_step_e2e(r, rr, wl, mode, rank, world, barrier, frame_host)
-                e_rays += st["rays"] + st["rays_reused"]
+                e_rays += st["rays"]
                 e_kernel_ms += st["render_ms"]
             barrier()
             e_dt = total(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
@@ -355,20 +365,49 @@ def main():
                "bmp_write_ms": bmp_ms,
                "frame_time_to_bmp_ms": (e_dt / e2e_steps * 1e3 + bmp_ms) if bmp_ms is not None else None}
 
+    # ---- N > 1: is the frame the ranks render TOGETHER the frame one GPU renders alone?  (outside the timed regions) ----
+    frame_equal = None
+    if world > 1:
+        chk_spp = 1
+        if mode == "shared":
+            shared_frame(r, wl.cam, W, H, chk_spp, bounces, rank, barrier)
+            barrier()
+            together = r.read_frame(W, H) if rank == 0 else None
+        else:
+            r.render_strided(wl.cam, W, H, chk_spp, bounces, rank, world)
+            from ripoff_raytracer_b200 import multigpu as _mg
+            together = _mg.merge_strided_frames(dist, r.read_frame(W, H), rank, device="cuda")
+        if rank == 0:
+            import zlib
+            alone = rr.Renderer((local,))   # a context of its own: private queue, private frame
+            alone.upload_arrays(host["tris"], host["meshes"], host["ranges"], host["spheres"])
+            want, _, _ = alone.render(wl.cam, W, H, chk_spp, bounces)
+            alone.close()
+            frame_equal = {"equal": bool(np.array_equal(together, want)), "spp": chk_spp, "crc32_together": zlib.crc32(together.tobytes()),
+                           "crc32_one_gpu": zlib.crc32(want.tobytes()), "differing_pixels": int((together != want).any(-1).sum())}
+        barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_render): counted intersection work / live kernel time ----
+    # ---- rooflines of the dominant kernel (k_render): counted intersection work / live kernel time ----
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
         pass
+    import ctypes as C
+    def probe_peak(what):
+        v = C.c_float()
+        _abi.check(_abi.lib().rr_probe_peak(what, C.byref(v)), "rr_probe_peak")
+        return float(v.value)
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     sm_max = (clk.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0)
-    fp32_peak_tflops = sm_count * 128 * 2 * sm_max * 1e6 / 1e12  # 128 FP32 lanes/SM, FMA = 2 flop
+    fp32_nominal = sm_count * 128 * 2 * sm_max * 1e6 / 1e12  # 128 FP32 lanes/SM, FMA = 2 flop
+    fp32_measured = probe_peak(0)                            # FFMA issue rate of this device, measured now
+    l2_measured = probe_peak(1)                              # L2 read bandwidth of this device, measured now
     per_launch_rays = traced_all / args.steps / world
     ach_tflops = per_launch_rays * flops_per_ray / kernel_s / 1e12 if kernel_s else 0.0
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -381,26 +420,31 @@ def main():
         traffic_src = f"{per_ray:.1f} B/ray x rays of this launch; measured by ncu on {ncu['k_render']['config']}"
     except Exception:
         pass
-    # Two rooflines of the same launch.  `roofline` follows the bench contract (bound "hbm": algorithmic bytes of the
-    # counted intersection tests over the measured HBM copy peak; `traffic` is what DRAM actually moved, from the
-    # committed ncu capture).  `roofline_fp32` is the one north_star names: counted intersection flops over the FP32
-    # FMA peak.  Neither bound is what limits a divergent BVH walk: most of the algorithmic
-    # bytes are served by L1/L2, and the FMA pipe is ~14 % busy.
-    roofline = {"bound": "hbm", "kernel": "k_render", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
-                "bytes_per_ray": bytes_per_ray, "box_tests_per_ray": n_box, "tri_tests_per_ray": n_tri,
-                "sphere_tests_per_ray": n_sph, "kernel_ms": kernel_s * 1e3,
-                "note": "algorithmic bytes = 32 B per box test + 48 B per triangle test + 16 B per sphere test (SURVEY.md 8d), "
-                        "counted by the instrumented kernel on the same scene; traffic well BELOW them: the walk runs out of L1/L2"}
-    roofline_fp32 = {
-        "bound": "fp32", "kernel": "k_render", "achieved": ach_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-        "frac": ach_tflops / fp32_peak_tflops,
-        "peak_source": f"nominal FP32 FMA peak: {sm_count} SMs x 128 lanes x 2 flop x {sm_max:.0f} MHz (MEASURED_PEAKS.json holds no FP32 figure)",
-        "flops_per_ray": flops_per_ray,
-        "note": "24 flop per box test, 53 per triangle test, 24 per sphere test; result arithmetic is issued unfused (numerics "
-                "contract), slab tests use FFMA.  A divergent BVH walk is latency-bound, not FMA-bound: DESIGN.md section 5.2",
+    # `roofline` is the roof north_star names and SURVEY.md 8d states for this path: counted intersection flops over the
+    # FP32 FMA rate (measured on this device by rr_probe_peak; the nominal figure beside it).  The same launch against the
+    # two memory roofs follows in `roofline_l2` and `roofline_bytes` (the counted bytes are served by L1 / L2: the DRAM
+    # traffic ncu measured is a tenth of them).  None of the three binds a divergent BVH walk, which is bound by the
+    # latency of its dependent node fetches: the useful efficiency figures are issue-slot
+    # utilisation and lanes per instruction in profiles/.
+    tests = {"box_tests_per_ray": n_box, "tri_tests_per_ray": n_tri, "sphere_tests_per_ray": n_sph}
+    roofline = {
+        "bound": "fp32", "kernel": "k_render", "achieved": ach_tflops, "peak": fp32_measured, "unit": "TFLOP/s",
+        "frac": ach_tflops / fp32_measured if fp32_measured else None, "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": "FP32 FMA rate measured on this device by rr_probe_peak(0) (MEASURED_PEAKS.json holds no FP32 figure)",
+        "peak_nominal": fp32_nominal, "frac_of_nominal": ach_tflops / fp32_nominal,
+        "flops_per_ray": flops_per_ray, **tests, "kernel_ms": kernel_s * 1e3,
+        "note": "24 flop per box test, 53 per triangle test, 24 per sphere test (SURVEY.md 8d), counted by the instrumented kernel on "
+                "the same scene; result arithmetic is issued unfused (numerics contract), slab tests use FFMA",
     }
+    roofline_l2 = {"bound": "l2", "kernel": "k_render", "achieved": ach_gbs, "peak": l2_measured, "unit": "GB/s",
+                   "frac": ach_gbs / l2_measured if l2_measured else None, "bytes_per_ray": bytes_per_ray,
+                   "peak_source": "L2 read bandwidth measured on this device by rr_probe_peak(1): 32 MB read 64 times, 16-byte loads"}
+    roofline_bytes = {"bound": "hbm", "kernel": "k_render", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                      "frac": ach_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
+                      "bytes_per_ray": bytes_per_ray,
+                      "note": "algorithmic bytes = 32 B per box test + 48 B per triangle test + 16 B per sphere test (SURVEY.md 8d); DRAM "
+                              "moves far fewer (traffic): this is NOT the binding roof, the walk runs out of L1 / L2"}
 
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -409,16 +453,23 @@ def main():
         "msamples_per_s": samples_all / dt / 1e6, "frame_time_s": dt / args.steps, "wall_ms_per_step": wall / args.steps * 1e3,
         "timing": "CUDA events on the launching stream around each render kernel, max over ranks per step",
         "rays_per_sample": rays_all / samples_all,
-        "rays_traced_fraction": traced_all / max(rays_all, 1.0), "tile_queue": mode,
-        "clocks": clk, "gpu_launches": args.steps * world, "roofline": roofline, "roofline_fp32": roofline_fp32,
+        "tile_queue": mode,
+        "clocks": clk, "gpu_launches": args.steps * world, "roofline": roofline, "roofline_l2": roofline_l2,
+        "roofline_bytes": roofline_bytes,
     }
+    if frame_equal is not None:
+        line["frame_equal"] = frame_equal["equal"]
+        line["frame_check"] = frame_equal
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
         try:
             res = cpu_reference_run(wl, 1, 1, budget_s=20.0)
             line["cpu_baseline"] = {"value": res["mrays_s"], "unit": "Mrays/s", "cores": res["cores"], "kind": res["kind"],
-                                    "sample": res["sample"], "msamples_per_s": res["msamples_s"]}
+                                    "sample": res["sample"], "msamples_per_s": res["msamples_s"], "reference_sah": res["reference_sah"]}
+            if res["reference_sah"]:  # next to our box tests per ray: the same count for the reference's own hierarchy
+                line["roofline"]["box_tests_per_ray_reference_sah"] = res["reference_sah"]["box_tests_per_ray"]
+                line["roofline"]["tri_tests_per_ray_reference_sah"] = res["reference_sah"]["tri_tests_per_ray"]
         except Exception as e:  # the checker is optional for the measurement itself
             line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     print(json.dumps(line), flush=True)
@@ -426,14 +477,21 @@ def main():
         dist.destroy_process_group()
 
 
+def shared_frame(r, cam, W, H, spp, bounces, rank, barrier):
+    """One frame through the shared tile queue, protocol of include/rr_api.h: every rank is back from the previous
+    frame (barrier), rank 0 resets the counter, nobody pops before the reset is done (barrier), all render."""
+    barrier()
+    if rank == 0:
+        r.queue_reset()
+    barrier()
+    return r.render_shared(cam, W, H, spp, bounces)
+
+
 def device_step_e2e(r, rr, wl, mode, rank, world, barrier, frame_host):
     """One multi-GPU frame ending with the frame in rank 0's host buffer."""
     W, H = wl.width, wl.height
     if mode == "shared":
-        if rank == 0:
-            r.queue_reset()
-        barrier()
-        st = r.render_shared(wl.cam, W, H, wl.spp, wl.bounces)
+        st = shared_frame(r, wl.cam, W, H, wl.spp, wl.bounces, rank, barrier)
         barrier()
         if rank == 0:
             r.read_frame(W, H, out=frame_host)  # D2H straight into the pinned host frame

@@ -122,7 +122,8 @@ typedef enum rr_status {
   RR_ERR_BAD_MESH_RANGE = 6, /* mesh range outside the triangle array */
   RR_ERR_BVH_DEPTH = 7,      /* hierarchy deeper than the traversal stack */
   RR_ERR_IO = 8,             /* file could not be opened / parsed */
-  RR_ERR_UNSUPPORTED = 9
+  RR_ERR_UNSUPPORTED = 9,
+  RR_ERR_QUEUE = 10          /* shared tile queue misuse: reset while a frame was in flight, frame larger than the exported one */
 } rr_status;
 
 const char* rr_error_string(int status);
@@ -197,7 +198,7 @@ int rr_update_meshes(rr_ctx* ctx, const rr_mesh* meshes, size_t n_meshes);
 typedef struct rr_stats {
   uint64_t samples;      /* Trace() calls = W*H*spp                         */
   uint64_t rays;         /* path segments traced (closest-hit queries)      */
-  uint64_t rays_reused;  /* segments answered from the per-pixel primary-hit cache */
+  uint64_t stack_overflows; /* always 0: a non-zero count makes the render fail with RR_ERR_BVH_DEPTH */
   uint64_t box_tests;    /* ray/AABB tests                                  */
   uint64_t tri_tests;    /* ray/triangle tests                              */
   uint64_t sphere_tests; /* ray/sphere tests                                */
@@ -234,6 +235,11 @@ int rr_render_ex(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t hei
  * running while at least this many lanes can step, [6]: speculative traversal on/off, [7]: persistent
  * CTAs per SM (0 = as many as fit).  n < 8 leaves the rest unchanged; values == NULL restores defaults. */
 int rr_set_tuning(rr_ctx* ctx, const uint32_t* values, size_t n);
+
+/* Progress of the render that is running on this context (callable from a second host thread while rr_render blocks;
+ * the analogue of the "Rendering tile i of n" line of src/image.hpp:316-323, 363-377): tiles taken from the queue so
+ * far and tiles of the frame.  Reads the device's tile counter with an 8-byte copy on a stream of its own. */
+int rr_render_progress(rr_ctx* ctx, uint64_t* tiles_popped, uint64_t* tiles_total);
 
 /* Device-resident variant used for kernel-only timing: renders into the
  * context's own frame buffer on the device and does not copy it back.
@@ -296,15 +302,25 @@ int rr_bvh_read(rr_ctx* ctx, int which, uint64_t* codes, uint32_t* order, int32_
  * over NVLink.  handle buffers are RR_IPC_HANDLE_BYTES each.
  * ---------------------------------------------------------------------- */
 #define RR_IPC_HANDLE_BYTES 64
+/* Rank 0: allocates the shared frame (width*height*4 bytes, an allocation of its own that no later render of this
+ * context frees or moves) and exports it with the tile counter.  Exporting again replaces the shared frame: handles
+ * given out before are dead and every peer has to import the new ones. */
 int rr_queue_export(rr_ctx* ctx, uint32_t width, uint32_t height, uint8_t* queue_handle, uint8_t* frame_handle);
+/* Other ranks: width / height must be the exported ones (they bound what rr_render_shared may write). */
 int rr_queue_import(rr_ctx* ctx, uint32_t width, uint32_t height, const uint8_t* queue_handle,
                     const uint8_t* frame_handle);
-/* rank 0, before every shared frame: counter = 0. */
+/* Protocol of one shared frame (every rank, in this order):
+ *     barrier A   -- every rank has RETURNED from rr_render_shared of the previous frame
+ *     rank 0: rr_queue_reset
+ *     barrier B   -- the reset is done before anybody pops
+ *     every rank: rr_render_shared
+ * The counter carries a 16-bit frame epoch (reset k sets epoch k; the k-th rr_render_shared of a rank after its
+ * export / import expects epoch k), so a reset that overtakes a kernel still popping, or a rank that skipped a frame,
+ * is reported as RR_ERR_QUEUE by the rr_render_shared that saw it instead of painting tiles of the wrong frame. */
 int rr_queue_reset(rr_ctx* ctx);
-/* Render the tiles this rank manages to pop from the shared queue.  Pixels go
- * to the shared frame if one is attached (peer stores), else to the local
- * frame buffer (tiles not owned stay 0).  Non-blocking pairs are not offered:
- * returns when this rank's kernel has drained the queue. */
+/* Render the tiles this rank manages to pop from the shared queue; pixels go to the shared frame (peer stores over
+ * NVLink on the importing ranks).  width*height*4 must not exceed the exported / imported frame (RR_ERR_QUEUE).
+ * Returns when this rank's kernel has drained the queue. */
 int rr_render_shared(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
                      uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, rr_stats* stats_out);
 /* Static partition fallback (no peer access): render only tiles t with
@@ -314,6 +330,18 @@ int rr_render_strided(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_
                       rr_stats* stats_out);
 /* Device pointer of the local frame buffer (for an NCCL gather by the caller). */
 int rr_frame_device_ptr(rr_ctx* ctx, uint64_t* ptr_out, uint64_t* bytes_out);
+
+/* ------------------------------------------------------------------------
+ * Test hooks (tests/test_gpu_parity.py): the device side of the numerics contract and of the RNG, evaluated on
+ * the GPU for arrays of inputs.  fn: 0 cos, 1 sin, 2 log, 3 exp2, 4 powr(x, y), 5 tan.  rr_probe_rng: the seed of
+ * `pixel` (src/Trace.cl:158-166), then state / value after 4 x RandomValue and 2 x rand01, then a RandomDirection.
+ * ---------------------------------------------------------------------- */
+int rr_probe_math(int fn, const float* x, const float* y, float* out, uint64_t n);
+int rr_probe_rng(uint32_t pixel, int32_t frame, uint32_t* out_u32_8, float* out_f32_9);
+/* Measured roofline denominators on the current device (bench.py): what = 0: FP32 FMA issue rate in TFLOP/s (8
+ * independent FFMA chains per thread, 8 CTAs of 256 threads per SM); what = 1: L2 read bandwidth in GB/s (a 32 MB
+ * buffer read 64 times with 16-byte loads that bypass L1). */
+int rr_probe_peak(int what, float* value_out);
 
 /* ------------------------------------------------------------------------
  * Host helpers that sit either side of the path (same formats as the reference).

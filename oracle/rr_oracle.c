@@ -441,6 +441,21 @@ static inline int ray_box(const ray_t* r, const float* bmin, const float* bmax, 
   return tmax >= fmaxf(tmin, 0.0f);
 }
 
+/* Per-ray part of the conservative slack (same statement as rr_internal.h ray_slack): the rounding error of the
+ * slab test AND of the triangle test's `origin - A` grows with the ray ORIGIN, not with the box, so every box the
+ * ray is tested against is additionally widened by 2^-18 of the largest |origin coordinate| (mesh-local origin for
+ * the walk inside a mesh).  Without it a camera 10^4 scene extents away loses hits to culling
+ * (tests/test_oracle.py::test_far_origin_hierarchy_only_culls). */
+static inline float ray_slack(const ray_t* r) {
+  float m = fmaxf(fmaxf(fabsf(r->origin.x), fabsf(r->origin.y)), fabsf(r->origin.z));
+  return (m < 3.0e38f ? m : 0.0f) * 3.814697265625e-06f;
+}
+static inline int ray_box_slack(const ray_t* r, const float* bmin, const float* bmax, float slack, float* outDist) {
+  float lo[3] = {bmin[0] - slack, bmin[1] - slack, bmin[2] - slack};
+  float hi[3] = {bmax[0] + slack, bmax[1] + slack, bmax[2] + slack};
+  return ray_box(r, lo, hi, outDist);
+}
+
 typedef struct {
   int didHit;
   float dst;
@@ -502,9 +517,10 @@ static void mesh_closest_lbvh(const rro_scene* sc, const rro_meshx* mx, const ra
   best->dst = tmax;
   best->prim = 0x7fffffff;
   float distRoot;
+  const float slack = ray_slack(ray);
   if (!sc->brute_force) {
     c->box_tests++;
-    if (!ray_box(ray, mx->bmin, mx->bmax, &distRoot)) return;
+    if (!ray_box_slack(ray, mx->bmin, mx->bmax, slack, &distRoot)) return;
   }
   const rro_lbvh* b = &sc->tb;
   if (mx->count <= RRO_DIRECT_MAX || sc->brute_force) {
@@ -524,8 +540,8 @@ static void mesh_closest_lbvh(const rro_scene* sc, const rro_meshx* mx, const ra
     float ba[6], bb[6], dA, dB;
     box_of_ref(b, L, ba);
     box_of_ref(b, R, bb);
-    inflate_box(ba, mx->delta);
-    inflate_box(bb, mx->delta);
+    inflate_box(ba, mx->delta + slack);
+    inflate_box(bb, mx->delta + slack);
     c->box_tests += 2;
     int hA = ray_box(ray, ba, ba + 3, &dA) && dA <= best->dst;
     int hB = ray_box(ray, bb, bb + 3, &dB) && dB <= best->dst;
@@ -642,9 +658,10 @@ static void spheres_closest(const rro_scene* sc, const ray_t* ray, float tmax, h
   best->prim = 0x7fffffff;
   if (sc->n_spheres == 0) return;
   float distRoot;
+  const float slack = ray_slack(ray);
   if (!sc->brute_force) {
     c->box_tests++;
-    if (!ray_box(ray, sc->sph_bmin, sc->sph_bmax, &distRoot)) return;
+    if (!ray_box_slack(ray, sc->sph_bmin, sc->sph_bmax, slack, &distRoot)) return;
   }
   const rro_lbvh* b = &sc->sb;
   if (sc->n_spheres <= RRO_DIRECT_MAX || sc->brute_force) {
@@ -664,8 +681,8 @@ static void spheres_closest(const rro_scene* sc, const ray_t* ray, float tmax, h
     float ba[6], bb[6], dA, dB;
     box_of_ref(b, L, ba);
     box_of_ref(b, R, bb);
-    inflate_box(ba, sc->sph_delta);
-    inflate_box(bb, sc->sph_delta);
+    inflate_box(ba, sc->sph_delta + slack);
+    inflate_box(bb, sc->sph_delta + slack);
     c->box_tests += 2;
     int hA = ray_box(ray, ba, ba + 3, &dA) && dA <= best->dst;
     int hB = ray_box(ray, bb, bb + 3, &dB) && dB <= best->dst;
@@ -1011,7 +1028,7 @@ void rro_random_direction(uint32_t* state, float* out3) {
   v3 d = random_direction(state);
   out3[0] = d.x; out3[1] = d.y; out3[2] = d.z;
 }
-/* numerics contract, vectorised for tests/test_math_parity.py: fn 0 cos, 1 sin, 2 log, 3 exp2, 4 powr(x, y[i]), 5 tan */
+/* numerics contract, vectorised for the tests (test_numerics_contract_accuracy, test_numerics_contract_is_bit_identical_on_device): fn 0 cos, 1 sin, 2 log, 3 exp2, 4 powr(x, y[i]), 5 tan */
 void rro_math(int fn, const float* x, const float* y, float* out, uint64_t n) {
   for (uint64_t i = 0; i < n; ++i) {
     switch (fn) {

@@ -83,7 +83,7 @@ class Stats(C.Structure):
     _fields_ = [
         ("samples", C.c_uint64),
         ("rays", C.c_uint64),
-        ("rays_reused", C.c_uint64),
+        ("stack_overflows", C.c_uint64),
         ("box_tests", C.c_uint64),
         ("tri_tests", C.c_uint64),
         ("sphere_tests", C.c_uint64),
@@ -128,6 +128,10 @@ SYMBOLS = {
     "rr_set_tuning": (C.c_int, [_vp, _vp, _sz]),
     "rr_render_device": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, C.POINTER(Stats)]),
     "rr_read_frame": (C.c_int, [_vp, _vp, _sz]),
+    "rr_render_progress": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
+    "rr_probe_math": (C.c_int, [C.c_int, _vp, _vp, _vp, _u64]),
+    "rr_probe_rng": (C.c_int, [_u32, _i32, _vp, _vp]),
+    "rr_probe_peak": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
     "rr_accum_reset": (C.c_int, [_vp, _u32, _u32]),
     "rr_accum_add_frame": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, _vp, C.POINTER(Stats)]),
     "rr_accum_frame_count": (C.c_int, [_vp, C.POINTER(_u32)]),

@@ -6,6 +6,7 @@
 // fallback: every entry point that needs a device fails with RR_ERR_NO_DEVICE /
 // RR_ERR_CUDA when there is none.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -142,10 +143,17 @@ struct Device {
   uint32_t stack_entries = 0;           // per slot: 3 per level of the deepest wide hierarchy + slack
   unsigned long long* queue = nullptr;  // local tile counter
   Counters* counters = nullptr;
-  // shared (multi-process) attachments
+  // shared (multi-process) attachments.  The exporter's shared frame is an allocation of its own (never d.frame, which
+  // ensure_frame may free and move); shared_bytes bounds what rr_render_shared may write through either mapping.
   unsigned long long* shared_queue = nullptr;
   uint8_t* shared_frame = nullptr;
+  size_t shared_bytes = 0;
+  uint32_t shared_w = 0, shared_h = 0;
+  uint32_t shared_epoch = 0;  // frames rendered through the shared queue since the export / import
   bool shared_imported = false;
+  // progress polling (rr_render_progress): a stream of its own, so that the 8-byte copy overtakes the running kernel
+  cudaStream_t poll_stream = nullptr;
+  unsigned long long* poll_host = nullptr;  // pinned
 };
 
 }  // namespace rr
@@ -156,6 +164,8 @@ struct rr_ctx {
   bool has_scene = false;
   bool peer_ok = false;  // devices 1.. can address device 0's memory
   rr::Tuning tune;
+  std::atomic<uint64_t> progress_total{0};  // tiles of the frame being rendered (0: none)
+  std::atomic<const unsigned long long*> progress_queue{nullptr};  // the counter its warps pop
 };
 
 namespace rr {
@@ -309,6 +319,30 @@ __global__ void __launch_bounds__(256) k_accum_add(uint32_t* __restrict__ frame,
   }
 }
 
+// ---- measured roofline denominators (rr_probe_peak; bench.py) --------------------------------------------------
+// MEASURED_PEAKS.json holds an HBM copy and a bf16 GEMM figure; the two roofs this path is read against -- FP32 FMA
+// issue and L2 bandwidth -- are measured here, on the device the bench runs on, by two plain kernels.
+__global__ void __launch_bounds__(256) k_peak_fma(float* out, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.0f, a2 = a0 + 2.0f, a3 = a0 + 3.0f, a4 = a0 + 4.0f, a5 = a0 + 5.0f, a6 = a0 + 6.0f, a7 = a0 + 7.0f;
+  const float m = 0.999f, c = 1e-3f;
+  for (int i = 0; i < iters; ++i) {  // 8 independent FFMA chains per thread
+    a0 = __fmaf_rn(a0, m, c); a1 = __fmaf_rn(a1, m, c); a2 = __fmaf_rn(a2, m, c); a3 = __fmaf_rn(a3, m, c);
+    a4 = __fmaf_rn(a4, m, c); a5 = __fmaf_rn(a5, m, c); a6 = __fmaf_rn(a6, m, c); a7 = __fmaf_rn(a7, m, c);
+  }
+  const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 12345.678f) out[0] = r;  // keeps the chains alive
+}
+__global__ void __launch_bounds__(256) k_peak_l2(const uint4* __restrict__ buf, size_t n16, int passes, unsigned* out) {
+  unsigned acc = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int pass = 0; pass < passes; ++pass)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+      const uint4 v = __ldcg(buf + i);  // L2 only: the L1 would not hold 32 MB anyway
+      acc += v.x ^ v.y ^ v.z ^ v.w;
+    }
+  if (acc == 0x12345678u) out[0] = acc;
+}
+
 struct IndexedInput {  // host arrays of rr_upload_scene_indexed
   const float* positions = nullptr;
   size_t n_positions = 0;
@@ -334,6 +368,13 @@ struct SegPlan {
   std::vector<uint32_t> mesh_seg;      // mesh -> segment
 };
 
+// Argument checks shared by the three upload entry points.
+static int check_upload_counts(size_t n_tris, size_t n_meshes, size_t n_spheres) {
+  if (n_tris >= 0x7fffffffull || n_spheres >= 0x7fffffffull) return fail(RR_ERR_INVALID_ARGUMENT, "too many primitives (31-bit indices)");
+  if (n_meshes >= 0x1fffff00ull) return fail(RR_ERR_INVALID_ARGUMENT, "too many meshes (the slot word keeps mesh + 1 in 29 bits)");
+  return RR_OK;
+}
+
 static int plan_segments(const rr_mesh_range* ranges, size_t n_meshes, size_t n_tris, SegPlan& plan) {
   struct R { uint64_t first, count; };
   std::vector<R> uniq;
@@ -350,9 +391,11 @@ static int plan_segments(const rr_mesh_range* ranges, size_t n_meshes, size_t n_
   plan.first.clear(); plan.count.clear();
   for (auto& r : uniq) { plan.first.push_back((uint32_t)r.first); plan.count.push_back((uint32_t)r.count); }
   plan.mesh_seg.resize(n_meshes);
-  for (size_t i = 0; i < n_meshes; ++i) {
-    for (size_t k = 0; k < uniq.size(); ++k)
-      if (uniq[k].first == ranges[i].firstTriangle && uniq[k].count == ranges[i].numTriangles) { plan.mesh_seg[i] = (uint32_t)k; break; }
+  for (size_t i = 0; i < n_meshes; ++i) {  // uniq is sorted by (first, count): binary search
+    const R want{ranges[i].firstTriangle, ranges[i].numTriangles};
+    const auto it = std::lower_bound(uniq.begin(), uniq.end(), want,
+                                     [](const R& a, const R& b) { return a.first != b.first ? a.first < b.first : a.count < b.count; });
+    plan.mesh_seg[i] = (uint32_t)(it - uniq.begin());
   }
   return RR_OK;
 }
@@ -735,8 +778,9 @@ static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam
   p.counters = d.counters;
 }
 
-static int check_render_args(const rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t H, uint32_t spp) {
+static int check_render_args(const rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t H, uint32_t spp, uint32_t bounces = 0) {
   if (!ctx || !cam) return fail(RR_ERR_INVALID_ARGUMENT, "null context or camera");
+  if (bounces > RR_MAX_BOUNCES) return fail(RR_ERR_INVALID_ARGUMENT, "max_bounces above 8388607 (the bounce counter has 23 bits)");
   if (!ctx->has_scene) return fail(RR_ERR_NO_SCENE, "rr_upload_scene has not been called");
   if (W == 0 || H == 0 || spp == 0) return fail(RR_ERR_INVALID_ARGUMENT, "width, height and spp must be positive");
   if ((uint64_t)W * H > 0x7fffffffull) return fail(RR_ERR_INVALID_ARGUMENT, "image too large (pixel index must fit 31 bits)");
@@ -747,7 +791,7 @@ static void read_stats(const Counters& c, uint64_t samples, float ms, float buil
   if (!out) return;
   out->samples = samples;
   out->rays = c.rays;
-  out->rays_reused = c.rays_reused;
+  out->stack_overflows = c.stack_overflows;
   out->box_tests = c.box_tests;
   out->tri_tests = c.tri_tests;
   out->sphere_tests = c.sphere_tests;
@@ -763,7 +807,7 @@ static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t 
                         int32_t frame_index, uint32_t tile_size, bool want_radiance, bool count_tests, int mode,
                         uint32_t rank, uint32_t world, rr_stats* stats_out) {
   // mode 0: local queue, 1: shared (imported/exported) queue + frame, 2: static stride partition
-  int rc = check_render_args(ctx, cam, W, H, spp);
+  int rc = check_render_args(ctx, cam, W, H, spp, bounces);
   if (rc) return rc;
   const size_t nd = ctx->dev.size();
   if (want_radiance && nd > 1) return fail(RR_ERR_UNSUPPORTED, "radiance output needs a single-device context");
@@ -776,10 +820,20 @@ static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t 
   if (mode != 1) {
     RR_CUDA(cudaMemsetAsync(d0.queue, 0, sizeof(unsigned long long), d0.stream));
     if (mode == 2) RR_CUDA(cudaMemsetAsync(d0.frame, 0, (size_t)W * H * 4, d0.stream));
-  } else if (!d0.shared_queue) {
-    return fail(RR_ERR_INVALID_ARGUMENT, "rr_render_shared needs rr_queue_export or rr_queue_import first");
+  } else {
+    if (!d0.shared_queue) return fail(RR_ERR_INVALID_ARGUMENT, "rr_render_shared needs rr_queue_export or rr_queue_import first");
+    if ((size_t)W * H * 4 > d0.shared_bytes)
+      return fail(RR_ERR_QUEUE, "frame of " + std::to_string(W) + "x" + std::to_string(H) + " exceeds the shared frame (" +
+                                    std::to_string(d0.shared_w) + "x" + std::to_string(d0.shared_h) + ")");
+    d0.shared_epoch++;  // the epoch rr_queue_reset has put into the counter for this frame
   }
   RR_CUDA(cudaStreamSynchronize(d0.stream));
+  {
+    RenderParams q;
+    fill_params(ctx, d0, cam, W, H, spp, bounces, frame_index, tile_size, q);
+    ctx->progress_queue.store(mode == 1 ? d0.shared_queue : d0.queue);
+    ctx->progress_total.store((uint64_t)q.tiles_x * q.tiles_y);
+  }
   for (size_t k = 0; k < nd; ++k) {
     Device& d = ctx->dev[k];
     RR_CUDA(cudaSetDevice(d.ordinal));
@@ -789,6 +843,7 @@ static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t 
     if (mode == 1) {
       p.queue = d.shared_queue;
       p.frame = d.shared_frame;
+      p.queue_epoch = d0.shared_epoch & 0xffffu;
     } else {
       p.queue = d0.queue;  // peers pop device 0's counter
       p.frame = d0.frame;
@@ -811,11 +866,18 @@ static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t 
     ms_max = std::max(ms_max, ms);
     Counters c;
     RR_CUDA(cudaMemcpy(&c, d.counters, sizeof(c), cudaMemcpyDeviceToHost));
-    total.rays += c.rays; total.rays_reused += c.rays_reused; total.box_tests += c.box_tests;
+    total.rays += c.rays; total.stack_overflows += c.stack_overflows; total.queue_errors += c.queue_errors; total.box_tests += c.box_tests;
     total.tri_tests += c.tri_tests; total.sphere_tests += c.sphere_tests; total.tiles += c.tiles;
     for (int q = 0; q < 5; ++q) { total.phase_runs[q] += c.phase_runs[q]; total.phase_lanes[q] += c.phase_lanes[q]; }
   }
+  ctx->progress_total.store(0);
   read_stats(total, (uint64_t)W * H * spp, ms_max, d0.build_ms, stats_out);
+  if (total.stack_overflows)
+    return fail(RR_ERR_BVH_DEPTH, std::to_string(total.stack_overflows) + " node steps ran out of traversal stack (" +
+                                      std::to_string(d0.stack_entries) + " entries per path): the frame is incomplete");
+  if (total.queue_errors)
+    return fail(RR_ERR_QUEUE, "the shared tile counter changed epoch during the frame: rr_queue_reset must run between two barriers, "
+                              "after every rank has returned from rr_render_shared (include/rr_api.h)");
   return RR_OK;
 }
 
@@ -837,11 +899,12 @@ const char* rr_error_string(int status) {
     case RR_ERR_BVH_DEPTH: return "BVH deeper than the traversal stack";
     case RR_ERR_IO: return "I/O error";
     case RR_ERR_UNSUPPORTED: return "unsupported";
+    case RR_ERR_QUEUE: return "shared tile queue misuse";
     default: return "unknown status";
   }
 }
 const char* rr_last_error(void) { return g_last_error.c_str(); }
-int rr_version(void) { return 300; }
+int rr_version(void) { return 400; }
 
 int rr_device_count(int* out) {
   if (!out) return fail(RR_ERR_INVALID_ARGUMENT, "null output");
@@ -886,6 +949,8 @@ int rr_create(const int* cuda_ordinals, int n, rr_ctx** out) {
     if (e == cudaSuccess) e = cudaEventCreate(&d.ev1);
     if (e == cudaSuccess) e = cudaMalloc(&d.queue, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&d.counters, sizeof(Counters));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.poll_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost(&d.poll_host, sizeof(unsigned long long));
     if (e == cudaSuccess) {
       d.stack_warps = (uint32_t)(prop.multiProcessorCount * render_max_warps_per_sm());
       // the scratch block itself is sized at upload time (its stack part depends on the scene)
@@ -918,7 +983,11 @@ void rr_destroy(rr_ctx* ctx) {
     if (d.shared_imported) {
       if (d.shared_queue) cudaIpcCloseMemHandle(d.shared_queue);
       if (d.shared_frame) cudaIpcCloseMemHandle(d.shared_frame);
+    } else if (d.shared_frame) {
+      cudaFree(d.shared_frame);
     }
+    if (d.poll_stream) cudaStreamDestroy(d.poll_stream);
+    if (d.poll_host) cudaFreeHost(d.poll_host);
     cudaFree(d.frame); cudaFree(d.radiance); cudaFree(d.accum); cudaFree(d.queue); cudaFree(d.counters); cudaFree(d.cold);
     dev_trim(d.ordinal);
     if (d.ev0) cudaEventDestroy(d.ev0);
@@ -934,9 +1003,10 @@ int rr_upload_scene(rr_ctx* ctx, const rr_triangle* tris, size_t n_tris, const r
   if (!ctx) return fail(RR_ERR_INVALID_ARGUMENT, "null context");
   if ((n_tris && !tris) || (n_meshes && (!meshes || !ranges)) || (n_spheres && !spheres))
     return fail(RR_ERR_INVALID_ARGUMENT, "null array with non-zero count");
-  if (n_tris >= 0x7fffffffull || n_spheres >= 0x7fffffffull) return fail(RR_ERR_INVALID_ARGUMENT, "too many primitives (31-bit indices)");
+  int rc = check_upload_counts(n_tris, n_meshes, n_spheres);
+  if (rc) return rc;
   SegPlan plan;
-  int rc = plan_segments(ranges, n_meshes, n_tris, plan);
+  rc = plan_segments(ranges, n_meshes, n_tris, plan);
   if (rc) return rc;
   ctx->has_scene = false;
   for (Device& d : ctx->dev) {
@@ -954,15 +1024,15 @@ int rr_upload_scene_indexed(rr_ctx* ctx, const float* positions, size_t n_positi
   if (!ctx) return fail(RR_ERR_INVALID_ARGUMENT, "null context");
   if ((n_tris && (!positions || !normals || !corners)) || (n_meshes && (!meshes || !ranges)) || (n_spheres && !spheres))
     return fail(RR_ERR_INVALID_ARGUMENT, "null array with non-zero count");
-  if (n_tris >= 0x7fffffffull || n_spheres >= 0x7fffffffull || n_positions >= 0xffffffffull || n_normals >= 0xffffffffull)
-    return fail(RR_ERR_INVALID_ARGUMENT, "too many primitives (31-bit indices)");
-  if (n_meshes >= 0xffff0ull) return fail(RR_ERR_INVALID_ARGUMENT, "too many meshes");
+  if (n_positions >= 0xffffffffull || n_normals >= 0xffffffffull) return fail(RR_ERR_INVALID_ARGUMENT, "too many vertices (32-bit indices)");
+  int rc = check_upload_counts(n_tris, n_meshes, n_spheres);
+  if (rc) return rc;
   for (size_t i = 0; i < n_tris; ++i)  // the gather kernel trusts the indices
     for (int k = 0; k < 6; ++k)
       if (corners[6 * i + k] >= (k < 3 ? n_positions : n_normals))
         return fail(RR_ERR_INVALID_ARGUMENT, "triangle " + std::to_string(i) + ": corner index out of range");
   SegPlan plan;
-  int rc = plan_segments(ranges, n_meshes, n_tris, plan);
+  rc = plan_segments(ranges, n_meshes, n_tris, plan);
   if (rc) return rc;
   IndexedInput in;
   in.positions = positions; in.n_positions = n_positions; in.normals = normals; in.n_normals = n_normals; in.corners = corners;
@@ -978,7 +1048,8 @@ int rr_upload_scene_indexed(rr_ctx* ctx, const float* positions, size_t n_positi
 
 int rr_upload_scene_ref(rr_ctx* ctx, const rr_triangle* tris, size_t n_tris, const rr_mesh* meshes, size_t n_meshes,
                         const rr_ref_node* nodes, size_t n_nodes) {
-  if (n_meshes && !nodes) return fail(RR_ERR_INVALID_ARGUMENT, "null node list");
+  if (!ctx) return fail(RR_ERR_INVALID_ARGUMENT, "null context");
+  if ((n_meshes && (!nodes || !meshes)) || (n_tris && !tris)) return fail(RR_ERR_INVALID_ARGUMENT, "null array with non-zero count");
   std::vector<rr_mesh_range> ranges(n_meshes);
   std::vector<uint64_t> stack;
   for (size_t i = 0; i < n_meshes; ++i) {
@@ -1039,11 +1110,28 @@ int rr_render_device(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t
   return render_frame(ctx, cam, width, height, spp, max_bounces, frame_index, tile_size, false, false, 0, 0, 1, stats_out);
 }
 
+int rr_render_progress(rr_ctx* ctx, uint64_t* tiles_popped, uint64_t* tiles_total) {
+  if (!ctx || !tiles_popped || !tiles_total) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
+  Device& d = ctx->dev[0];
+  const uint64_t total = ctx->progress_total.load();
+  *tiles_total = total;
+  *tiles_popped = 0;
+  const unsigned long long* src = ctx->progress_queue.load();
+  if (!total || !src) return RR_OK;  // nothing is being rendered
+  RR_CUDA(cudaSetDevice(d.ordinal));
+  RR_CUDA(cudaMemcpyAsync(d.poll_host, src, sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.poll_stream));
+  RR_CUDA(cudaStreamSynchronize(d.poll_stream));
+  const uint64_t popped = *d.poll_host & ((1ull << RR_QUEUE_EPOCH_SHIFT) - 1ull);  // every warp's last, failing pop counts too
+  *tiles_popped = popped < total ? popped : total;
+  return RR_OK;
+}
+
 int rr_read_frame(rr_ctx* ctx, uint8_t* rgba_out, size_t bytes) {
   if (!ctx || !rgba_out) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
   Device& d0 = ctx->dev[0];
-  const uint8_t* src = d0.shared_frame && !d0.shared_imported ? d0.shared_frame : d0.frame;
-  if (!src || bytes > d0.frame_bytes) return fail(RR_ERR_INVALID_ARGUMENT, "no frame of that size has been rendered");
+  const bool from_shared = d0.shared_frame && !d0.shared_imported;  // the exporting rank reads the gathered frame
+  const uint8_t* src = from_shared ? d0.shared_frame : d0.frame;
+  if (!src || bytes > (from_shared ? d0.shared_bytes : d0.frame_bytes)) return fail(RR_ERR_INVALID_ARGUMENT, "no frame of that size has been rendered");
   RR_CUDA(cudaSetDevice(d0.ordinal));
   RR_CUDA(cudaMemcpy(rgba_out, src, bytes, cudaMemcpyDeviceToHost));
   return RR_OK;
@@ -1135,7 +1223,7 @@ int rr_render_progressive(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uin
     rc = rr_accum_add_frame(ctx, cam, width, height, spp, max_bounces, (int32_t)((uint32_t)first_frame_index + k), tile_size,
                             k + 1 == n_frames ? rgba_out : nullptr, &st);
     if (rc) return rc;
-    total.samples += st.samples; total.rays += st.rays; total.rays_reused += st.rays_reused; total.box_tests += st.box_tests;
+    total.samples += st.samples; total.rays += st.rays; total.stack_overflows += st.stack_overflows; total.box_tests += st.box_tests;
     total.tri_tests += st.tri_tests; total.sphere_tests += st.sphere_tests; total.tiles += st.tiles;
     total.render_ms += st.render_ms; total.build_ms = st.build_ms;
   }
@@ -1152,13 +1240,13 @@ int rr_primary_hits(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t 
   const size_t n = (size_t)width * height;
   int32_t *dm = nullptr, *dp = nullptr;
   float* dd = nullptr;
-  RR_CUDA(cudaMalloc(&dm, n * 4));
-  RR_CUDA(cudaMalloc(&dp, n * 4));
-  RR_CUDA(cudaMalloc(&dd, n * 4));
+  cudaError_t e = cudaMalloc(&dm, n * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&dp, n * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&dd, n * 4);
   RenderParams p;
   fill_params(ctx, d, cam, width, height, 1, 1, 0, 0, p);
   p.hit_mesh = dm; p.hit_prim = dp; p.hit_dst = dd;
-  cudaError_t e = cudaMemsetAsync(d.queue, 0, sizeof(unsigned long long), d.stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d.queue, 0, sizeof(unsigned long long), d.stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(d.counters, 0, sizeof(Counters), d.stream);
   if (e == cudaSuccess) e = launch_primary(p, d.sm_count, d.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
@@ -1199,17 +1287,30 @@ int rr_bvh_read(rr_ctx* ctx, int which, uint64_t* codes, uint32_t* order, int32_
 int rr_queue_export(rr_ctx* ctx, uint32_t width, uint32_t height, uint8_t* queue_handle, uint8_t* frame_handle) {
   if (!ctx || !queue_handle || !frame_handle) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == RR_IPC_HANDLE_BYTES, "IPC handle size");
+  if (width == 0 || height == 0 || (uint64_t)width * height > 0x7fffffffull) return fail(RR_ERR_INVALID_ARGUMENT, "bad image size");
   Device& d = ctx->dev[0];
-  int rc = ensure_frame(d, width, height, false);
-  if (rc) return rc;
+  RR_CUDA(cudaSetDevice(d.ordinal));
+  if (d.shared_imported) return fail(RR_ERR_INVALID_ARGUMENT, "this context has imported a queue; export from a context of its own");
+  const size_t bytes = (size_t)width * height * 4;
+  if (d.shared_frame && bytes != d.shared_bytes) {  // a new size: the old handles die with the old allocation
+    RR_CUDA(cudaStreamSynchronize(d.stream));
+    cudaFree(d.shared_frame);
+    d.shared_frame = nullptr; d.shared_bytes = 0;
+  }
+  if (!d.shared_frame) {
+    RR_CUDA(cudaMalloc(&d.shared_frame, bytes));
+    d.shared_bytes = bytes;
+  }
+  d.shared_w = width; d.shared_h = height;
   cudaIpcMemHandle_t hq, hf;
   RR_CUDA(cudaIpcGetMemHandle(&hq, d.queue));
-  RR_CUDA(cudaIpcGetMemHandle(&hf, d.frame));
+  RR_CUDA(cudaIpcGetMemHandle(&hf, d.shared_frame));
   memcpy(queue_handle, &hq, sizeof(hq));
   memcpy(frame_handle, &hf, sizeof(hf));
   d.shared_queue = d.queue;
-  d.shared_frame = d.frame;
   d.shared_imported = false;
+  d.shared_epoch = 0;
+  RR_CUDA(cudaMemset(d.shared_queue, 0, sizeof(unsigned long long)));
   return RR_OK;
 }
 
@@ -1217,13 +1318,14 @@ int rr_queue_import(rr_ctx* ctx, uint32_t width, uint32_t height, const uint8_t*
                     const uint8_t* frame_handle) {
   if (!ctx || !queue_handle || !frame_handle) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
   Device& d = ctx->dev[0];
+  if (width == 0 || height == 0 || (uint64_t)width * height > 0x7fffffffull) return fail(RR_ERR_INVALID_ARGUMENT, "bad image size");
   RR_CUDA(cudaSetDevice(d.ordinal));
-  int rc = ensure_frame(d, width, height, false);
-  if (rc) return rc;
   if (d.shared_imported) {
     if (d.shared_queue) cudaIpcCloseMemHandle(d.shared_queue);
     if (d.shared_frame) cudaIpcCloseMemHandle(d.shared_frame);
-    d.shared_queue = nullptr; d.shared_frame = nullptr; d.shared_imported = false;
+    d.shared_queue = nullptr; d.shared_frame = nullptr; d.shared_imported = false; d.shared_bytes = 0;
+  } else if (d.shared_frame) {
+    return fail(RR_ERR_INVALID_ARGUMENT, "this context has exported a queue; import into a context of its own");
   }
   cudaIpcMemHandle_t hq, hf;
   memcpy(&hq, queue_handle, sizeof(hq));
@@ -1233,6 +1335,9 @@ int rr_queue_import(rr_ctx* ctx, uint32_t width, uint32_t height, const uint8_t*
   RR_CUDA(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
   d.shared_queue = (unsigned long long*)pq;
   d.shared_frame = (uint8_t*)pf;
+  d.shared_bytes = (size_t)width * height * 4;  // as declared by the caller: must be the exported size
+  d.shared_w = width; d.shared_h = height;
+  d.shared_epoch = 0;
   d.shared_imported = true;
   return RR_OK;
 }
@@ -1242,7 +1347,9 @@ int rr_queue_reset(rr_ctx* ctx) {
   Device& d = ctx->dev[0];
   if (!d.shared_queue || d.shared_imported) return fail(RR_ERR_INVALID_ARGUMENT, "only the exporting rank resets the queue");
   RR_CUDA(cudaSetDevice(d.ordinal));
-  RR_CUDA(cudaMemset(d.shared_queue, 0, sizeof(unsigned long long)));
+  // the epoch of the frame that follows: this rank's next rr_render_shared is its (shared_epoch + 1)-th
+  const unsigned long long word = (unsigned long long)((d.shared_epoch + 1u) & 0xffffu) << RR_QUEUE_EPOCH_SHIFT;
+  RR_CUDA(cudaMemcpy(d.shared_queue, &word, sizeof(word), cudaMemcpyHostToDevice));
   return RR_OK;
 }
 
@@ -1265,15 +1372,16 @@ int rr_frame_device_ptr(rr_ctx* ctx, uint64_t* ptr_out, uint64_t* bytes_out) {
   return RR_OK;
 }
 
-// ---- probes used by the parity tests (not part of include/rr_api.h) ------------
+// ---- probes used by the parity tests (include/rr_api.h "Test hooks") ------------
 int rr_probe_math(int fn, const float* x, const float* y, float* out, uint64_t n) {
+  if (!x || !out) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
   float *dx = nullptr, *dy = nullptr, *dout = nullptr;
-  RR_CUDA(cudaMalloc(&dx, n * 4 + 4));
-  RR_CUDA(cudaMalloc(&dy, n * 4 + 4));
-  RR_CUDA(cudaMalloc(&dout, n * 4 + 4));
-  RR_CUDA(cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice));
-  RR_CUDA(cudaMemcpy(dy, y ? y : x, n * 4, cudaMemcpyHostToDevice));
-  cudaError_t e = launch_math_probe(fn, dx, dy, dout, n, 0);
+  cudaError_t e = cudaMalloc(&dx, n * 4 + 4);
+  if (e == cudaSuccess) e = cudaMalloc(&dy, n * 4 + 4);
+  if (e == cudaSuccess) e = cudaMalloc(&dout, n * 4 + 4);
+  if (e == cudaSuccess) e = cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dy, y ? y : x, n * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_math_probe(fn, dx, dy, dout, n, 0);
   if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost);
   cudaFree(dx); cudaFree(dy); cudaFree(dout);
   if (e != cudaSuccess) return cuda_fail(e, "rr_probe_math");
@@ -1281,15 +1389,68 @@ int rr_probe_math(int fn, const float* x, const float* y, float* out, uint64_t n
 }
 
 int rr_probe_rng(uint32_t pixel, int32_t frame, uint32_t* out_u32_8, float* out_f32_9) {
+  if (!out_u32_8 || !out_f32_9) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
   uint32_t* du = nullptr;
   float* df = nullptr;
-  RR_CUDA(cudaMalloc(&du, 8 * 4));
-  RR_CUDA(cudaMalloc(&df, 9 * 4));
-  cudaError_t e = launch_rng_probe(pixel, frame, du, df, 0);
+  cudaError_t e = cudaMalloc(&du, 8 * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&df, 9 * 4);
+  if (e == cudaSuccess) e = launch_rng_probe(pixel, frame, du, df, 0);
   if (e == cudaSuccess) e = cudaMemcpy(out_u32_8, du, 32, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaMemcpy(out_f32_9, df, 36, cudaMemcpyDeviceToHost);
   cudaFree(du); cudaFree(df);
   if (e != cudaSuccess) return cuda_fail(e, "rr_probe_rng");
+  return RR_OK;
+}
+
+int rr_probe_peak(int what, float* value_out) {
+  if (!value_out) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
+  *value_out = 0.0f;
+  int dev = 0;
+  RR_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  RR_CUDA(cudaGetDeviceProperties(&prop, dev));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  void* buf = nullptr;
+  unsigned* out = nullptr;
+  cudaError_t e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) e = cudaMalloc(&out, 16);
+  float best_ms = 1e30f;
+  double work = 0.0;
+  if (what == 0) {  // FP32 FMA: 8 CTAs of 256 threads per SM, 8 chains per thread
+    const int iters = 1 << 14, grid = prop.multiProcessorCount * 8;
+    work = (double)grid * 256 * iters * 8 * 2;  // flop
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k) {
+      cudaEventRecord(e0, 0);
+      k_peak_fma<<<grid, 256>>>(reinterpret_cast<float*>(out), iters);
+      cudaEventRecord(e1, 0);
+      e = cudaEventSynchronize(e1);
+      float ms = 0.0f;
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+      if (k > 0 && ms < best_ms) best_ms = ms;
+    }
+    if (e == cudaSuccess) *value_out = (float)(work / (best_ms * 1e-3) / 1e12);  // TFLOP/s
+  } else {  // L2 read bandwidth: a 32 MB buffer read 64 times with 16-byte loads
+    const size_t bytes = 32u << 20;
+    const int passes = 64;
+    if (e == cudaSuccess) e = cudaMalloc(&buf, bytes);
+    if (e == cudaSuccess) e = cudaMemset(buf, 1, bytes);
+    work = (double)bytes * passes;
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k) {
+      cudaEventRecord(e0, 0);
+      k_peak_l2<<<prop.multiProcessorCount * 8, 256>>>(reinterpret_cast<const uint4*>(buf), bytes / 16, passes, out);
+      cudaEventRecord(e1, 0);
+      e = cudaEventSynchronize(e1);
+      float ms = 0.0f;
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+      if (k > 0 && ms < best_ms) best_ms = ms;
+    }
+    if (e == cudaSuccess) *value_out = (float)(work / (best_ms * 1e-3) / 1e9);  // GB/s
+  }
+  cudaFree(buf); cudaFree(out);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (e != cudaSuccess) return cuda_fail(e, "rr_probe_peak");
   return RR_OK;
 }
 

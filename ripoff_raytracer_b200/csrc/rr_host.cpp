@@ -175,18 +175,22 @@ void obj_pass2(const char* data, size_t size, ObjChunk& c, bool strict, const fl
     const char* e = nl ? nl : data + size;
     const long nv = (long)(c.base_v + face.lv), nn = (long)(c.base_n + face.ln);  // defined before this line
     if (strict) {
-      // three corners `v/vt/vn` or `v//vn` (src/readobj.hpp:307-312); a 4th corner is ignored
+      // three corners, ALL `v/vt/vn` or ALL `v//vn`: the reference tries one sscanf pattern per form
+      // (src/readobj.hpp:307-312), so a line that mixes the two is an "Unsupported face format"; a 4th corner is ignored
       p += 2;
       long v[3], n[3];
       bool ok = true;
+      int form = -1;  // 0: v//vn, 1: v/vt/vn
       for (int k = 0; k < 3 && ok; ++k) {
         long vt;
         ok = parse_long(p, e, v[k]) && p < e && *p == '/';
         if (!ok) break;
         ++p;
+        int f = 0;
         if (p < e && *p == '/') ++p;
-        else { ok = parse_long(p, e, vt) && p < e && *p == '/'; if (!ok) break; ++p; }
-        ok = parse_long(p, e, n[k]);
+        else { f = 1; ok = parse_long(p, e, vt) && p < e && *p == '/'; if (!ok) break; ++p; }
+        if (form < 0) form = f;
+        ok = f == form && parse_long(p, e, n[k]);
       }
       if (!ok) continue;
       for (int k = 0; k < 3; ++k) {

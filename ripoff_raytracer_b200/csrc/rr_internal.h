@@ -11,6 +11,8 @@
 #define RR_MAX_DEPTH 64               // deepest binary hierarchy accepted (the reference's BVHStackSize, src/Trace.cl:2)
 #define RR_STACK_MAX 200               // traversal stack entries at most: a 4-wide node pushes up to 3 per level
 #define RR_MAX_INVISIBLE_PASSES 256u   // pass-throughs of Invisible surfaces per path before it is ended
+#define RR_MAX_BOUNCES 0x7fffffu       // the bounce counter shares a 32-bit slot word with the 9-bit pass counter
+#define RR_QUEUE_EPOCH_SHIFT 48        // tile counter word: frame epoch (16 bits) << 48 | tiles popped
 #define RR_DIRECT_MAX 4               // segments this small are tested without a hierarchy
 #define RR_TILE_W 8                   // default work tile: 8 x 4 pixels = one warp
 #define RR_TILE_H 4
@@ -90,7 +92,9 @@ struct DCamera {
 };
 
 struct Counters {
-  unsigned long long rays, rays_reused, box_tests, tri_tests, sphere_tests, tiles;
+  unsigned long long rays, box_tests, tri_tests, sphere_tests, tiles;
+  unsigned long long stack_overflows;  // node steps that could not push their far children (must stay 0: the stacks are sized per scene)
+  unsigned long long queue_errors;     // tile pops that met a counter of another frame (rr_queue_reset during a frame)
   unsigned long long phase_runs[5], phase_lanes[5];  // scheduler statistics (instrumented kernel only)
 };
 
@@ -133,7 +137,8 @@ struct RenderParams {
   uint32_t stack_entries;            // 3 per level of the deepest 4-wide hierarchy + slack
   uint32_t* cold;                    // cold slot words, RR_COLD_WORDS * RR_POOL per warp (scratch)
   uint32_t stack_warps;              // warps the scratch was sized for
-  unsigned long long* queue;         // tile counter (may live in a peer GPU's memory)
+  unsigned long long* queue;         // tile counter (may live in a peer GPU's memory): frame epoch << 48 | next tile
+  uint32_t queue_epoch;              // epoch this launch expects in the counter (0 for a context-local queue)
   uint8_t* frame;                    // RGBA8 (may live in a peer GPU's memory)
   float* radiance;                   // optional, local
   Counters* counters;
@@ -168,6 +173,13 @@ __host__ __device__ inline float box_delta(const float* seg_box6) {
     if (a > m && a < 3.0e38f) m = a;
   }
   return m * 3.814697265625e-06f;
+}
+// The per-ray part of the slack: 2^-18 of the largest |origin coordinate| (rr_render.cu slab_slack).
+__host__ __device__ inline float ray_slack(float ox, float oy, float oz) {
+  const float ax = ox < 0.0f ? -ox : ox, ay = oy < 0.0f ? -oy : oy, az = oz < 0.0f ? -oz : oz;
+  float m = ax > ay ? ax : ay;
+  m = m > az ? m : az;
+  return (m < 3.0e38f ? m : 0.0f) * 3.814697265625e-06f;
 }
 void lbvh_free(Lbvh& b);
 

@@ -6,7 +6,7 @@
 // 5 candidate planes x 3 axes, in-place partition of triangleList).  The build
 // is bit-exact against oracle/rr_oracle.c (lbvh_build_segment): identical keys,
 // identical sorted order (stable in the uploaded index), identical topology and
-// boxes -- tests/test_lbvh_parity.py.
+// boxes -- tests/test_gpu_parity.py::test_lbvh_build_order_is_bit_exact (and ::test_full_size_configs_are_bit_exact).
 //
 // Every kernel here is HBM/latency-bound integer and min/max work; nothing is
 // GEMM-shaped.  Compiled with -fmad=false (the key quantisation must round

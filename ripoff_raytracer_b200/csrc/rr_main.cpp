@@ -14,6 +14,7 @@
 // and <dir>/output_<n>.bmp (the numbering render.sh feeds to ffmpeg).  RR_FRAME_TOTAL > 1 averages that many
 // differently seeded frames per image (src/main.cpp:575-582).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -22,6 +23,7 @@
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rr_api.h"
@@ -49,6 +51,43 @@ bool ask_uint(unsigned int* out) {
     return false;
   }
 }
+
+// The progress line of the reference's tile loops (src/image.hpp:316-323, 363-377), same text and the same estimate
+// (remaining = elapsed * (100 / percent - 1)).  The reference prints it from the loop that enqueues one OpenCL launch
+// per tile; here ONE persistent kernel renders the frame while rr_render blocks, so a second host thread polls the
+// device's tile counter (rr_render_progress) and prints the line a few times per second.
+class ProgressLine {
+ public:
+  explicit ProgressLine(rr_ctx* ctx) : ctx_(ctx), start_(std::chrono::high_resolution_clock::now()), thread_([this] { run(); }) {}
+  // joins the poller and prints the closing line of src/image.hpp:343-344 / 376-377
+  void finish(uint64_t tiles_total) {
+    stop_.store(true);
+    thread_.join();
+    std::cout << "\rRendering tile " << tiles_total << " of " << tiles_total << " (100%) " << elapsed_ms() << " ms elapsed; 0 ms remaining"
+              << std::endl;
+  }
+
+ private:
+  unsigned long elapsed_ms() const {
+    return (unsigned long)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::high_resolution_clock::now() - start_).count();
+  }
+  void run() {
+    while (!stop_.load()) {
+      uint64_t done = 0, total = 0;
+      if (rr_render_progress(ctx_, &done, &total) == RR_OK && total > 0 && done > 0) {
+        const double percentCompleted = (double)done / (double)total * 100.0;
+        const unsigned long millisecondsPassed = elapsed_ms();
+        std::cout << "\033[2K\rRendering tile " << done << " of " << total << " (" << percentCompleted << "%) " << millisecondsPassed
+                  << "ms elapsed; " << (unsigned long)(millisecondsPassed * ((100.0 / percentCompleted) - 1.0)) << "ms remaining" << std::flush;
+      }
+      std::this_thread::sleep_for(std::chrono::milliseconds(200));
+    }
+  }
+  rr_ctx* ctx_;
+  std::chrono::high_resolution_clock::time_point start_;
+  std::atomic<bool> stop_{false};
+  std::thread thread_;
+};
 
 }  // namespace
 
@@ -164,9 +203,14 @@ int main() {
   (void)TILE_SIZE;
   // one image: a single frame with seed term 0 (src/image.hpp:228), or FRAME_TOTAL frames seeded 1.. and averaged
   auto render_image = [&](rr_stats* st) {
+    ProgressLine progress(ctx);
+    int rc2;
     if (FRAME_TOTAL > 1)
-      return rr_render_progressive(ctx, &cam, WIDTH, HEIGHT, RAYS_PER_PIXEL, MAX_BOUNCE_COUNT, 1, (uint32_t)FRAME_TOTAL, 0, pixels.data(), st);
-    return rr_render_ex(ctx, &cam, WIDTH, HEIGHT, RAYS_PER_PIXEL, MAX_BOUNCE_COUNT, 0, 0, pixels.data(), nullptr, st, 0);
+      rc2 = rr_render_progressive(ctx, &cam, WIDTH, HEIGHT, RAYS_PER_PIXEL, MAX_BOUNCE_COUNT, 1, (uint32_t)FRAME_TOTAL, 0, pixels.data(), st);
+    else
+      rc2 = rr_render_ex(ctx, &cam, WIDTH, HEIGHT, RAYS_PER_PIXEL, MAX_BOUNCE_COUNT, 0, 0, pixels.data(), nullptr, st, 0);
+    progress.finish(rc2 == RR_OK ? st->tiles / (uint64_t)FRAME_TOTAL : 0);
+    return rc2;
   };
   auto report = [&](const rr_stats& st, double ms) {
     std::cout << "Rendered " << st.tiles << " tiles, " << st.samples << " samples, " << st.rays << " path segments in " << ms

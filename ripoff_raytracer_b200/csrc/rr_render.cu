@@ -24,8 +24,10 @@
 //   * a node step is one 128-byte fetch (a 4-wide node: the binary LBVH node
 //     collapsed with its grandchildren) and four slab tests; a slot may postpone
 //     one leaf and keep walking (speculative traversal);
-//   * the per-path colour state lives in shared memory so that the traversal
-//     fits 64 registers and 32 warps stay resident per SM.
+//   * every warp owns a pool of 96 path slots (one pixel each), three times as many as lanes, so that the phase
+//     that runs finds ~30 ready slots; the hot words of a slot live in shared memory, the words only the shade /
+//     pixel phases touch and the traversal stack below its top in an L2-resident per-warp scratch.  96 registers,
+//     5 CTAs of 4 warps per SM.
 #include <math.h>
 
 #include "rr_internal.h"
@@ -127,14 +129,25 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(xs));
   return r;
 }
+// `ek` is the per-ray slack of slab_slack() below: every slab is widened by it on both sides.
 __device__ __forceinline__ bool box_cull(float lox, float loy, float loz, float hix, float hiy, float hiz, const V3& inv,
-                                         const V3& noi, float tbest, float& tn) {
+                                         const V3& noi, const V3& ek, float tbest, float& tn) {
   const float t0x = __fmaf_rn(lox, inv.x, noi.x), t1x = __fmaf_rn(hix, inv.x, noi.x);
   const float t0y = __fmaf_rn(loy, inv.y, noi.y), t1y = __fmaf_rn(hiy, inv.y, noi.y);
   const float t0z = __fmaf_rn(loz, inv.z, noi.z), t1z = __fmaf_rn(hiz, inv.z, noi.z);
-  tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
-  const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+  tn = fmaxf(fmaxf(fminf(t0x, t1x) - ek.x, fminf(t0y, t1y) - ek.y), fminf(t0z, t1z) - ek.z);
+  const float tf = fminf(fminf(fmaxf(t0x, t1x) + ek.x, fmaxf(t0y, t1y) + ek.y), fmaxf(t0z, t1z) + ek.z);
   return tf >= fmaxf(tn, 0.0f) && tn <= tbest;
+}
+// Per-ray part of the conservative culling slack.  The rounding error of a slab test (and of the triangle test's
+// `origin - A`, src/Trace.cl:283) grows with the ray ORIGIN, not with the box: a box is therefore widened, besides its
+// build-time box_delta, by ray_slack(origin) = 2^-18 of the largest |origin coordinate| in every direction -- in the
+// parametric form of the slab test that is ek = slack * |1/d| per axis (oracle/rr_oracle.c ray_slack states the same
+// bound).  Inside a scene it is of the size of box_delta; it matters for a camera far outside
+// (tests: |origin| / extent up to 10^4) and for meshes re-posed with a small scale (origin / scale).
+__device__ __forceinline__ V3 slab_slack(const V3& o, const V3& inv) {
+  const float s = ray_slack(o.x, o.y, o.z);
+  return mk(s * fabsf(inv.x), s * fabsf(inv.y), s * fabsf(inv.z));
 }
 
 constexpr int32_t NO_PRIM = 0x7fffffff;
@@ -271,10 +284,15 @@ __device__ __noinline__ uint32_t tonemap_rgba(V3 c) {
 // Tiles are numbered row-major.  With a shared counter (possibly in a peer
 // GPU's memory, hence the system-scope atomic) every warp of every GPU pops the
 // next tile; with a static partition rank r renders tiles r, r+world, ...
-__device__ __forceinline__ bool pop_tile(const RenderParams& p, uint32_t& tile) {
+// The counter word is (frame epoch << 48 | tiles popped).  A pop that meets another epoch (rr_queue_reset ran while
+// this launch was still popping, or a rank is a frame behind) takes nothing and is counted: rr_render_shared then
+// fails with RR_ERR_QUEUE instead of rendering a tile of the wrong frame.
+__device__ __forceinline__ bool pop_tile(const RenderParams& p, uint32_t& tile, bool& epoch_error) {
   unsigned long long t = 0;
   if ((threadIdx.x & 31) == 0) t = atomicAdd_system(p.queue, 1ull);
   t = __shfl_sync(0xffffffffu, t, 0);
+  if ((uint32_t)(t >> RR_QUEUE_EPOCH_SHIFT) != p.queue_epoch) { epoch_error = true; return false; }
+  t &= (1ull << RR_QUEUE_EPOCH_SHIFT) - 1ull;
   t = (unsigned long long)p.tile_begin + t * p.tile_stride;
   tile = (uint32_t)t;
   return t < (unsigned long long)p.tiles_x * p.tiles_y;
@@ -303,7 +321,7 @@ enum {
   NW
 };
 enum {
-  C_RNG = 0, C_SAMPLE, C_BOUNCE,                // bounce | passes << 16
+  C_RNG = 0, C_SAMPLE, C_BOUNCE,                // bounce | passes << 23
   C_BPRIM, C_BPX, C_BPY, C_BPZ, C_BNX, C_BNY, C_BNZ,  // primitive, point and normal of the closest hit
   C_LNX, C_LNY, C_LNZ,                          // normal of the closest hit inside the current mesh
   C_THR, C_THR1, C_THR2, C_INC, C_INC1, C_INC2, C_ACC, C_ACC1, C_ACC2, C_PD, C_PD1, C_PD2,
@@ -321,7 +339,7 @@ __device__ __forceinline__ uint32_t ref_slot(int32_t r) { return (uint32_t)(-r) 
 // With a top level (`blocks` != nullptr, more than 32 meshes) the chunk is four blocks of eight meshes and a block
 // whose box the ray misses is skipped.
 __device__ __noinline__ uint32_t scan_meshes_fn(const DMesh* __restrict__ meshes, const float4* __restrict__ blocks, int32_t base,
-                                                int32_t last_mesh, V3 winv, V3 wnoi, float tmax, unsigned* tests) {
+                                                int32_t last_mesh, V3 winv, V3 wnoi, V3 wek, float tmax, unsigned* tests) {
   uint32_t mask = 0;
   const int32_t end = min(base + 32, last_mesh + 1);
   for (int32_t k0 = base; k0 < end; k0 += 8) {
@@ -329,14 +347,14 @@ __device__ __noinline__ uint32_t scan_meshes_fn(const DMesh* __restrict__ meshes
     if (blocks) {
       const float4 blo = __ldg(blocks + 2 * (k0 >> 3)), bhi = __ldg(blocks + 2 * (k0 >> 3) + 1);
       if (tests) ++*tests;
-      if (!box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, winv, wnoi, tmax, tn)) continue;
+      if (!box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, winv, wnoi, wek, tmax, tn)) continue;
     }
     const int32_t e = min(k0 + 8, end);
     if (tests) *tests += (unsigned)(e - k0);
     for (int32_t k = k0; k < e; ++k) {
       const DMesh* M = meshes + k;
       const float4 wlo = __ldg(&M->wmin), whi = __ldg(&M->wmax);
-      const bool hit = box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, tmax, tn);
+      const bool hit = box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, wek, tmax, tn);
       if (hit && !(__float_as_uint(wlo.w) & RR_MF_SKIP)) mask |= 1u << (k - base);
     }
   }
@@ -350,7 +368,7 @@ __device__ __noinline__ uint32_t scan_meshes_fn(const DMesh* __restrict__ meshes
 // every level whose span starts at c (top level first) a box the ray misses skips its whole span; returns the first
 // chunk the ray enters before `tmax`, or a value > last_chunk.  Out of line: scenes with at most 32 meshes never come here.
 __device__ __noinline__ int32_t next_chunk_fn(const float4* __restrict__ tlas, const uint32_t* __restrict__ lv, int32_t c,
-                                              int32_t last_chunk, V3 winv, V3 wnoi, float tmax, unsigned* tests) {
+                                              int32_t last_chunk, V3 winv, V3 wnoi, V3 wek, float tmax, unsigned* tests) {
   const int levels = (int)__ldg(lv);  // lv: level count, then the first box of every level
   while (c <= last_chunk) {
     bool skipped = false;
@@ -361,7 +379,7 @@ __device__ __noinline__ int32_t next_chunk_fn(const float4* __restrict__ tlas, c
       const float4* b = tlas + 2 * ((size_t)__ldg(lv + 1 + l) + (size_t)(c >> (2 * l)));
       const float4 lo = __ldg(b), hi = __ldg(b + 1);
       if (tests) ++*tests;
-      if (!box_cull(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, winv, wnoi, tmax, tn)) { c += span; skipped = true; break; }
+      if (!box_cull(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, winv, wnoi, wek, tmax, tn)) { c += span; skipped = true; break; }
     }
     if (!skipped) break;
   }
@@ -397,6 +415,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   uint32_t n_need = POOL;  // slots waiting for a pixel
   // statistics
   uint32_t n_rays = 0, n_tiles = 0;  // per lane / per warp: far below 2^32 even for an 8K, 1024-spp frame on one GPU
+  uint32_t n_overflow = 0;           // pushes dropped for lack of stack entries: must stay 0 (the host fails the render otherwise)
+  bool epoch_error = false;
   unsigned c_box = 0, c_tri = 0, c_sph = 0;
   unsigned ph_runs[5] = {0, 0, 0, 0, 0}, ph_lanes[5] = {0, 0, 0, 0, 0};
 
@@ -452,9 +472,9 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     return ((cur >= REF_POP && (speculate || pend_cnt == 0)) ? K_T : 0u) | (pend_cnt ? K_L : 0u);
   };
 
-  auto scan_meshes = [&](int32_t base, const V3& winv, const V3& wnoi, float tmax) -> uint32_t {
+  auto scan_meshes = [&](int32_t base, const V3& winv, const V3& wnoi, const V3& wek, float tmax) -> uint32_t {
     unsigned tests = 0;
-    const uint32_t mask = scan_meshes_fn(p.meshes, p.tlas_blocks, base, p.last_mesh, winv, wnoi, tmax, COUNT ? &tests : nullptr);
+    const uint32_t mask = scan_meshes_fn(p.meshes, p.tlas_blocks, base, p.last_mesh, winv, wnoi, wek, tmax, COUNT ? &tests : nullptr);
     if (COUNT) c_box += tests;
     return mask;
   };
@@ -497,19 +517,19 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   // Enters the next candidate mesh (src/Trace.cl:444-463): world box against the closest hit so far,
   // WorldToLocalRay, root box.  Returns the slot's new key (traversal started, or K_H: no candidate left).
   // One step of the search: false = look at the next candidate, true = done (`key` set).
-  auto enter_step = [&](const V3& winv, const V3& wnoi, uint32_t& key) -> bool {
+  auto enter_step = [&](const V3& winv, const V3& wnoi, const V3& wek, uint32_t& key) -> bool {
     {
       if (cand == 0) {
         int32_t base = (m & ~31) + 32;
         if (base > p.last_mesh) { key = K_H; return true; }
         if (p.tlas) {  // skip the chunks (and groups of chunks) the ray does not enter before the closest hit so far
           unsigned tests = 0;
-          base = next_chunk_fn(p.tlas, p.tlas_levels, base >> 5, p.last_mesh >> 5, winv, wnoi, best_dst, COUNT ? &tests : nullptr) << 5;
+          base = next_chunk_fn(p.tlas, p.tlas_levels, base >> 5, p.last_mesh >> 5, winv, wnoi, wek, best_dst, COUNT ? &tests : nullptr) << 5;
           if (COUNT) c_box += tests;
           if (base > p.last_mesh) { key = K_H; return true; }
         }
         m = base;
-        cand = scan_meshes(base, winv, wnoi, best_dst);
+        cand = scan_meshes(base, winv, wnoi, wek, best_dst);
         return false;
       }
       const int k = __ffs((int)cand) - 1;
@@ -523,9 +543,10 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       float tn;
       if (best_dst < INFINITY) {  // a hit exists: the box may now lie behind it
         if (COUNT) c_box++;
-        if (!box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, best_dst, tn)) return false;
+        if (!box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, wek, best_dst, tn)) return false;
       }
       mflags = __float_as_uint(wlo.w);
+      V3 lek = wek;
       if (mflags & RR_MF_SPHERES) {
         lo = origin; ld = dir; linv = winv; lnoi = wnoi;
       } else {
@@ -545,9 +566,10 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         ld = normalize(ld);
         linv = mk(rcp_approx(ld.x), rcp_approx(ld.y), rcp_approx(ld.z));
         lnoi = mk(-(lo.x * linv.x), -(lo.y * linv.y), -(lo.z * linv.z));
+        lek = slab_slack(lo, linv);
       }
       if (COUNT) c_box++;
-      if (!box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, linv, lnoi, INFINITY, tn)) return false;
+      if (!box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, linv, lnoi, lek, INFINITY, tn)) return false;
       const uint32_t first = __float_as_uint(blo.w), count = __float_as_uint(bhi.w);
       // The sphere set lives in world space and is the last entry in the tie order (highest mesh index): a sphere at or
       // beyond the closest hit so far can never win, so its walk starts with that distance as the bound.
@@ -566,9 +588,9 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       return true;
     }
   };
-  auto enter_next_mesh = [&](const V3& winv, const V3& wnoi) -> uint32_t {
+  auto enter_next_mesh = [&](const V3& winv, const V3& wnoi, const V3& wek) -> uint32_t {
     uint32_t key = 0;
-    while (!enter_step(winv, wnoi, key)) {}
+    while (!enter_step(winv, wnoi, wek, key)) {}
     return key;
   };
   // what setup and shade write back after finish_mesh / enter_next_mesh
@@ -615,7 +637,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     PST3(W_DX, s, dir);
     const V3 winv = mk(rcp_approx(dir.x), rcp_approx(dir.y), rcp_approx(dir.z));
     const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
-    PW(W_CAND, s) = scan_meshes(0, winv, wnoi, INFINITY);
+    PW(W_CAND, s) = scan_meshes(0, winv, wnoi, slab_slack(origin, winv), INFINITY);
     PW(W_M, s) = 1u;  // chunk 0, no backface flag
     PSF(W_BDST, s, INFINITY);
     PW(W_BMAT, s) = 0u;
@@ -673,6 +695,9 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       } else {
         cur = REF_END; sp = 0; pend_cnt = 0;
       }
+      // the per-ray slack (slab_slack) is folded into the offsets: entry planes move towards the origin, exit planes away
+      const V3 lek = slab_slack(lo, linv);
+      const V3 nnoi = lnoi - lek, fnoi = lnoi + lek;
       // which quad of a node holds the entry / exit plane of each axis (node layout: min.x min.y min.z max.x max.y max.z)
       const int qnx = linv.x < 0.0f ? 3 : 0, qny = linv.y < 0.0f ? 4 : 1, qnz = linv.z < 0.0f ? 5 : 2;
       const int qfx = 3 - qnx, qfy = 5 - qny, qfz = 7 - qnz;
@@ -723,8 +748,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             // sort key of a child: entry distance (clamped at 0, two low mantissa bits dropped) | child number;
             // a child the ray misses (or an unused NaN box) sorts last
             auto child_key = [&](float pnx, float pny, float pnz, float pfx, float pfy, float pfz, uint32_t c) -> uint32_t {
-              const float tn = fmaxf(fmaxf(__fmaf_rn(pnx, linv.x, lnoi.x), __fmaf_rn(pny, linv.y, lnoi.y)), __fmaf_rn(pnz, linv.z, lnoi.z));
-              const float tf = fminf(fminf(__fmaf_rn(pfx, linv.x, lnoi.x), __fmaf_rn(pfy, linv.y, lnoi.y)), __fmaf_rn(pfz, linv.z, lnoi.z));
+              const float tn = fmaxf(fmaxf(__fmaf_rn(pnx, linv.x, nnoi.x), __fmaf_rn(pny, linv.y, nnoi.y)), __fmaf_rn(pnz, linv.z, nnoi.z));
+              const float tf = fminf(fminf(__fmaf_rn(pfx, linv.x, fnoi.x), __fmaf_rn(pfy, linv.y, fnoi.y)), __fmaf_rn(pfz, linv.z, fnoi.z));
               const float t0 = fmaxf(tn, 0.0f);
               return (tf >= t0 && tn <= lt) ? ((__float_as_uint(t0) & ~3u) | c) : 0xffffffffu;
             };
@@ -753,7 +778,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             }
             // misses sort last, so the children to push are a suffix of the hits: farthest first, the nearest of
             // them ends up as the (register-resident) top; the previous top is spilled once
-            if (hits >= 2 && sp + hits - 1 <= (int)p.stack_entries) {
+            if (hits >= 2 && sp + hits - 1 > (int)p.stack_entries) n_overflow++;  // cannot happen (3 entries per wide level + 4); counted, not hidden
+            else if (hits >= 2) {
               uint2* const w = stk + sp * POOL;  // one address; the stores below use constant offsets from it
               if (sp > 0) w[-POOL] = top;
               if (hits >= 3) w[0] = hits == 4 ? make_uint2((uint32_t)r3, k3 & ~3u) : make_uint2((uint32_t)r2, k2 & ~3u);
@@ -895,7 +921,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
         load_ray_state();
         finish_mesh();  // nothing to finish for a new ray (no local hit)
-        const uint32_t key = enter_next_mesh(winv, wnoi);
+        const uint32_t key = enter_next_mesh(winv, wnoi, slab_slack(origin, winv));
         store_ray_state(key);
       }
     } else if (phase == PH_SHADE) {
@@ -920,8 +946,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
           rng = CW(C_RNG, s);
           sample = CW(C_SAMPLE, s);
           const uint32_t bw = CW(C_BOUNCE, s);
-          bounce = bw & 0xffffu;
-          passes = bw >> 16;
+          bounce = bw & RR_MAX_BOUNCES;
+          passes = bw >> 23;
           SceneHit hit;
           hit.did = best_dst < INFINITY;
           hit.dst = best_dst;
@@ -963,7 +989,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         } else {  // next segment: the setup phase collects its candidate meshes
           CW(C_RNG, s) = rng;
           CW(C_SAMPLE, s) = sample;
-          CW(C_BOUNCE, s) = bounce | (passes << 16);
+          CW(C_BOUNCE, s) = bounce | (passes << 23);  // bounce <= max_bounces <= RR_MAX_BOUNCES, passes <= 257
           store_new_ray();
         }
       }
@@ -979,7 +1005,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         if (tile_next >= tile_pixels) {
           if (queue_empty) break;
           uint32_t tile;
-          if (!pop_tile(p, tile)) { queue_empty = true; break; }
+          if (!pop_tile(p, tile, epoch_error)) { queue_empty = true; break; }
           n_tiles++;
           tile_x0 = (tile % p.tiles_x) * p.tile_w;
           tile_y0 = (tile / p.tiles_x) * p.tile_h;
@@ -1036,9 +1062,12 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   unsigned long long r = n_rays;  // summed over the warp in 64 bits
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) r += __shfl_xor_sync(full, r, off);
+  const unsigned ovf = __reduce_add_sync(full, n_overflow);
   if (lane == 0) {
     atomicAdd(&p.counters->rays, r);
     atomicAdd(&p.counters->tiles, (unsigned long long)n_tiles);
+    if (ovf) atomicAdd(&p.counters->stack_overflows, (unsigned long long)ovf);
+    if (epoch_error) atomicAdd(&p.counters->queue_errors, 1ull);
   }
   if (COUNT) {
     unsigned long long b = c_box, t = c_tri, sq = c_sph;
@@ -1101,7 +1130,7 @@ size_t render_stack_bytes_per_warp(uint32_t stack_entries) { return (size_t)stac
 size_t render_cold_bytes_per_warp() { return (size_t)NC * POOL * sizeof(uint32_t); }
 int render_max_warps_per_sm() { return (RR_MIN_CTAS + 1) * WARPS; }  // the launch clamps its grid to this
 
-// ---- probes for the bit-level parity tests (tests/test_math_parity.py) ---------
+// ---- probes for the bit-level parity tests (rr_probe_math / rr_probe_rng, tests/test_gpu_parity.py) ---------
 __global__ void k_math_probe(int fn, const float* x, const float* y, float* out, uint64_t n) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -6,6 +6,7 @@ import pytest
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(Path(__file__).resolve().parent))  # tests/cases.py
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
 
@@ -21,6 +22,13 @@ def golden_small():
 @pytest.fixture(scope="session")
 def golden_wide():
     return dict(np.load(GOLDEN / "default_wide.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_zoo():
+    """Checker / Glassy / OneSided / specular meshes with pitch, yaw, roll and scale, rendered by the compiled
+    reference with its own SAH hierarchy (tests/golden/make_golden.py zoo)."""
+    return dict(np.load(GOLDEN / "zoo_ref.npz"))
 
 
 @pytest.fixture(scope="session")

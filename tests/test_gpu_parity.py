@@ -174,8 +174,9 @@ def test_lbvh_build_order_is_bit_exact(renderer, golden_wide, case):
     assert np.array_equal(got["bounds"][used], want["bounds"][used])
 
 
-def test_primary_hits_bit_exact_vs_oracle_and_reference(renderer, golden_small):
-    g = golden_small
+@pytest.mark.parametrize("which", ["golden_small", "golden_zoo"])
+def test_primary_hits_bit_exact_vs_oracle_and_reference(renderer, which, request):
+    g = request.getfixturevalue(which)
     W, H = int(g["W"]), int(g["H"])
     renderer.upload_arrays(g["tris"], g["meshes"], g["ranges"])
     mesh, prim, dst = renderer.primary_hits(g["cam"], W, H)
@@ -185,6 +186,8 @@ def test_primary_hits_bit_exact_vs_oracle_and_reference(renderer, golden_small):
     hit = g["primary_hit"]
     assert np.array_equal(mesh >= 0, hit[..., 0] > 0)
     assert np.array_equal(bits(dst)[mesh >= 0], bits(hit[..., 1])[mesh >= 0])
+    # ... and the material type / back-face flag the reference attached to the hit (src/Trace.cl:465-481)
+    assert np.array_equal(g["meshes"]["material"]["type"][mesh[mesh >= 0]], g["primary_flags"][mesh >= 0] >> 8)
 
 
 def test_primary_hits_full_default_scene(renderer, knight_obj):
@@ -199,7 +202,7 @@ def test_primary_hits_full_default_scene(renderer, knight_obj):
     assert (mesh == 7).sum() > 5000  # the OBJ mesh is visible
 
 
-@pytest.mark.parametrize("which", ["golden_small", "golden_wide"])
+@pytest.mark.parametrize("which", ["golden_small", "golden_wide", "golden_zoo"])
 def test_images_match_reference_golden(renderer, which, request):
     """L0/L1/L2 of the parity ladder against the REFERENCE's outputs: bit-exact 8-bit image and radiance."""
     g = request.getfixturevalue(which)
@@ -245,7 +248,7 @@ def test_default_scene_image_and_counters_vs_oracle(renderer, knight_obj):
         # identical paths => identical segment count.  Box/triangle test counts are NOT compared: the kernel
         # walks the hierarchy speculatively (postponed leaves), so it does a little more culling work than
         # the oracle's strictly ordered walk -- the result does not depend on the order (delta-inflated boxes).
-        assert st["rays"] + st["rays_reused"] == ost["rays"]
+        assert st["rays"] == ost["rays"]
         assert ost["tri_tests"] <= st["tri_tests"] * 2 and st["tri_tests"] <= ost["tri_tests"] * 2
         assert sum(st["phase_runs"]) > 0 and all(l <= 32 * r for l, r in zip(st["phase_lanes"], st["phase_runs"]))
 
@@ -266,7 +269,7 @@ def test_material_zoo_with_instances_and_spheres(renderer):
         got, grad, st = renderer.render(cam, W, H, spp, bounces, radiance=True, count_tests=True)
         assert_images_equal(got, want, f"zoo spp={spp} b={bounces}")
         assert np.array_equal(bits(grad), bits(wrad))
-        assert st["rays"] + st["rays_reused"] == ost["rays"]
+        assert st["rays"] == ost["rays"]
 
 
 def test_sphere_field_matches_oracle(renderer):
@@ -665,3 +668,108 @@ def test_many_instances_top_level_is_bit_exact(count):
     ren.close()
     wrad2 = Oracle(t, m2, r, sp).render(wl.cam, W, H, 2, 6, radiance=True, threads=16)[1]
     assert np.array_equal(bits(grad2), bits(wrad2))
+
+
+@pytest.mark.parametrize("scale", [1.0, 0.01])
+@pytest.mark.parametrize("ratio", [1e2, 1e3, 1e4])
+def test_far_origin_is_bit_exact(renderer, ratio, scale):
+    """camera 10^2 .. 10^4 mesh extents away (and the same with scale 0.01, i.e. a mesh-local origin
+    100 times further out).  The GPU's FMA-form slab tests with an approximate reciprocal stay conservative through the
+    per-ray slack (rr_render.cu slab_slack): primary hits and radiance equal the oracle's, whose walk equals brute force
+    (tests/test_oracle.py::test_far_origin_hierarchy_only_culls)."""
+    from cases import far_origin_case
+
+    t, m, r, cam, W, H = far_origin_case(ratio, scale)
+    renderer.upload_arrays(t, m, r)
+    o = Oracle(t, m, r)
+    mesh, prim, dst = renderer.primary_hits(cam, W, H)
+    om, op, od = o.primary(cam, W, H)
+    assert (om >= 0).sum() > 5000
+    assert np.array_equal(mesh, om) and np.array_equal(prim, op) and np.array_equal(bits(dst), bits(od))
+    got, grad, st = renderer.render(cam, W, H, 2, 6, radiance=True)
+    want, wrad, ost = o.render(cam, W, H, 2, 6, radiance=True)
+    assert st["rays"] == ost["rays"]
+    assert np.array_equal(bits(grad), bits(wrad)) and np.array_equal(got, want)
+
+
+# ------------------------------------------------- full-size BASELINE configurations --
+def _full_size_check(wl, W, H, spp, label):
+    """LBVH build order (triangle and sphere hierarchies), primary hits and multi-bounce radiance of an UNREDUCED
+    BASELINE.json scene against the oracle -- the scene `bench.py` measures, not a scaled-down copy of it."""
+    t, m, r, sp = wl.scene.arrays()
+    ren = rr.Renderer()
+    ren.upload(wl.scene)
+    o = Oracle(t, m, r, sp)
+    for which in ((0, 1) if len(sp) else (0,)):
+        got, want = ren.bvh(which), o.lbvh(which)
+        for key in ("codes", "order", "left", "right", "parent", "bounds"):
+            assert np.array_equal(got[key], want[key]), f"{label}: LBVH {which} {key}"
+    mesh, prim, dst = ren.primary_hits(wl.cam, W, H)
+    om, op, od = o.primary(wl.cam, W, H, threads=16)
+    assert np.array_equal(mesh, om) and np.array_equal(prim, op) and np.array_equal(bits(dst), bits(od)), f"{label}: primary hits"
+    got, grad, st = ren.render(wl.cam, W, H, spp, wl.bounces, radiance=True, count_tests=True)
+    ren.close()
+    want, wrad, ost = o.render(wl.cam, W, H, spp, wl.bounces, radiance=True, threads=16)
+    assert st["rays"] == ost["rays"] and st["stack_overflows"] == 0
+    assert np.array_equal(bits(grad), bits(wrad)), f"{label}: radiance"
+    assert_images_equal(got, want, label)
+    return len(t), st
+
+
+def test_full_size_c4_is_bit_exact():
+    """BASELINE configs[3] at full size (1 012 014 triangles + 256 spheres: the bench scene, with its deep LBVH,
+    duplicate Morton keys and per-scene stack sizing), 480x270: build order, primary hits, 1 spp x 50 bounces."""
+    from ripoff_raytracer_b200 import workloads
+
+    wl = workloads.c4_mixed1m(width=480, height=270, spp=1)
+    n, st = _full_size_check(wl, 480, 270, 1, "C4 full size")
+    assert n == 1_012_014 and st["rays"] > 500_000
+
+
+def test_full_size_c3_is_bit_exact():
+    """BASELINE configs[2] at full size (81 934 triangles, mesh scaled 0.5 and rotated), 480x270, 2 spp x 50 bounces."""
+    from ripoff_raytracer_b200 import workloads
+
+    wl = workloads.c3_mesh100k(width=480, height=270, spp=2)
+    n, _ = _full_size_check(wl, 480, 270, 2, "C3 full size")
+    assert n == 81_934
+
+
+def test_full_size_c2_is_bit_exact():
+    """BASELINE configs[1] at full size (1 024 spheres + two quads), 480x270, 4 spp x 8 bounces."""
+    from ripoff_raytracer_b200 import workloads
+
+    wl = workloads.c2_spheres(width=480, height=270, spp=4)
+    _full_size_check(wl, 480, 270, 4, "C2 full size")
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("RR_TEST_C5"), reason="10 M triangles: ~1 GB of arrays, minutes of scene generation; set RR_TEST_C5=1 (log of one run: profiles/parity_r02_c5_full_size.log)")
+def test_full_size_c5_build_order_and_primary_hits():
+    """BASELINE configs[4] (10 192 014 triangles + 256 spheres): LBVH build order and primary hits vs the oracle."""
+    from ripoff_raytracer_b200 import workloads
+
+    wl = workloads.c5_mesh10m(width=480, height=270, spp=1)
+    n, _ = _full_size_check(wl, 480, 270, 1, "C5 full size")
+    assert n == 10_192_014
+
+
+# ------------------------------------------------- one process per GPU: shared queue over CUDA IPC --
+def test_two_processes_share_queue_and_frame_over_ipc(knight_obj, tmp_path):
+    """What `bench.py --gpus N` runs and SCALE measures: one process per GPU, rank 0 exports the tile counter and the
+    frame (rr_queue_export), the others attach over CUDA IPC and pop / store over NVLink.  The gathered frame must be
+    the single-GPU frame bit for bit and every tile must have been rendered exactly once.  Also: a reset that
+    overtakes the protocol, and a frame larger than the exported one, are reported, not painted."""
+    if _device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    worker = Path(__file__).resolve().parent / "ipc_worker.py"
+    port = 29500 + (__import__("os").getpid() % 500)
+    procs = [subprocess.Popen([sys.executable, str(worker), str(rank), "2", str(port), str(knight_obj), str(tmp_path)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for rank in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for rank, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {rank}:\n{out}"
+    assert "frame_equal=True" in outs[0] and "tiles_ok=True" in outs[0] and "misuse_reported=True" in outs[0], outs[0]

@@ -55,6 +55,8 @@ def test_obj_loader_dialects_and_bad_faces(tmp_path):
         "f 1//1 2//1 4//1 3//1\n"   # quad: 4th corner dropped (src/readobj.hpp:307-312)
         "f 1 2 3\n"                 # unsupported: skipped
         "f 1//1 2//1 9//1\n"        # out of bounds: skipped
+        "f 1//1 2/7/1 3//1\n"       # mixed corner forms: neither sscanf pattern of the reference matches -> skipped
+        "f 1/7/1 2//1 3/9/1\n"      # same
     )
     s = rr.Scene()
     mesh, rng = s.load_obj(p)

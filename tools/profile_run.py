@@ -32,7 +32,7 @@ for _ in range(a.frames):
         _, _, st = r.render(wl.cam, wl.width, wl.height, wl.spp, wl.bounces, count_tests=True)
     else:
         st = r.render_device(wl.cam, wl.width, wl.height, wl.spp, wl.bounces)
-    rays = st["rays"] + st["rays_reused"]
+    rays = st["rays"]
     st["mrays_s"] = rays / st["render_ms"] / 1e3
     st["msamples_s"] = st["samples"] / st["render_ms"] / 1e3
     print(json.dumps(st))
