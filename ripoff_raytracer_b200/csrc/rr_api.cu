@@ -117,6 +117,9 @@ struct Device {
   Lbvh tb, sb;
   float4 *tri_geom = nullptr, *tri_nrm = nullptr, *sph_geom = nullptr;
   float4* nodes = nullptr;  // triangle hierarchies, then the sphere hierarchy
+  float4* top_nodes = nullptr;  // RR_TOP_STAGE: copies of the top nodes of the largest hierarchy
+  uint32_t top_count = 0;
+  int32_t top_root = -1;
   DMesh* meshes = nullptr;
   DMaterial* materials = nullptr;
   // inputs of k_prepare_meshes, kept so that rr_update_meshes can re-pose the scene without a rebuild
@@ -355,6 +358,7 @@ static void free_scene(Device& d) {
   cudaSetDevice(d.ordinal);
   dev_free(d.tris); dev_free(d.spheres); dev_free(d.tri_box); dev_free(d.sph_box);
   dev_free(d.tri_geom); dev_free(d.tri_nrm); dev_free(d.sph_geom); dev_free(d.meshes); dev_free(d.materials);
+  dev_free(d.top_nodes); d.top_nodes = nullptr; d.top_count = 0; d.top_root = -1;
   dev_free(d.nodes); dev_free(d.meshes_in); dev_free(d.mesh_seg); dev_free(d.mesh_pos); dev_free(d.tlas_blocks); dev_free(d.tlas_levels);
   d.meshes_in = nullptr; d.mesh_seg = nullptr; d.mesh_pos = nullptr; d.tlas_blocks = nullptr; d.tlas = nullptr; d.tlas_levels = nullptr;
   d.tris = nullptr; d.spheres = nullptr; d.tri_box = nullptr; d.sph_box = nullptr;
@@ -370,7 +374,7 @@ struct SegPlan {
 
 // Argument checks shared by the three upload entry points.
 static int check_upload_counts(size_t n_tris, size_t n_meshes, size_t n_spheres) {
-  if (n_tris >= 0x7fffffffull || n_spheres >= 0x7fffffffull) return fail(RR_ERR_INVALID_ARGUMENT, "too many primitives (31-bit indices)");
+  if (n_tris >= RR_MAX_PRIMS || n_spheres >= RR_MAX_PRIMS) return fail(RR_ERR_INVALID_ARGUMENT, "too many primitives (a leaf reference keeps the slot in 29 bits)");
   if (n_meshes >= 0x1fffff00ull) return fail(RR_ERR_INVALID_ARGUMENT, "too many meshes (the slot word keeps mesh + 1 in 29 bits)");
   return RR_OK;
 }
@@ -661,13 +665,16 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
   if (n_spheres) RR_CUDA(cudaMemcpyAsync(d.spheres, spheres, n_spheres * sizeof(rr_sphere), cudaMemcpyHostToDevice, st));
   RR_CUDA(cudaEventRecord(d.ev0, st));
   RR_CUDA(launch_tri_boxes(d.tris, n_tris, d.tri_box, st));
-  RR_CUDA(lbvh_build(d.tb, d.tri_box, n_tris, plan.first.data(), plan.count.data(), (uint32_t)plan.first.size(), 0, st));
+  // primitives per leaf (1 .. RR_LEAF_MAX); RR_LEAF_MAX_PRIMS in the environment overrides the default for A/B runs
+  uint32_t leaf_max = RR_LEAF_DEFAULT;
+  if (const char* e = getenv("RR_LEAF_MAX_PRIMS")) leaf_max = (uint32_t)std::max(1, atoi(e));
+  RR_CUDA(lbvh_build(d.tb, d.tri_box, n_tris, plan.first.data(), plan.count.data(), (uint32_t)plan.first.size(), 0, leaf_max, st));
   RR_CUDA(dev_malloc(&d.tri_geom, std::max<uint64_t>(d.tb.n, 1) * 48));
   RR_CUDA(dev_malloc(&d.tri_nrm, std::max<uint64_t>(d.tb.n, 1) * 48));
   RR_CUDA(launch_pack_tris(d.tris, d.tb.order, d.tb.n, d.tri_geom, d.tri_nrm, st));
   RR_CUDA(launch_sphere_boxes(d.spheres, n_spheres, d.sph_box, st));
   uint32_t sf = 0, sc = (uint32_t)n_spheres;
-  RR_CUDA(lbvh_build(d.sb, d.sph_box, n_spheres, &sf, &sc, n_spheres ? 1u : 0u, (int32_t)d.tb.n, st));
+  RR_CUDA(lbvh_build(d.sb, d.sph_box, n_spheres, &sf, &sc, n_spheres ? 1u : 0u, (int32_t)d.tb.n, leaf_max, st));
   RR_CUDA(dev_malloc(&d.sph_geom, std::max<size_t>(n_spheres, 1) * 16));
   RR_CUDA(launch_pack_spheres(d.spheres, d.sb.order, d.sb.n, d.sph_geom, st));
   // one node array: triangle hierarchies at [0, tb.n), the sphere hierarchy behind them
@@ -675,6 +682,36 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
   RR_CUDA(dev_malloc(&d.nodes, std::max<uint64_t>(d.tb.n + d.sb.n, 1) * node_bytes));
   if (d.tb.n) RR_CUDA(cudaMemcpyAsync(d.nodes, d.tb.nodes, d.tb.n * node_bytes, cudaMemcpyDeviceToDevice, st));
   if (d.sb.n) RR_CUDA(cudaMemcpyAsync(d.nodes + RR_NODE_QUADS * d.tb.n, d.sb.nodes, d.sb.n * node_bytes, cudaMemcpyDeviceToDevice, st));
+#if RR_TOP_STAGE
+  {  // the root of the largest triangle hierarchy and its inner children, copied out for the kernel to stage
+    size_t big = 0;
+    uint64_t sfirst = 0, big_sfirst = 0;
+    for (size_t k = 0; k < plan.count.size(); ++k) {
+      if (plan.count[k] > plan.count[big]) { big = k; big_sfirst = sfirst; }
+      sfirst += plan.count[k];
+    }
+    if (!plan.count.empty() && plan.count[big] > RR_DIRECT_MAX) {
+      RR_CUDA(cudaStreamSynchronize(st));
+      std::vector<float4> top(RR_NODE_QUADS * (size_t)RR_TOP_STAGE);
+      RR_CUDA(cudaMemcpy(top.data(), d.nodes + RR_NODE_QUADS * big_sfirst, 128, cudaMemcpyDeviceToHost));
+      uint32_t n_top = 1;
+      int32_t refs[4], cnt;
+      memcpy(refs, &top[6], 16);
+      memcpy(&cnt, &top[7].x, 4);
+      for (int k = 0; k < 4 && n_top < (uint32_t)RR_TOP_STAGE; ++k) {
+        if (k >= cnt || refs[k] < 0) continue;  // unused child slot, or a leaf
+        RR_CUDA(cudaMemcpy(top.data() + RR_NODE_QUADS * (size_t)n_top, d.nodes + RR_NODE_QUADS * (size_t)refs[k], 128, cudaMemcpyDeviceToHost));
+        refs[k] = RR_TOP_TAG + (int32_t)n_top;
+        ++n_top;
+      }
+      memcpy(&top[6], refs, 16);
+      RR_CUDA(dev_malloc(&d.top_nodes, sizeof(float4) * top.size()));
+      RR_CUDA(cudaMemcpy(d.top_nodes, top.data(), sizeof(float4) * top.size(), cudaMemcpyHostToDevice));
+      d.top_count = n_top;
+      d.top_root = (int32_t)big_sfirst;
+    }
+  }
+#endif
   // mesh + material tables (the inputs stay on the device for rr_update_meshes; free_scene releases them)
   rr_mesh*& d_meshes_in = d.meshes_in;
   uint32_t *&d_mesh_seg = d.mesh_seg, *&d_mesh_pos = d.mesh_pos;
@@ -755,6 +792,9 @@ static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam
   }
   p.sph_geom = d.sph_geom;
   p.sph_order = d.sb.order;
+  p.top_nodes = d.top_nodes;
+  p.top_count = d.top_count;
+  p.top_root = d.top_root;
   p.tune = ctx->tune;
   for (int k = 0; k < 3; ++k) p.cam.pos[k] = cam->position.s[k];
   p.cam.pitch = cam->pitch; p.cam.yaw = cam->yaw; p.cam.roll = cam->roll; p.cam.fov = cam->fov; p.cam.aspect = cam->aspectRatio;

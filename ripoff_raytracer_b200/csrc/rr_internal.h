@@ -14,6 +14,11 @@
 #define RR_MAX_BOUNCES 0x7fffffu       // the bounce counter shares a 32-bit slot word with the 9-bit pass counter
 #define RR_QUEUE_EPOCH_SHIFT 48        // tile counter word: frame epoch (16 bits) << 48 | tiles popped
 #define RR_DIRECT_MAX 4               // segments this small are tested without a hierarchy
+#define RR_LEAF_MAX 4                 // primitives per leaf of a hierarchy at most (the leaf reference keeps count - 1 in 2 bits)
+#ifndef RR_LEAF_DEFAULT
+#define RR_LEAF_DEFAULT 4             // what rr_upload_scene builds with
+#endif
+#define RR_MAX_PRIMS 0x1ffffff0ull    // ... and the first sorted slot in the 29 bits above them
 #define RR_TILE_W 8                   // default work tile: 8 x 4 pixels = one warp
 #define RR_TILE_H 4
 #define RR_NODE_QUADS 8   // float4 per traversal node (4-wide node, 128 bytes)
@@ -26,6 +31,10 @@
 #ifndef RR_MIN_CTAS
 #define RR_MIN_CTAS 5     // resident CTAs per SM the render kernel is compiled for
 #endif
+#ifndef RR_TOP_STAGE
+#define RR_TOP_STAGE 0    // > 0: this many nodes of the top of the largest hierarchy are staged in shared memory (A/B switch)
+#endif
+#define RR_TOP_TAG 0x40000000  // node references at or above this value address the staged copy
 #define RR_POOL_WORDS 28  // 32-bit words of one slot in shared memory
 #define RR_COLD_WORDS 25  // ... and in the per-warp global scratch
 
@@ -124,6 +133,9 @@ struct RenderParams {
   const float4* tlas_blocks; // one box per block of 8 meshes
   const float4* tlas;        // level 0: one box per chunk of 32 meshes; level l: one box per 4^l chunks
   const uint32_t* tlas_levels; // number of levels in `tlas`, then the index of the first box of every level
+  const float4* top_nodes;   // RR_TOP_STAGE: the staged nodes (root first; the root's references point at the staged children)
+  uint32_t top_count;        //               how many (0: nothing staged)
+  int32_t top_root;          //               node index of the hierarchy root they belong to
   const float4* sph_geom;    // (center, radius) per slot
   const uint32_t* sph_order; // slot -> sphere index
   Tuning tune;
@@ -163,7 +175,7 @@ inline cudaError_t dev_malloc(T** p, size_t bytes) { return dev_malloc_bytes(rei
 // ref_offset is added to the inner-node references of the packed traversal nodes (the sphere
 // hierarchy is stored behind the triangle hierarchies in one array).
 cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, const uint32_t* h_seg_first,
-                       const uint32_t* h_seg_count, uint32_t n_segs, int32_t ref_offset, cudaStream_t stream);
+                       const uint32_t* h_seg_count, uint32_t n_segs, int32_t ref_offset, uint32_t leaf_max, cudaStream_t stream);
 // Conservative slack added to every box a ray is tested against: 2^-18 of the largest |coordinate|
 // of the segment box (about 60 ulp), so that the closest hit does not depend on the traversal order.
 __host__ __device__ inline float box_delta(const float* seg_box6) {

@@ -338,7 +338,8 @@ __device__ __forceinline__ int key_delta(const uint64_t* __restrict__ codes, int
 
 __global__ void k_karras(const uint64_t* __restrict__ codes_all, uint64_t n, const uint32_t* __restrict__ seg_sfirst,
                          const uint32_t* __restrict__ seg_count, int n_segs, int32_t* __restrict__ left,
-                         int32_t* __restrict__ right, int32_t* __restrict__ parent, int32_t* __restrict__ leaf_parent) {
+                         int32_t* __restrict__ right, int32_t* __restrict__ parent, int32_t* __restrict__ leaf_parent,
+                         uint32_t* __restrict__ range_first, uint32_t* __restrict__ range_count) {
   uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n) return;
   int s = seg_search(seg_sfirst, n_segs, (uint32_t)g);
@@ -372,6 +373,8 @@ __global__ void k_karras(const uint64_t* __restrict__ codes_all, uint64_t n, con
   else { R = (int32_t)(first + gamma + 1); parent[first + gamma + 1] = me; }
   left[me] = L;
   right[me] = R;
+  range_first[me] = (uint32_t)(first + lo);  // the sorted slots under this node: [first + lo, first + hi]
+  range_count[me] = (uint32_t)(hi - lo + 1);
 }
 
 __device__ __forceinline__ void load_ref_box(int32_t ref, const uint32_t* __restrict__ order,
@@ -426,12 +429,15 @@ __global__ void k_refit(uint64_t n, const uint32_t* __restrict__ order, const fl
 // starts from the two children of a binary node and keeps replacing the inner child with the LARGEST SURFACE AREA by
 // that child's two children until it has four (or only leaves are left).  Every inner child becomes a wide node of
 // the next level (it keeps its binary index; binary nodes that were absorbed are never fetched).
+// A subtree of at most `leaf_max` (<= 4) primitives is not descended: the primitives of an LBVH subtree are consecutive
+// sorted slots, so the subtree becomes ONE leaf reference (first slot, count) with the subtree's box, and its nodes are
+// never packed or fetched.  Fewer levels and a third of the node bytes for a few more primitive tests per ray.
 //   q0..q2 = min.x[4] min.y[4] min.z[4]   q3..q5 = max.x[4] max.y[4] max.z[4]   q6 = ref[4]   q7 = (#children, -, -, -)
 // Unused child slots hold a NaN box: every comparison of the slab test fails, no ray enters it (an inverted
 // box would not do: the test orders the two planes of a slab itself).  The boxes are inflated by
 // the segment's box_delta() so that culling is conservative (the closest hit then does not depend on the order
 // in which a traversal visits the nodes).  ref: inner = index in the combined node array (ref_offset added),
-// leaf = -(slot + 2) (so that -1 is free for "pop", rr_render.cu).
+// leaf = -((first slot << 2 | count - 1) + 2) (so that -1 is free for "pop", rr_render.cu ref_slot / ref_count).
 __global__ void k_wide_roots(const uint32_t* __restrict__ seg_sfirst, const uint32_t* __restrict__ seg_count, int n_segs,
                              int32_t* __restrict__ frontier, unsigned int* __restrict__ count) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -449,18 +455,20 @@ __global__ void k_pack_wide(const int32_t* __restrict__ frontier, unsigned int n
                             const float* __restrict__ prim_box, const int32_t* __restrict__ left,
                             const int32_t* __restrict__ right, const float* __restrict__ bounds,
                             const uint32_t* __restrict__ seg_sfirst, int n_segs, const float* __restrict__ seg_box,
-                            int32_t ref_offset, float4* __restrict__ nodes) {
+                            int32_t ref_offset, const uint32_t* __restrict__ range_first,
+                            const uint32_t* __restrict__ range_count, uint32_t leaf_max, float4* __restrict__ nodes) {
   const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_front) return;
   const int32_t g = frontier[i];
   int32_t kids[4] = {left[g], right[g], 0, 0};
   int cnt = 2;
+  auto opens = [&](int32_t kid) { return kid >= 0 && range_count[kid] > leaf_max; };  // an inner node that stays a node
   while (cnt < 4) {
     int best = -1;
     float best_area = -1.0f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (k < cnt && kids[k] >= 0) {
+      if (k < cnt && opens(kids[k])) {
         const float a = half_area(bounds + 6 * (uint64_t)kids[k]);
         if (a > best_area) { best_area = a; best = k; }  // ties: the earlier child
       }
@@ -492,8 +500,14 @@ __global__ void k_pack_wide(const int32_t* __restrict__ frontier, unsigned int n
       load_ref_box(kids[k], order, prim_box, bounds, bx);
 #pragma unroll
       for (int a = 0; a < 3; ++a) { lo[a][k] = bx[a] - d; hi[a][k] = bx[3 + a] + d; }
-      ref[k] = kids[k] >= 0 ? kids[k] + ref_offset : kids[k] - 1;
-      if (kids[k] >= 0) next[atomicAdd(next_count, 1u)] = kids[k];
+      if (opens(kids[k])) {
+        ref[k] = kids[k] + ref_offset;
+        next[atomicAdd(next_count, 1u)] = kids[k];
+      } else {  // one primitive, or a whole subtree of at most leaf_max primitives
+        const uint32_t first = kids[k] >= 0 ? range_first[kids[k]] : (uint32_t)~kids[k];
+        const uint32_t count = kids[k] >= 0 ? range_count[kids[k]] : 1u;
+        ref[k] = -(int32_t)(((first << 2) | (count - 1u)) + 2u);
+      }
     }
   }
   float4* o = nodes + RR_NODE_QUADS * (uint64_t)g;
@@ -565,8 +579,9 @@ static cudaError_t dalloc(T** p, uint64_t count) {
 }
 
 cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, const uint32_t* h_seg_first,
-                       const uint32_t* h_seg_count, uint32_t n_segs, int32_t ref_offset, cudaStream_t st) {
+                       const uint32_t* h_seg_count, uint32_t n_segs, int32_t ref_offset, uint32_t leaf_max, cudaStream_t st) {
   lbvh_free(out);
+  leaf_max = leaf_max < 1u ? 1u : leaf_max > RR_LEAF_MAX ? RR_LEAF_MAX : leaf_max;
   out.n_segs = n_segs;
   uint64_t n = 0;
   uint32_t* h_sfirst = (uint32_t*)malloc((n_segs ? n_segs : 1) * sizeof(uint32_t));
@@ -580,6 +595,7 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
   uint32_t *vals_a = nullptr, *vals_b = nullptr, *seg_id = nullptr, *hist = nullptr;
   int* seg_box_ord = nullptr;
   int32_t* leaf_parent = nullptr;
+  uint32_t *range_first = nullptr, *range_count = nullptr;
   unsigned int *flags = nullptr, *d_depth = nullptr, *front_count = nullptr;
   int32_t *front_a = nullptr, *front_b = nullptr;
   const uint32_t n_tiles = (uint32_t)((n_total + SORT_TILE - 1) / SORT_TILE);
@@ -607,6 +623,8 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
   RR_TRY(dalloc(&hist, (uint64_t)256 * (n_tiles ? n_tiles : 1) + 256));  // per-(digit, tile) counters + 256 digit totals
   RR_TRY(dalloc(&seg_box_ord, (uint64_t)(n_segs ? n_segs : 1) * 6));
   RR_TRY(dalloc(&leaf_parent, n));
+  RR_TRY(dalloc(&range_first, n));
+  RR_TRY(dalloc(&range_count, n));
   RR_TRY(dalloc(&flags, n));
   RR_TRY(dalloc(&d_depth, 1));
   if (n_segs) {
@@ -656,7 +674,7 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
     k_fill_i32<<<grid_for(n, 256), 256, 0, st>>>(out.parent, n, -1);
     k_fill_i32<<<grid_for(n, 256), 256, 0, st>>>(leaf_parent, n, -1);
     k_karras<<<grid_for(n, 128), 128, 0, st>>>(out.codes, n, out.seg_sfirst, out.seg_count, (int)n_segs, out.left, out.right,
-                                               out.parent, leaf_parent);
+                                               out.parent, leaf_parent, range_first, range_count);
     k_refit<<<grid_for(n, 128), 128, 0, st>>>(n, out.order, d_prim_box, out.left, out.right, out.parent, leaf_parent,
                                               out.bounds, flags, d_depth);
     RR_TRY(cudaGetLastError());
@@ -677,7 +695,7 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
       RR_TRY(cudaMemsetAsync(cnt_out, 0, 4, st));
       k_pack_wide<<<grid_for(h_count, 128), 128, 0, st>>>(fin, h_count, fout, cnt_out, out.order, d_prim_box, out.left, out.right,
                                                           out.bounds, out.seg_sfirst, (int)n_segs, out.seg_box, ref_offset,
-                                                          out.nodes);
+                                                          range_first, range_count, leaf_max, out.nodes);
       RR_TRY(cudaMemcpyAsync(&h_count, cnt_out, 4, cudaMemcpyDeviceToHost, st));
       RR_TRY(cudaStreamSynchronize(st));
       int32_t* t = fin; fin = fout; fout = t;
@@ -689,7 +707,7 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
   RR_TRY(cudaStreamSynchronize(st));
 done:
   dev_free(keys_a); dev_free(keys_b); dev_free(vals_a); dev_free(vals_b); dev_free(seg_id); dev_free(hist);
-  dev_free(seg_box_ord); dev_free(leaf_parent); dev_free(flags); dev_free(d_depth);
+  dev_free(seg_box_ord); dev_free(leaf_parent); dev_free(range_first); dev_free(range_count); dev_free(flags); dev_free(d_depth);
   dev_free(front_a); dev_free(front_b); dev_free(front_count);
   free(h_sfirst);
 #undef RR_TRY

@@ -287,11 +287,14 @@ __device__ __noinline__ uint32_t tonemap_rgba(V3 c) {
 // The counter word is (frame epoch << 48 | tiles popped).  A pop that meets another epoch (rr_queue_reset ran while
 // this launch was still popping, or a rank is a frame behind) takes nothing and is counted: rr_render_shared then
 // fails with RR_ERR_QUEUE instead of rendering a tile of the wrong frame.
-__device__ __forceinline__ bool pop_tile(const RenderParams& p, uint32_t& tile, bool& epoch_error) {
+__device__ __forceinline__ bool pop_tile(const RenderParams& p, uint32_t& tile) {
   unsigned long long t = 0;
   if ((threadIdx.x & 31) == 0) t = atomicAdd_system(p.queue, 1ull);
   t = __shfl_sync(0xffffffffu, t, 0);
-  if ((uint32_t)(t >> RR_QUEUE_EPOCH_SHIFT) != p.queue_epoch) { epoch_error = true; return false; }
+  if ((uint32_t)(t >> RR_QUEUE_EPOCH_SHIFT) != p.queue_epoch) {  // (counted at once: no register is kept for an event that must not happen)
+    if ((threadIdx.x & 31) == 0) atomicAdd(&p.counters->queue_errors, 1ull);
+    return false;
+  }
   t &= (1ull << RR_QUEUE_EPOCH_SHIFT) - 1ull;
   t = (unsigned long long)p.tile_begin + t * p.tile_stride;
   tile = (uint32_t)t;
@@ -328,11 +331,13 @@ enum {
   NC
 };
 static_assert(NW == RR_POOL_WORDS && NC == RR_COLD_WORDS, "rr_internal.h RR_POOL_WORDS / RR_COLD_WORDS");
-// Node references.  In the packed nodes a leaf is -(slot + 2), so that "inner node or pop" is cur >= -1.
+// Node references.  In the packed nodes a leaf is -((first slot << 2 | count - 1) + 2): up to RR_LEAF_MAX consecutive
+// sorted slots (rr_lbvh.cu k_pack_wide), and "inner node or pop" is cur >= -1.
 constexpr int32_t REF_POP = -1;                   // take the next entry of the stack
 constexpr int32_t REF_END = (int32_t)0x80000000;  // traversal of this mesh finished
 __device__ __forceinline__ bool ref_is_leaf(int32_t r) { return r < REF_POP && r != REF_END; }
-__device__ __forceinline__ uint32_t ref_slot(int32_t r) { return (uint32_t)(-r) - 2u; }
+__device__ __forceinline__ uint32_t ref_slot(int32_t r) { return ((uint32_t)(-r) - 2u) >> 2; }
+__device__ __forceinline__ uint32_t ref_count(int32_t r) { return (((uint32_t)(-r) - 2u) & 3u) + 1u; }
 
 // World-box tests of the meshes [base, base + 32): bit k set = the ray enters mesh base + k's box before `tmax`.
 // Every lane walks the whole chunk, so the loop is convergent.  Out of line: one copy serves shade, pixel and setup.
@@ -386,9 +391,37 @@ __device__ __noinline__ int32_t next_chunk_fn(const float4* __restrict__ tlas, c
   return c;
 }
 
+#if RR_TOP_STAGE
+__device__ __forceinline__ uint32_t smem_addr(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
+#endif
+
 template <bool COUNT, bool PRIMARY>
 __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p) {
   extern __shared__ uint32_t pool_all[];
+#if RR_TOP_STAGE
+  // Top of the largest hierarchy staged in shared memory (north_star: "shared-memory or TMA staging of the BVH top
+  // levels"): ONE bulk async copy (TMA, cp.async.bulk -> UBLKCP) per CTA brings the root and its inner children in,
+  // completion through an mbarrier.  A/B switch: the production build has RR_TOP_STAGE = 0 (profiles/README.md).
+  const float4* const top_s = reinterpret_cast<const float4*>(pool_all + WARPS * (NW * POOL + 32 + 8));
+  __shared__ __align__(8) unsigned long long top_bar;
+  if (p.top_count) {
+    const uint32_t bar = smem_addr(&top_bar), dst = smem_addr(top_s), bytes = p.top_count * 128u;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(p.top_nodes), "r"(bytes), "r"(bar)
+                   : "memory");
+    }
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0; selp.u32 %0, 1, 0, q; }" : "=r"(done) : "r"(bar) : "memory");
+  }
+#endif
   const unsigned lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
   const unsigned full = 0xffffffffu;
@@ -415,8 +448,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   uint32_t n_need = POOL;  // slots waiting for a pixel
   // statistics
   uint32_t n_rays = 0, n_tiles = 0;  // per lane / per warp: far below 2^32 even for an 8K, 1024-spp frame on one GPU
-  uint32_t n_overflow = 0;           // pushes dropped for lack of stack entries: must stay 0 (the host fails the render otherwise)
-  bool epoch_error = false;
   unsigned c_box = 0, c_tri = 0, c_sph = 0;
   unsigned ph_runs[5] = {0, 0, 0, 0, 0}, ph_lanes[5] = {0, 0, 0, 0, 0};
 
@@ -583,6 +614,9 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       } else {
         pend_cnt = 0;
         cur = (int32_t)first;  // root node
+#if RR_TOP_STAGE
+        if (p.top_count && cur == p.top_root) cur = RR_TOP_TAG;  // the staged copy of this root
+#endif
       }
       key = trav_key();
       return true;
@@ -726,7 +760,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             if (!found) { cur = REF_END; break; }
           }
           if (next >= 0) { cur = next; break; }
-          if (pend_cnt == 0) { pend_slot = ref_slot(next); pend_cnt = 1; next = REF_POP; continue; }
+          if (pend_cnt == 0) { pend_slot = ref_slot(next); pend_cnt = ref_count(next); next = REF_POP; continue; }
           cur = next;  // a second leaf while one is postponed: wait for the leaf phase
           break;
         }
@@ -741,10 +775,24 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             // one 128-byte node: the boxes of up to four children (SoA) and their references.  The quads holding the
             // planes the ray ENTERS / LEAVES through are picked by the sign of its direction (qn*/qf*, set up
             // once per run), so no per-child min/max is needed to order the two planes of a slab.
+#if RR_TOP_STAGE
+            float4 nx, ny, nz, fx, fy, fz, rf;
+            if (cur >= RR_TOP_TAG) {  // staged node: seven 16-byte loads from shared memory
+              const float4* nd = top_s + RR_NODE_QUADS * (size_t)(cur - RR_TOP_TAG);
+              nx = nd[qnx]; ny = nd[qny]; nz = nd[qnz]; fx = nd[qfx]; fy = nd[qfy]; fz = nd[qfz]; rf = nd[6];
+              if (COUNT) c_box += (unsigned)__float_as_int(nd[7].x);
+            } else {
+              const float4* nd = p.nodes + RR_NODE_QUADS * (size_t)cur;
+              nx = __ldg(nd + qnx); ny = __ldg(nd + qny); nz = __ldg(nd + qnz); fx = __ldg(nd + qfx);
+              fy = __ldg(nd + qfy); fz = __ldg(nd + qfz); rf = __ldg(nd + 6);
+              if (COUNT) c_box += (unsigned)__float_as_int(__ldg(&nd[7].x));
+            }
+#else
             const float4* nd = p.nodes + RR_NODE_QUADS * (size_t)cur;
             const float4 nx = __ldg(nd + qnx), ny = __ldg(nd + qny), nz = __ldg(nd + qnz), fx = __ldg(nd + qfx),
                          fy = __ldg(nd + qfy), fz = __ldg(nd + qfz), rf = __ldg(nd + 6);
             if (COUNT) c_box += (unsigned)__float_as_int(__ldg(&nd[7].x));
+#endif
             // sort key of a child: entry distance (clamped at 0, two low mantissa bits dropped) | child number;
             // a child the ray misses (or an unused NaN box) sorts last
             auto child_key = [&](float pnx, float pny, float pnz, float pfx, float pfy, float pfz, uint32_t c) -> uint32_t {
@@ -771,15 +819,17 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             int32_t r0 = ref_of(k0), r1 = ref_of(k1), r2 = ref_of(k2), r3 = ref_of(k3);
             int hits = (k0 != 0xffffffffu) + (k1 != 0xffffffffu) + (k2 != 0xffffffffu) + (k3 != 0xffffffffu);
             if (hits > 0 && r0 < REF_POP && pend_cnt == 0) {  // the nearest child is a leaf: postpone it, go on with the next one
-              pend_slot = ref_slot(r0); pend_cnt = 1;
+              pend_slot = ref_slot(r0); pend_cnt = ref_count(r0);
               k0 = k1; k1 = k2; k2 = k3;
               r0 = r1; r1 = r2; r2 = r3;
               hits--;
             }
             // misses sort last, so the children to push are a suffix of the hits: farthest first, the nearest of
             // them ends up as the (register-resident) top; the previous top is spilled once
-            if (hits >= 2 && sp + hits - 1 > (int)p.stack_entries) n_overflow++;  // cannot happen (3 entries per wide level + 4); counted, not hidden
-            else if (hits >= 2) {
+            if (hits >= 2 && sp + hits - 1 > (int)p.stack_entries) {
+              // cannot happen (3 entries per wide level + 4); counted, not hidden: the host fails the render with RR_ERR_BVH_DEPTH
+              atomicAdd(&p.counters->stack_overflows, 1ull);
+            } else if (hits >= 2) {
               uint2* const w = stk + sp * POOL;  // one address; the stores below use constant offsets from it
               if (sp > 0) w[-POOL] = top;
               if (hits >= 3) w[0] = hits == 4 ? make_uint2((uint32_t)r3, k3 & ~3u) : make_uint2((uint32_t)r2, k2 & ~3u);
@@ -902,7 +952,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         }
         if (pend_cnt == 0 && ref_is_leaf(cur)) {  // the leaf this slot was waiting on becomes the postponed one
           pend_slot = ref_slot(cur);
-          pend_cnt = 1;
+          pend_cnt = ref_count(cur);
           cur = REF_POP;
           PW(W_CUR, s) = (uint32_t)cur;
         }
@@ -1005,7 +1055,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         if (tile_next >= tile_pixels) {
           if (queue_empty) break;
           uint32_t tile;
-          if (!pop_tile(p, tile, epoch_error)) { queue_empty = true; break; }
+          if (!pop_tile(p, tile)) { queue_empty = true; break; }
           n_tiles++;
           tile_x0 = (tile % p.tiles_x) * p.tile_w;
           tile_y0 = (tile / p.tiles_x) * p.tile_h;
@@ -1062,12 +1112,9 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   unsigned long long r = n_rays;  // summed over the warp in 64 bits
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) r += __shfl_xor_sync(full, r, off);
-  const unsigned ovf = __reduce_add_sync(full, n_overflow);
   if (lane == 0) {
     atomicAdd(&p.counters->rays, r);
     atomicAdd(&p.counters->tiles, (unsigned long long)n_tiles);
-    if (ovf) atomicAdd(&p.counters->stack_overflows, (unsigned long long)ovf);
-    if (epoch_error) atomicAdd(&p.counters->queue_errors, 1ull);
   }
   if (COUNT) {
     unsigned long long b = c_box, t = c_tri, sq = c_sph;
@@ -1096,7 +1143,7 @@ void default_tuning(Tuning& t) {
   t.ctas_per_sm = 0;
 }
 
-constexpr size_t RENDER_SMEM = (size_t)WARPS * (NW * POOL + 32 + 8) * sizeof(uint32_t);
+constexpr size_t RENDER_SMEM = (size_t)WARPS * (NW * POOL + 32 + 8) * sizeof(uint32_t) + (size_t)RR_TOP_STAGE * 128;
 
 template <class K>
 static cudaError_t launch_persistent(K kernel, const RenderParams& p, int sm_count, cudaStream_t s) {

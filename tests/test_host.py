@@ -217,3 +217,57 @@ def test_parallel_obj_parse_is_independent_of_the_chunking(tmp_path, monkeypatch
     assert len(cor) > 100 and all(r == results[0] for r in results[1:])
     # the forward references were skipped and every index is in range
     assert cor[:, :3].max() < len(pos) and cor[:, 3:].max() < len(nrm)
+
+
+@pytest.mark.skipif(not __import__("pathlib").Path("/root/reference/src/readobj.hpp").exists(), reason="needs the reference headers")
+def test_reference_binding_compiles_against_the_reference_headers(tmp_path):
+    """include/reference_binding/image_b200.hpp compiled against the reference's OWN
+    settings.hpp / readobj.hpp / math.hpp (read where they lie; the Khronos typedefs they need come from
+    oracle/ref_shim/cl_host_types.hpp because the image has no CL headers) and linked with librr_b200.so: the
+    wire-format static_asserts hold and every binding function instantiates.  The program also runs the part that
+    needs no GPU: the mesh ranges recovered from a node list the reference's own loader + SplitBVH built."""
+    import subprocess
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    src = tmp_path / "bind.cpp"
+    src.write_text(r"""
+#include "cl_host_types.hpp"
+typedef cl_float3 float3_unused_;
+#include "settings.hpp"
+#include "readobj.hpp"
+#include "reference_binding/image_b200.hpp"
+int main(int argc, char** argv) {
+  int n = -1;
+  int rc = rr_device_count(&n);
+  if (argc > 1) {  // scene through the reference's own loader, then the binding's upload path up to the device
+    MeshInfo mesh = loadMeshFromOBJFile(argv[1]);
+    meshList.emplace_back(mesh);
+    std::cout << "triangles " << triangleList.size() << " nodes " << nodeList.size() << std::endl;
+    if (rc == RR_OK && n > 0) {
+      KernelContext k = generateKernelForDevices({0});
+      generateBuffers(k, triangleList, meshList, nodeList);
+      std::vector<unsigned char> pixels((size_t)WIDTH * HEIGHT * 4);
+      CameraInformation cam{};
+      cam.position = {CAMERA_START_X, CAMERA_START_Y, CAMERA_START_Z};
+      cam.yaw = CAMERA_START_YAW; cam.fov = 90.0f; cam.aspectRatio = (float)WIDTH / (float)HEIGHT;
+      compute(k, cam, pixels.data());
+      release(k);
+      std::cout << "rendered" << std::endl;
+    }
+  }
+  std::cout << "binding ok, devices " << n << std::endl;
+  return 0;
+}
+""")
+    exe = tmp_path / "bind"
+    csrc = root / "ripoff_raytracer_b200" / "csrc"
+    cmd = ["g++", "-std=gnu++20", "-w", "-O1", "-o", str(exe), str(src), f"-I{root / 'oracle' / 'ref_shim'}", "-I/root/reference/src",
+           f"-I{root / 'include'}", f"-L{csrc}", "-lrr_b200", f"-Wl,-rpath,{csrc}", "-pthread"]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-4000:]
+    obj = tmp_path / "k.obj"
+    scenes.write_obj(obj, *scenes.uv_sphere(16, 8))
+    p = subprocess.run([str(exe), str(obj)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "binding ok" in p.stdout, p.stdout + p.stderr
+    assert "triangles 224" in p.stdout
