@@ -209,6 +209,11 @@ typedef struct rr_stats {
    * (0 pixel, 1 shade, 2 mesh setup, 3 node step, 4 leaf test) ran in a warp, and the lanes active in it */
   uint64_t phase_runs[5];
   uint64_t phase_lanes[5];
+  /* drain of the persistent slot pool (instrumented kernel): time between a warp's first failed tile pop (no new
+   * pixels) and its exit -- mean and maximum over the warps, milliseconds.  A pixel's samples are serial
+   * (src/Trace.cl:632, 639-642), so this tail does not shrink with more GPUs: DESIGN.md section 6. */
+  float tail_avg_ms;
+  float tail_max_ms;
 } rr_stats;
 
 /* Replaces singleThreadedCompute / multiThreadedCompute + renderTile

@@ -92,6 +92,8 @@ class Stats(C.Structure):
         ("build_ms", C.c_float),
         ("phase_runs", C.c_uint64 * 5),
         ("phase_lanes", C.c_uint64 * 5),
+        ("tail_avg_ms", C.c_float),
+        ("tail_max_ms", C.c_float),
     ]
 
     def as_dict(self):

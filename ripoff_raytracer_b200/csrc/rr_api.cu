@@ -839,6 +839,8 @@ static void read_stats(const Counters& c, uint64_t samples, float ms, float buil
   out->render_ms = ms;
   out->build_ms = build_ms;
   for (int k = 0; k < 5; ++k) { out->phase_runs[k] = c.phase_runs[k]; out->phase_lanes[k] = c.phase_lanes[k]; }
+  out->tail_avg_ms = c.tail_warps ? (float)((double)c.tail_ns_sum / (double)c.tail_warps * 1e-6) : 0.0f;
+  out->tail_max_ms = (float)((double)c.tail_ns_max * 1e-6);
 }
 
 // Renders one frame on all devices of the context.  Device 0 owns the queue and
@@ -909,6 +911,7 @@ static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t 
     total.rays += c.rays; total.stack_overflows += c.stack_overflows; total.queue_errors += c.queue_errors; total.box_tests += c.box_tests;
     total.tri_tests += c.tri_tests; total.sphere_tests += c.sphere_tests; total.tiles += c.tiles;
     for (int q = 0; q < 5; ++q) { total.phase_runs[q] += c.phase_runs[q]; total.phase_lanes[q] += c.phase_lanes[q]; }
+    total.tail_ns_sum += c.tail_ns_sum; total.tail_warps += c.tail_warps; total.tail_ns_max = std::max(total.tail_ns_max, c.tail_ns_max);
   }
   ctx->progress_total.store(0);
   read_stats(total, (uint64_t)W * H * spp, ms_max, d0.build_ms, stats_out);

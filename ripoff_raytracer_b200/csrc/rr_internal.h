@@ -105,6 +105,9 @@ struct Counters {
   unsigned long long stack_overflows;  // node steps that could not push their far children (must stay 0: the stacks are sized per scene)
   unsigned long long queue_errors;     // tile pops that met a counter of another frame (rr_queue_reset during a frame)
   unsigned long long phase_runs[5], phase_lanes[5];  // scheduler statistics (instrumented kernel only)
+  // drain of the persistent slot pool (instrumented kernel only): per warp, the time between its first failed tile pop
+  // (queue empty: no new pixels) and its exit, in ns of %globaltimer
+  unsigned long long tail_ns_sum, tail_ns_max, tail_warps;
 };
 
 // Warp scheduler knobs of k_render.  Phases: 0 pixel, 1 shade, 2 setup, 3 traverse, 4 leaf.

@@ -450,6 +450,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   uint32_t n_rays = 0, n_tiles = 0;  // per lane / per warp: far below 2^32 even for an 8K, 1024-spp frame on one GPU
   unsigned c_box = 0, c_tri = 0, c_sph = 0;
   unsigned ph_runs[5] = {0, 0, 0, 0, 0}, ph_lanes[5] = {0, 0, 0, 0, 0};
+  unsigned long long t_empty = 0;  // COUNT: %globaltimer when this warp found the tile queue empty
 
   const uint32_t wP = p.tune.weight[PH_PIXEL], wH = p.tune.weight[PH_SHADE], wS = p.tune.weight[PH_SETUP],
                  wT = p.tune.weight[PH_TRAV], wL = p.tune.weight[PH_LEAF];
@@ -1091,6 +1092,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         tile_next += __popc(mb);
       }
       more_pixels = !(queue_empty && tile_next >= tile_pixels);
+      if (COUNT && queue_empty && t_empty == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_empty));
       __syncwarp();
       if (lane == 0) { tstate[0] = tile_x0; tstate[1] = tile_y0; tstate[2] = tile_w; tstate[3] = tile_next; tstate[4] = tile_pixels; }
       const bool got = s >= 0 && !need;
@@ -1132,6 +1134,12 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         atomicAdd(&p.counters->phase_runs[k], (unsigned long long)ph_runs[k]);
         atomicAdd(&p.counters->phase_lanes[k], (unsigned long long)ph_lanes[k]);
       }
+      unsigned long long t_exit;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_exit));
+      const unsigned long long tail = t_empty ? t_exit - t_empty : 0ull;
+      atomicAdd(&p.counters->tail_ns_sum, tail);
+      atomicMax(&p.counters->tail_ns_max, tail);
+      atomicAdd(&p.counters->tail_warps, 1ull);
     }
   }
 }
