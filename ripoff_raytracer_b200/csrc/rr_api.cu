@@ -126,6 +126,11 @@ struct Device {
   rr_mesh* meshes_in = nullptr;
   uint32_t *mesh_seg = nullptr, *mesh_pos = nullptr;
   std::vector<uint64_t> entry_count;  // host: primitives of every mesh (+ the sphere set), for the visiting order
+  // host copies for frame_needs_slack(): the uploaded MeshInfo array, the largest |coordinate| of every mesh's local
+  // box and of the sphere set's box
+  std::vector<rr_mesh> h_meshes;
+  std::vector<float> h_mesh_absmax;
+  float h_sph_absmax = 0.0f;
   float4* tlas_blocks = nullptr;      // > 32 meshes: the implicit top-level tree, one allocation: block boxes ...
   float4* tlas = nullptr;             // ... then the chunk level and the levels above it (RenderParams::tlas)
   uint32_t* tlas_levels = nullptr;    // device: level count, first box of every level (RenderParams::tlas_levels)
@@ -733,6 +738,24 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
   }
   RR_CUDA(cudaEventRecord(d.ev1, st));
   RR_CUDA(cudaStreamSynchronize(st));
+  {  // what frame_needs_slack() looks at
+    auto absmax6 = [](const float* b) {
+      float m = 0.0f;
+      for (int k = 0; k < 6; ++k) { const float a = std::fabs(b[k]); if (a > m && a < 3.0e38f) m = a; }
+      return m;
+    };
+    d.h_meshes.assign(meshes, meshes + n_meshes);
+    d.h_mesh_absmax.assign(n_meshes, 0.0f);
+    std::vector<float> sb(6 * std::max<size_t>(plan.first.size(), 1));
+    if (!plan.first.empty()) RR_CUDA(cudaMemcpy(sb.data(), d.tb.seg_box, plan.first.size() * 24, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n_meshes; ++i) d.h_mesh_absmax[i] = plan.count[plan.mesh_seg[i]] ? absmax6(&sb[6 * plan.mesh_seg[i]]) : 0.0f;
+    d.h_sph_absmax = 0.0f;
+    if (n_spheres) {
+      float b6[6];
+      RR_CUDA(cudaMemcpy(b6, d.sb.seg_box, 24, cudaMemcpyDeviceToHost));
+      d.h_sph_absmax = absmax6(b6);
+    }
+  }
   RR_CUDA(cudaEventElapsedTime(&d.build_ms, d.ev0, d.ev1));
   dev_free(d.tb.nodes); d.tb.nodes = nullptr;  // copied into d.nodes
   dev_free(d.sb.nodes); d.sb.nodes = nullptr;
@@ -772,6 +795,36 @@ static int ensure_frame(Device& d, uint32_t W, uint32_t H, bool want_radiance) {
     d.radiance_bytes = rneed;
   }
   return RR_OK;
+}
+
+// Does this frame need the kernel instantiation with the per-ray culling slack (rr_render.cu RaySlack)?  Every box is
+// inflated at build time by box_delta = 2^-18 (64 ulp) of the largest |coordinate| A of its mesh, which covers the
+// rounding error of slab and triangle tests while the mesh-local ray origin stays within 16 A.  A ray starts at the
+// camera or at a hit point, so |origin| <= O = max(|cam|, radius of the scene), and in mesh m's space
+// |local origin| <= (O + |pos_m|) / |scale_m|.  The world-space tests (mesh world boxes, 2^-13 relative slack of their
+// own) tolerate a larger ratio.  If any mesh exceeds its bound the frame runs with the per-ray term (a few % slower).
+static bool frame_needs_slack(const rr_ctx* ctx, const Device& d, const rr_camera* cam) {
+  if (ctx->tune.speculate & 16u) return true;   // tuning bits 4 / 5: force either instantiation (tests, A/B)
+  if (ctx->tune.speculate & 32u) return false;
+  auto len3 = [](const float* v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+  float radius = 1.7320508f * d.h_sph_absmax;  // of everything a path can hit
+  for (size_t i = 0; i < d.h_meshes.size(); ++i) {
+    const rr_mesh& m = d.h_meshes[i];
+    if (!(m.scale > RR_EPSILON) || d.h_mesh_absmax[i] == 0.0f) continue;
+    radius = std::max(radius, len3(m.pos.s) + m.scale * 1.7320508f * d.h_mesh_absmax[i]);
+  }
+  const float O = std::max(len3(cam->position.s), radius);
+  if (!(O < 3.0e38f)) return true;
+  if (d.h_sph_absmax > 0.0f && O > 16.0f * d.h_sph_absmax) return true;
+  for (size_t i = 0; i < d.h_meshes.size(); ++i) {
+    const rr_mesh& m = d.h_meshes[i];
+    const float A = d.h_mesh_absmax[i];
+    if (!(m.scale > RR_EPSILON) || A == 0.0f) continue;
+    const float P = len3(m.pos.s);
+    if ((O + P) / m.scale > 16.0f * A) return true;               // mesh-local tests: node boxes, root box
+    if (O > 256.0f * std::max(P, 0.5f * m.scale * A)) return true;  // world-space tests: the mesh's world box
+  }
+  return false;
 }
 
 static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam, uint32_t W, uint32_t H, uint32_t spp,
@@ -851,6 +904,7 @@ static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t 
   // mode 0: local queue, 1: shared (imported/exported) queue + frame, 2: static stride partition
   int rc = check_render_args(ctx, cam, W, H, spp, bounces);
   if (rc) return rc;
+  if (ctx->tune.speculate & 8u) count_tests = true;  // tuning bit 3: the instrumented kernel for every kind of frame (tools/tail_model.py)
   const size_t nd = ctx->dev.size();
   if (want_radiance && nd > 1) return fail(RR_ERR_UNSUPPORTED, "radiance output needs a single-device context");
   Device& d0 = ctx->dev[0];
@@ -893,7 +947,7 @@ static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t 
     }
     if (want_radiance) p.radiance = d.radiance;
     RR_CUDA(cudaEventRecord(d.ev0, d.stream));
-    RR_CUDA(launch_render(p, count_tests, d.sm_count, d.stream));
+    RR_CUDA(launch_render(p, count_tests, frame_needs_slack(ctx, d, cam), d.sm_count, d.stream));
     RR_CUDA(cudaEventRecord(d.ev1, d.stream));
   }
   Counters total;
@@ -1188,6 +1242,7 @@ int rr_update_meshes(rr_ctx* ctx, const rr_mesh* meshes, size_t n_meshes) {
   for (Device& d : ctx->dev) {
     RR_CUDA(cudaSetDevice(d.ordinal));
     if (n_meshes) RR_CUDA(cudaMemcpyAsync(d.meshes_in, meshes, n_meshes * sizeof(rr_mesh), cudaMemcpyHostToDevice, d.stream));
+    d.h_meshes.assign(meshes, meshes + n_meshes);
     const int rc = prepare_meshes(d, n_meshes, ctx->n_spheres);  // synchronises: the caller's array may go away
     if (rc) return rc;
   }
@@ -1291,7 +1346,7 @@ int rr_primary_hits(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t 
   p.hit_mesh = dm; p.hit_prim = dp; p.hit_dst = dd;
   if (e == cudaSuccess) e = cudaMemsetAsync(d.queue, 0, sizeof(unsigned long long), d.stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(d.counters, 0, sizeof(Counters), d.stream);
-  if (e == cudaSuccess) e = launch_primary(p, d.sm_count, d.stream);
+  if (e == cudaSuccess) e = launch_primary(p, frame_needs_slack(ctx, d, cam), d.sm_count, d.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
   if (e == cudaSuccess && mesh_out) e = cudaMemcpy(mesh_out, dm, n * 4, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && prim_out) e = cudaMemcpy(prim_out, dp, n * 4, cudaMemcpyDeviceToHost);

@@ -16,7 +16,7 @@
 #define RR_DIRECT_MAX 4               // segments this small are tested without a hierarchy
 #define RR_LEAF_MAX 4                 // primitives per leaf of a hierarchy at most (the leaf reference keeps count - 1 in 2 bits)
 #ifndef RR_LEAF_DEFAULT
-#define RR_LEAF_DEFAULT 4             // what rr_upload_scene builds with
+#define RR_LEAF_DEFAULT 2             // what rr_upload_scene builds with
 #endif
 #define RR_MAX_PRIMS 0x1ffffff0ull    // ... and the first sorted slot in the 29 bits above them
 #define RR_TILE_W 8                   // default work tile: 8 x 4 pixels = one warp
@@ -189,7 +189,7 @@ __host__ __device__ inline float box_delta(const float* seg_box6) {
   }
   return m * 3.814697265625e-06f;
 }
-// The per-ray part of the slack: 2^-18 of the largest |origin coordinate| (rr_render.cu slab_slack).
+// The per-ray part of the slack: 2^-18 of the largest |origin coordinate| (rr_render.cu RaySlack / make_slack).
 __host__ __device__ inline float ray_slack(float ox, float oy, float oz) {
   const float ax = ox < 0.0f ? -ox : ox, ay = oy < 0.0f ? -oy : oy, az = oz < 0.0f ? -oz : oz;
   float m = ax > ay ? ax : ay;
@@ -206,8 +206,9 @@ cudaError_t launch_pack_spheres(const rr_sphere* d_sph, const uint32_t* d_order,
                                 cudaStream_t s);
 
 // ---- render (rr_render.cu) --------------------------------------------------
-cudaError_t launch_render(const RenderParams& p, bool count_tests, int sm_count, cudaStream_t s);
-cudaError_t launch_primary(const RenderParams& p, int sm_count, cudaStream_t s);
+// slack: the instantiation with the per-ray culling slack (rr_render.cu RaySlack; chosen per frame by rr_api.cu frame_needs_slack)
+cudaError_t launch_render(const RenderParams& p, bool count_tests, bool slack, int sm_count, cudaStream_t s);
+cudaError_t launch_primary(const RenderParams& p, bool slack, int sm_count, cudaStream_t s);
 void default_tuning(Tuning& t);
 size_t render_stack_bytes_per_warp(uint32_t stack_entries);
 size_t render_cold_bytes_per_warp();

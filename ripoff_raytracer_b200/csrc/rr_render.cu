@@ -129,25 +129,47 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(xs));
   return r;
 }
-// `ek` is the per-ray slack of slab_slack() below: every slab is widened by it on both sides.
+// Per-ray part of the conservative culling slack.  The rounding error of a slab test (and of the triangle test's
+// `origin - A`, src/Trace.cl:283) grows with the ray ORIGIN, not with the box.  As long as the (mesh-local) origin stays
+// within 16x the largest box coordinate, the build-time box_delta (64 ulp of that coordinate) covers it and the kernel
+// runs without any per-ray term (SLACK = false: nothing below costs an instruction or a register).  For a camera far
+// outside, or a mesh posed with a tiny scale (origin / scale), the host (rr_api.cu frame_needs_slack) launches the
+// SLACK = true instantiation: every slab is additionally widened by ray_slack(origin) = 2^-18 of the largest |origin
+// coordinate| -- in the parametric form of the test ek = slack * |1/d| per axis (oracle/rr_oracle.c ray_slack states the
+// same bound; tests: |origin| / extent up to 10^4, tests/test_gpu_parity.py::test_far_origin_is_bit_exact).
+template <bool SLACK> struct RaySlack;
+template <> struct RaySlack<true> {
+  V3 e;
+  __device__ __forceinline__ float x() const { return e.x; }
+  __device__ __forceinline__ float y() const { return e.y; }
+  __device__ __forceinline__ float z() const { return e.z; }
+};
+template <> struct RaySlack<false> {
+  __device__ __forceinline__ float x() const { return 0.0f; }
+  __device__ __forceinline__ float y() const { return 0.0f; }
+  __device__ __forceinline__ float z() const { return 0.0f; }
+};
+__device__ __forceinline__ void make_slack(RaySlack<true>& r, const V3& o, const V3& inv) {
+  const float s = ray_slack(o.x, o.y, o.z);
+  r.e = mk(s * fabsf(inv.x), s * fabsf(inv.y), s * fabsf(inv.z));
+}
+__device__ __forceinline__ void make_slack(RaySlack<false>&, const V3&, const V3&) {}
+
+template <bool SLACK>
 __device__ __forceinline__ bool box_cull(float lox, float loy, float loz, float hix, float hiy, float hiz, const V3& inv,
-                                         const V3& noi, const V3& ek, float tbest, float& tn) {
+                                         const V3& noi, const RaySlack<SLACK>& ek, float tbest, float& tn) {
   const float t0x = __fmaf_rn(lox, inv.x, noi.x), t1x = __fmaf_rn(hix, inv.x, noi.x);
   const float t0y = __fmaf_rn(loy, inv.y, noi.y), t1y = __fmaf_rn(hiy, inv.y, noi.y);
   const float t0z = __fmaf_rn(loz, inv.z, noi.z), t1z = __fmaf_rn(hiz, inv.z, noi.z);
-  tn = fmaxf(fmaxf(fminf(t0x, t1x) - ek.x, fminf(t0y, t1y) - ek.y), fminf(t0z, t1z) - ek.z);
-  const float tf = fminf(fminf(fmaxf(t0x, t1x) + ek.x, fmaxf(t0y, t1y) + ek.y), fmaxf(t0z, t1z) + ek.z);
+  float tf;
+  if (SLACK) {
+    tn = fmaxf(fmaxf(fminf(t0x, t1x) - ek.x(), fminf(t0y, t1y) - ek.y()), fminf(t0z, t1z) - ek.z());
+    tf = fminf(fminf(fmaxf(t0x, t1x) + ek.x(), fmaxf(t0y, t1y) + ek.y()), fmaxf(t0z, t1z) + ek.z());
+  } else {
+    tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+    tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+  }
   return tf >= fmaxf(tn, 0.0f) && tn <= tbest;
-}
-// Per-ray part of the conservative culling slack.  The rounding error of a slab test (and of the triangle test's
-// `origin - A`, src/Trace.cl:283) grows with the ray ORIGIN, not with the box: a box is therefore widened, besides its
-// build-time box_delta, by ray_slack(origin) = 2^-18 of the largest |origin coordinate| in every direction -- in the
-// parametric form of the slab test that is ek = slack * |1/d| per axis (oracle/rr_oracle.c ray_slack states the same
-// bound).  Inside a scene it is of the size of box_delta; it matters for a camera far outside
-// (tests: |origin| / extent up to 10^4) and for meshes re-posed with a small scale (origin / scale).
-__device__ __forceinline__ V3 slab_slack(const V3& o, const V3& inv) {
-  const float s = ray_slack(o.x, o.y, o.z);
-  return mk(s * fabsf(inv.x), s * fabsf(inv.y), s * fabsf(inv.z));
 }
 
 constexpr int32_t NO_PRIM = 0x7fffffff;
@@ -306,6 +328,12 @@ constexpr int WARPS = NT / 32;
 constexpr int POOL = RR_POOL;    // path slots per warp (rr_internal.h)
 constexpr int ROUNDS = POOL / 32;
 enum { PH_PIXEL = 0, PH_SHADE = 1, PH_SETUP = 2, PH_TRAV = 3, PH_LEAF = 4 };
+#ifndef RR_ENTER_IN_SHADE
+#define RR_ENTER_IN_SHADE 0   // A/B switch: the shade phase enters the first candidate mesh of the next segment
+#endif
+#ifndef RR_FINISH_IN_SHADE
+#define RR_FINISH_IN_SHADE 0  // A/B switch: the shade phase finishes the last mesh of a ray (rr_render.cu done_key)
+#endif
 // Vote key of a slot: one byte per phase, so that ONE warp reduction (REDUX) over the keys counts the
 // ready slots of every phase.  A slot that needs a pixel has key 0 and W_PIX == PIX_NEED.
 constexpr uint32_t K_T = 1u, K_L = 1u << 8, K_S = 1u << 16, K_H = 1u << 24;
@@ -343,8 +371,9 @@ __device__ __forceinline__ uint32_t ref_count(int32_t r) { return (((uint32_t)(-
 // Every lane walks the whole chunk, so the loop is convergent.  Out of line: one copy serves shade, pixel and setup.
 // With a top level (`blocks` != nullptr, more than 32 meshes) the chunk is four blocks of eight meshes and a block
 // whose box the ray misses is skipped.
+template <bool SLACK>
 __device__ __noinline__ uint32_t scan_meshes_fn(const DMesh* __restrict__ meshes, const float4* __restrict__ blocks, int32_t base,
-                                                int32_t last_mesh, V3 winv, V3 wnoi, V3 wek, float tmax, unsigned* tests) {
+                                                int32_t last_mesh, V3 winv, V3 wnoi, RaySlack<SLACK> wek, float tmax, unsigned* tests) {
   uint32_t mask = 0;
   const int32_t end = min(base + 32, last_mesh + 1);
   for (int32_t k0 = base; k0 < end; k0 += 8) {
@@ -372,8 +401,9 @@ __device__ __noinline__ uint32_t scan_meshes_fn(const DMesh* __restrict__ meshes
 // level below (128, 512, 2048 ... meshes).  The walk needs no stack and no per-ray state: from chunk `c` onwards, at
 // every level whose span starts at c (top level first) a box the ray misses skips its whole span; returns the first
 // chunk the ray enters before `tmax`, or a value > last_chunk.  Out of line: scenes with at most 32 meshes never come here.
+template <bool SLACK>
 __device__ __noinline__ int32_t next_chunk_fn(const float4* __restrict__ tlas, const uint32_t* __restrict__ lv, int32_t c,
-                                              int32_t last_chunk, V3 winv, V3 wnoi, V3 wek, float tmax, unsigned* tests) {
+                                              int32_t last_chunk, V3 winv, V3 wnoi, RaySlack<SLACK> wek, float tmax, unsigned* tests) {
   const int levels = (int)__ldg(lv);  // lv: level count, then the first box of every level
   while (c <= last_chunk) {
     bool skipped = false;
@@ -395,7 +425,7 @@ __device__ __noinline__ int32_t next_chunk_fn(const float4* __restrict__ tlas, c
 __device__ __forceinline__ uint32_t smem_addr(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
 #endif
 
-template <bool COUNT, bool PRIMARY>
+template <bool COUNT, bool PRIMARY, bool SLACK>
 __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p) {
   extern __shared__ uint32_t pool_all[];
 #if RR_TOP_STAGE
@@ -503,10 +533,21 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     if (cur == REF_END && pend_cnt == 0) return K_S;  // mesh done: the setup phase finishes it and enters the next one
     return ((cur >= REF_POP && (speculate || pend_cnt == 0)) ? K_T : 0u) | (pend_cnt ? K_L : 0u);
   };
+#if RR_FINISH_IN_SHADE
+  // The walk of the LAST candidate mesh of a ray has ended: nothing is left to enter, so the slot goes straight to the
+  // shade phase, which finishes the mesh itself (one setup round per ray less).  mesh_word = W_M of the slot.
+  auto done_key = [&](uint32_t key, uint32_t mesh_word) -> uint32_t {
+    if (key != K_S || PW(W_CAND, s) != 0u) return key;
+    const int mesh_pos = (int)(mesh_word & WM_MESH) - 1;
+    return ((mesh_pos & ~31) + 32 > p.last_mesh) ? K_H : K_S;
+  };
+#else
+  auto done_key = [&](uint32_t key, uint32_t) -> uint32_t { return key; };
+#endif
 
-  auto scan_meshes = [&](int32_t base, const V3& winv, const V3& wnoi, const V3& wek, float tmax) -> uint32_t {
+  auto scan_meshes = [&](int32_t base, const V3& winv, const V3& wnoi, const RaySlack<SLACK>& wek, float tmax) -> uint32_t {
     unsigned tests = 0;
-    const uint32_t mask = scan_meshes_fn(p.meshes, p.tlas_blocks, base, p.last_mesh, winv, wnoi, wek, tmax, COUNT ? &tests : nullptr);
+    const uint32_t mask = scan_meshes_fn<SLACK>(p.meshes, p.tlas_blocks, base, p.last_mesh, winv, wnoi, wek, tmax, COUNT ? &tests : nullptr);
     if (COUNT) c_box += tests;
     return mask;
   };
@@ -549,14 +590,14 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   // Enters the next candidate mesh (src/Trace.cl:444-463): world box against the closest hit so far,
   // WorldToLocalRay, root box.  Returns the slot's new key (traversal started, or K_H: no candidate left).
   // One step of the search: false = look at the next candidate, true = done (`key` set).
-  auto enter_step = [&](const V3& winv, const V3& wnoi, const V3& wek, uint32_t& key) -> bool {
+  auto enter_step = [&](const V3& winv, const V3& wnoi, const RaySlack<SLACK>& wek, uint32_t& key) -> bool {
     {
       if (cand == 0) {
         int32_t base = (m & ~31) + 32;
         if (base > p.last_mesh) { key = K_H; return true; }
         if (p.tlas) {  // skip the chunks (and groups of chunks) the ray does not enter before the closest hit so far
           unsigned tests = 0;
-          base = next_chunk_fn(p.tlas, p.tlas_levels, base >> 5, p.last_mesh >> 5, winv, wnoi, wek, best_dst, COUNT ? &tests : nullptr) << 5;
+          base = next_chunk_fn<SLACK>(p.tlas, p.tlas_levels, base >> 5, p.last_mesh >> 5, winv, wnoi, wek, best_dst, COUNT ? &tests : nullptr) << 5;
           if (COUNT) c_box += tests;
           if (base > p.last_mesh) { key = K_H; return true; }
         }
@@ -578,7 +619,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         if (!box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, wek, best_dst, tn)) return false;
       }
       mflags = __float_as_uint(wlo.w);
-      V3 lek = wek;
+      RaySlack<SLACK> lek = wek;
       if (mflags & RR_MF_SPHERES) {
         lo = origin; ld = dir; linv = winv; lnoi = wnoi;
       } else {
@@ -598,7 +639,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         ld = normalize(ld);
         linv = mk(rcp_approx(ld.x), rcp_approx(ld.y), rcp_approx(ld.z));
         lnoi = mk(-(lo.x * linv.x), -(lo.y * linv.y), -(lo.z * linv.z));
-        lek = slab_slack(lo, linv);
+        make_slack(lek, lo, linv);
       }
       if (COUNT) c_box++;
       if (!box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, linv, lnoi, lek, INFINITY, tn)) return false;
@@ -623,7 +664,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       return true;
     }
   };
-  auto enter_next_mesh = [&](const V3& winv, const V3& wnoi, const V3& wek) -> uint32_t {
+  auto enter_next_mesh = [&](const V3& winv, const V3& wnoi, const RaySlack<SLACK>& wek) -> uint32_t {
     uint32_t key = 0;
     while (!enter_step(winv, wnoi, wek, key)) {}
     return key;
@@ -667,12 +708,25 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   };
   // shade / pixel start the next segment: reset the closest hit (src/Trace.cl:437-444), collect the candidate
   // meshes (convergent here: every lane of these phases does it) and hand the slot to the setup phase
-  auto store_new_ray = [&]() {
+  auto store_new_ray = [&](bool enter_now) {
     PST3(W_OX, s, origin);
     PST3(W_DX, s, dir);
     const V3 winv = mk(rcp_approx(dir.x), rcp_approx(dir.y), rcp_approx(dir.z));
     const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
-    PW(W_CAND, s) = scan_meshes(0, winv, wnoi, slab_slack(origin, winv), INFINITY);
+    RaySlack<SLACK> wek;
+    make_slack(wek, origin, winv);
+#if RR_ENTER_IN_SHADE
+    if (enter_now) {  // the shade phase enters the first candidate mesh itself: no setup round between shade and the first walk
+      cand = scan_meshes(0, winv, wnoi, wek, INFINITY);
+      m = 0; lback = false; mflags = 0u;
+      best_dst = INFINITY; best_mat = 0; best_back = false; best_mesh = 0x7fffffff; best_prim = -1;
+      lprim = NO_PRIM;
+      n_rays++;
+      store_ray_state(enter_next_mesh(winv, wnoi, wek));
+      return;
+    }
+#endif
+    PW(W_CAND, s) = scan_meshes(0, winv, wnoi, wek, INFINITY);
     PW(W_M, s) = 1u;  // chunk 0, no backface flag
     PSF(W_BDST, s, INFINITY);
     PW(W_BMAT, s) = 0u;
@@ -730,9 +784,15 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       } else {
         cur = REF_END; sp = 0; pend_cnt = 0;
       }
-      // the per-ray slack (slab_slack) is folded into the offsets: entry planes move towards the origin, exit planes away
-      const V3 lek = slab_slack(lo, linv);
-      const V3 nnoi = lnoi - lek, fnoi = lnoi + lek;
+      // SLACK: the per-ray slack is folded into the offsets -- entry planes move towards the origin, exit planes away
+      // (three more registers in the loop; without SLACK nnoi and fnoi ARE lnoi)
+      V3 nnoi = lnoi, fnoi = lnoi;
+      if (SLACK) {
+        RaySlack<true> lek;
+        make_slack(lek, lo, linv);
+        nnoi = lnoi - lek.e;
+        fnoi = lnoi + lek.e;
+      }
       // which quad of a node holds the entry / exit plane of each axis (node layout: min.x min.y min.z max.x max.y max.z)
       const int qnx = linv.x < 0.0f ? 3 : 0, qny = linv.y < 0.0f ? 4 : 1, qnz = linv.z < 0.0f ? 5 : 2;
       const int qfx = 3 - qnx, qfy = 5 - qny, qfz = 7 - qnz;
@@ -851,7 +911,9 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         PW(W_PSLOT, s) = pend_slot;
         PW(W_TOPN, s) = top.x;
         PW(W_TOPD, s) = top.y;
-        PW(W_KEY, s) = trav_key();
+        uint32_t key = trav_key();
+        if (RR_FINISH_IN_SHADE && key == K_S) key = done_key(key, PW(W_M, s));
+        PW(W_KEY, s) = key;
       }
     } else if (phase == PH_LEAF) {
       // ================= leaf tests =================
@@ -959,7 +1021,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         }
         PW(W_SPC, s) = (uint32_t)sp | (pend_cnt << 8);
         PW(W_PSLOT, s) = pend_slot;
-        PW(W_KEY, s) = trav_key();
+        PW(W_KEY, s) = done_key(trav_key(), mw);
       }
     } else if (phase == PH_SETUP) {
       // ================= finish the current mesh, enter the next candidate (src/Trace.cl:444-482) =================
@@ -972,7 +1034,9 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
         load_ray_state();
         finish_mesh();  // nothing to finish for a new ray (no local hit)
-        const uint32_t key = enter_next_mesh(winv, wnoi, slab_slack(origin, winv));
+        RaySlack<SLACK> wek;
+        make_slack(wek, origin, winv);
+        const uint32_t key = enter_next_mesh(winv, wnoi, wek);
         store_ray_state(key);
       }
     } else if (phase == PH_SHADE) {
@@ -987,6 +1051,18 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         best_mat = (int32_t)(bm & 0x7fffffffu);
         best_back = (bm >> 31) != 0u;
         if (PRIMARY) { best_mesh = min(best_mat, p.n_meshes); best_prim = (int32_t)CW(C_BPRIM, s); }
+#if RR_FINISH_IN_SHADE
+        lprim = (int32_t)PW(W_LPRIM, s);
+        if (lprim != NO_PRIM) {  // the last mesh walked still holds its closest hit: LocalToWorldHit + keep-min here (done_key)
+          load_mesh_word();
+          best_mesh = best_dst < INFINITY ? min(best_mat, p.n_meshes) : 0x7fffffff;
+          mflags = __float_as_uint(__ldg(&p.meshes[m].wmin.w));
+          lo = PLD3(W_LOX, s);
+          ld = PLD3(W_LDX, s);
+          lt = PF(W_LT, s);
+          finish_mesh();
+        }
+#endif
         pix = (int32_t)PW(W_PIX, s);
         if (PRIMARY) {
           if (p.hit_mesh) p.hit_mesh[pix] = best_dst < INFINITY ? best_mesh : -1;
@@ -1041,7 +1117,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
           CW(C_RNG, s) = rng;
           CW(C_SAMPLE, s) = sample;
           CW(C_BOUNCE, s) = bounce | (passes << 23);  // bounce <= max_bounces <= RR_MAX_BOUNCES, passes <= 257
-          store_new_ray();
+          store_new_ray(true);
         }
       }
       n_need += __popc(__ballot_sync(full, pixel_done));
@@ -1085,7 +1161,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             CSF(C_INC, s, 0.0f); CSF(C_INC1, s, 0.0f); CSF(C_INC2, s, 0.0f);
             origin = cam_pos;
             dir = pd;
-            store_new_ray();
+            store_new_ray(false);
             need = false;
           }
         }
@@ -1169,16 +1245,16 @@ static cudaError_t launch_persistent(K kernel, const RenderParams& p, int sm_cou
   return cudaGetLastError();
 }
 
-cudaError_t launch_render(const RenderParams& p, bool count_tests, int sm_count, cudaStream_t s) {
-  if (count_tests) return launch_persistent(k_render<true, false>, p, sm_count, s);
-  return launch_persistent(k_render<false, false>, p, sm_count, s);
+cudaError_t launch_render(const RenderParams& p, bool count_tests, bool slack, int sm_count, cudaStream_t s) {
+  if (count_tests) return slack ? launch_persistent(k_render<true, false, true>, p, sm_count, s) : launch_persistent(k_render<true, false, false>, p, sm_count, s);
+  return slack ? launch_persistent(k_render<false, false, true>, p, sm_count, s) : launch_persistent(k_render<false, false, false>, p, sm_count, s);
 }
 
 // Primary-ray closest hit per pixel (MakeRay + CalculateRayCollisionWithTriangle): the same kernel, stopped
 // at the first shade phase.
-cudaError_t launch_primary(const RenderParams& p, int sm_count, cudaStream_t s) {
+cudaError_t launch_primary(const RenderParams& p, bool slack, int sm_count, cudaStream_t s) {
   if (!p.width || !p.height) return cudaSuccess;
-  return launch_persistent(k_render<false, true>, p, sm_count, s);
+  return slack ? launch_persistent(k_render<false, true, true>, p, sm_count, s) : launch_persistent(k_render<false, true, false>, p, sm_count, s);
 }
 
 size_t render_stack_bytes_per_warp(uint32_t stack_entries) { return (size_t)stack_entries * POOL * sizeof(uint2); }
