@@ -364,8 +364,9 @@ static_assert(NW == RR_POOL_WORDS && NC == RR_COLD_WORDS, "rr_internal.h RR_POOL
 constexpr int32_t REF_POP = -1;                   // take the next entry of the stack
 constexpr int32_t REF_END = (int32_t)0x80000000;  // traversal of this mesh finished
 __device__ __forceinline__ bool ref_is_leaf(int32_t r) { return r < REF_POP && r != REF_END; }
-__device__ __forceinline__ uint32_t ref_slot(int32_t r) { return ((uint32_t)(-r) - 2u) >> 2; }
-__device__ __forceinline__ uint32_t ref_count(int32_t r) { return (((uint32_t)(-r) - 2u) & 3u) + 1u; }
+// The leaf word (first slot << 2 | count - 1) of a leaf reference.  The node-step loop only carries it (pend_slot) with
+// a "one leaf is postponed" flag (pend_cnt = 1); the leaf phase takes it apart.
+__device__ __forceinline__ uint32_t ref_leaf_word(int32_t r) { return (uint32_t)(-r) - 2u; }
 
 // World-box tests of the meshes [base, base + 32): bit k set = the ray enters mesh base + k's box before `tmax`.
 // Every lane walks the whole chunk, so the loop is convergent.  Out of line: one copy serves shade, pixel and setup.
@@ -650,8 +651,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       lprim = NO_PRIM; lback = false;
       sp = 0;
       if (count <= RR_DIRECT_MAX) {  // no hierarchy: the primitives are tested one by one in the leaf phase
-        pend_slot = (mflags & RR_MF_SPHERES) ? 0u : first;
-        pend_cnt = count;
+        pend_slot = (((mflags & RR_MF_SPHERES) ? 0u : first) << 2) | (count - 1u);  // leaf word: all 1 - 4 primitives at once
+        pend_cnt = 1;
         cur = REF_END;
       } else {
         pend_cnt = 0;
@@ -821,7 +822,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             if (!found) { cur = REF_END; break; }
           }
           if (next >= 0) { cur = next; break; }
-          if (pend_cnt == 0) { pend_slot = ref_slot(next); pend_cnt = ref_count(next); next = REF_POP; continue; }
+          if (pend_cnt == 0) { pend_slot = ref_leaf_word(next); pend_cnt = 1; next = REF_POP; continue; }
           cur = next;  // a second leaf while one is postponed: wait for the leaf phase
           break;
         }
@@ -880,7 +881,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             int32_t r0 = ref_of(k0), r1 = ref_of(k1), r2 = ref_of(k2), r3 = ref_of(k3);
             int hits = (k0 != 0xffffffffu) + (k1 != 0xffffffffu) + (k2 != 0xffffffffu) + (k3 != 0xffffffffu);
             if (hits > 0 && r0 < REF_POP && pend_cnt == 0) {  // the nearest child is a leaf: postpone it, go on with the next one
-              pend_slot = ref_slot(r0); pend_cnt = ref_count(r0);
+              pend_slot = ref_leaf_word(r0); pend_cnt = 1;
               k0 = k1; k1 = k2; k2 = k3;
               r0 = r1; r1 = r2; r2 = r3;
               hits--;
@@ -888,8 +889,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             // misses sort last, so the children to push are a suffix of the hits: farthest first, the nearest of
             // them ends up as the (register-resident) top; the previous top is spilled once
             if (hits >= 2 && sp + hits - 1 > (int)p.stack_entries) {
-              // cannot happen (3 entries per wide level + 4); counted, not hidden: the host fails the render with RR_ERR_BVH_DEPTH
-              atomicAdd(&p.counters->stack_overflows, 1ull);
+              tstate[5] = 1u;  // cannot happen (3 entries per wide level + 4 are allocated); flagged, not hidden: RR_ERR_BVH_DEPTH
             } else if (hits >= 2) {
               uint2* const w = stk + sp * POOL;  // one address; the stores below use constant offsets from it
               if (sp > 0) w[-POOL] = top;
@@ -933,10 +933,12 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         V3 n3 = mk(0, 0, 0), nbest = n3;  // normal of the primitive under test / of the closest accepted hit
         // One primitive per round for a leaf of a hierarchy; the 2 - 4 primitives of a hierarchy-less mesh (the Cornell
         // quads) are tested back to back: a round trip through the vote per triangle costs more than the idle lanes.
+        uint32_t leaf_slot = pend_slot >> 2, leaf_left = (pend_slot & 3u) + 1u;  // the postponed leaf: 1 - 4 consecutive sorted slots
+#pragma unroll 1
         do {
-        const uint32_t slot = pend_slot;
-        pend_slot++;
-        pend_cnt--;
+        const uint32_t slot = leaf_slot;
+        leaf_slot++;
+        leaf_left--;
         if (mw & WM_SPHERES) {
           // EXTENSION (the reference kernel has no sphere primitive): semantics of oracle/rr_oracle.c ray_sphere
           if (COUNT) c_sph++;
@@ -1006,7 +1008,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             }
           }
         }
-        } while (pend_cnt > 0);
+        } while (leaf_left > 0);
+        pend_cnt = 0;
         if (accepted) {
           PSF(W_LT, s, lt);
           PW(W_LPRIM, s) = (uint32_t)lprim;
@@ -1014,8 +1017,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
           CST3(C_LNX, s, nbest);
         }
         if (pend_cnt == 0 && ref_is_leaf(cur)) {  // the leaf this slot was waiting on becomes the postponed one
-          pend_slot = ref_slot(cur);
-          pend_cnt = ref_count(cur);
+          pend_slot = ref_leaf_word(cur);
+          pend_cnt = 1;
           cur = REF_POP;
           PW(W_CUR, s) = (uint32_t)cur;
         }
@@ -1190,9 +1193,11 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   unsigned long long r = n_rays;  // summed over the warp in 64 bits
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) r += __shfl_xor_sync(full, r, off);
+  __syncwarp();
   if (lane == 0) {
     atomicAdd(&p.counters->rays, r);
     atomicAdd(&p.counters->tiles, (unsigned long long)n_tiles);
+    if (tstate[5]) atomicAdd(&p.counters->stack_overflows, 1ull);  // warps that dropped pushes
   }
   if (COUNT) {
     unsigned long long b = c_box, t = c_tri, sq = c_sph;
