@@ -224,7 +224,14 @@ typedef struct rr_stats {
  * reference always evaluates to 0 (src/image.hpp:228).  tile_size == 0 picks
  * the library default (8 x 4 pixels, the unit one warp pops from the tile
  * queue); larger values are honoured up to 32 x 32.  The image does not depend
- * on it. */
+ * on it.
+ * Supported geometry range: the closest hit is the brute-force minimum over all primitives (the hierarchy only
+ * culls) as long as ray origins -- the camera and every hit point, taken into each mesh's local space, i.e.
+ * (origin - pos) / scale -- stay within 10^4 times the mesh's extent; the library switches to a kernel with a
+ * per-ray culling slack by itself when a frame leaves the range its build-time box slack covers (16x).  Beyond
+ * 10^4 float32 no longer resolves the mesh's triangles from the origin and isolated pixels may differ from the
+ * brute-force result (tests/test_gpu_parity.py::test_far_origin_is_bit_exact).
+ * max_bounces <= 8388607. */
 int rr_render(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_bounces,
               int32_t frame_index, uint32_t tile_size, uint8_t* rgba_out);
 

@@ -131,6 +131,7 @@ struct Device {
   std::vector<rr_mesh> h_meshes;
   std::vector<float> h_mesh_absmax;
   float h_sph_absmax = 0.0f;
+  int h_sphere_materials = 0;  // RR_FEAT_MATERIALS if a sphere has a Checker / Glassy / Invisible material
   float4* tlas_blocks = nullptr;      // > 32 meshes: the implicit top-level tree, one allocation: block boxes ...
   float4* tlas = nullptr;             // ... then the chunk level and the levels above it (RenderParams::tlas)
   uint32_t* tlas_levels = nullptr;    // device: level count, first box of every level (RenderParams::tlas_levels)
@@ -680,7 +681,9 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
   RR_CUDA(launch_pack_tris(d.tris, d.tb.order, d.tb.n, d.tri_geom, d.tri_nrm, st));
   RR_CUDA(launch_sphere_boxes(d.spheres, n_spheres, d.sph_box, st));
   uint32_t sf = 0, sc = (uint32_t)n_spheres;
-  RR_CUDA(lbvh_build(d.sb, d.sph_box, n_spheres, &sf, &sc, n_spheres ? 1u : 0u, (int32_t)d.tb.n, leaf_max, st));
+  uint32_t sphere_leaf_max = RR_LEAF_DEFAULT_SPHERES;
+  if (const char* e = getenv("RR_LEAF_MAX_SPHERES")) sphere_leaf_max = (uint32_t)std::max(1, atoi(e));
+  RR_CUDA(lbvh_build(d.sb, d.sph_box, n_spheres, &sf, &sc, n_spheres ? 1u : 0u, (int32_t)d.tb.n, sphere_leaf_max, st));
   RR_CUDA(dev_malloc(&d.sph_geom, std::max<size_t>(n_spheres, 1) * 16));
   RR_CUDA(launch_pack_spheres(d.spheres, d.sb.order, d.sb.n, d.sph_geom, st));
   // one node array: triangle hierarchies at [0, tb.n), the sphere hierarchy behind them
@@ -751,6 +754,11 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
     if (!plan.first.empty()) RR_CUDA(cudaMemcpy(sb.data(), d.tb.seg_box, plan.first.size() * 24, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < n_meshes; ++i) d.h_mesh_absmax[i] = plan.count[plan.mesh_seg[i]] ? absmax6(&sb[6 * plan.mesh_seg[i]]) : 0.0f;
     d.h_sph_absmax = 0.0f;
+    d.h_sphere_materials = 0;
+    for (size_t i = 0; i < n_spheres; ++i) {
+      const int t = spheres[i].material.type;
+      if (t == RR_MATERIAL_CHECKER || t == RR_MATERIAL_GLASSY || t == RR_MATERIAL_INVISIBLE) d.h_sphere_materials = RR_FEAT_MATERIALS;
+    }
     if (n_spheres) {
       float b6[6];
       RR_CUDA(cudaMemcpy(b6, d.sb.seg_box, 24, cudaMemcpyDeviceToHost));
@@ -826,6 +834,20 @@ static bool frame_needs_slack(const rr_ctx* ctx, const Device& d, const rr_camer
     if (O > 256.0f * std::max(P, 0.5f * m.scale * A)) return true;  // world-space tests: the mesh's world box
   }
   return false;
+}
+
+// RR_FEAT_* bits of the scene as it is now (materials can change through rr_update_meshes).  Tuning bit 6 (64) forces
+// the instantiation with everything (A/B).
+static int scene_features(const rr_ctx* ctx, const Device& d) {
+  if (ctx->tune.speculate & 64u) return RR_FEAT_ALL;
+  int f = d.h_sphere_materials;
+  if (ctx->n_spheres) f |= RR_FEAT_SPHERES;
+  if (ctx->n_meshes + (ctx->n_spheres ? 1 : 0) > 32) f |= RR_FEAT_TLAS;
+  for (const rr_mesh& m : d.h_meshes) {
+    const int t = m.material.type;
+    if (t == RR_MATERIAL_CHECKER || t == RR_MATERIAL_GLASSY || t == RR_MATERIAL_INVISIBLE) { f |= RR_FEAT_MATERIALS; break; }
+  }
+  return f;
 }
 
 static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam, uint32_t W, uint32_t H, uint32_t spp,
@@ -948,7 +970,7 @@ static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t 
     }
     if (want_radiance) p.radiance = d.radiance;
     RR_CUDA(cudaEventRecord(d.ev0, d.stream));
-    RR_CUDA(launch_render(p, count_tests, frame_needs_slack(ctx, d, cam), d.sm_count, d.stream));
+    RR_CUDA(launch_render(p, count_tests, frame_needs_slack(ctx, d, cam), scene_features(ctx, d), d.sm_count, d.stream));
     RR_CUDA(cudaEventRecord(d.ev1, d.stream));
   }
   Counters total;

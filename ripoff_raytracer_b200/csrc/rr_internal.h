@@ -18,6 +18,9 @@
 #ifndef RR_LEAF_DEFAULT
 #define RR_LEAF_DEFAULT 2             // what rr_upload_scene builds with
 #endif
+#ifndef RR_LEAF_DEFAULT_SPHERES
+#define RR_LEAF_DEFAULT_SPHERES 2     // ... for the sphere hierarchy
+#endif
 #define RR_MAX_PRIMS 0x1ffffff0ull    // ... and the first sorted slot in the 29 bits above them
 #define RR_TILE_W 8                   // default work tile: 8 x 4 pixels = one warp
 #define RR_TILE_H 4
@@ -118,6 +121,12 @@ struct Tuning {
   uint32_t ctas_per_sm; // persistent CTAs per SM (0 = default)
 };
 
+// Scene features (k_render<..., FEAT>)
+#define RR_FEAT_SPHERES 1     // the sphere set
+#define RR_FEAT_MATERIALS 2   // Checker / Glassy / Invisible materials (Solid and OneSided are always compiled in)
+#define RR_FEAT_TLAS 4        // more than 32 meshes: the implicit top level
+#define RR_FEAT_ALL 7
+
 #define RR_TLAS_MAX_LEVELS 14  // 4^13 chunks of 32 meshes: more than the 31-bit mesh index allows
 
 // Everything a render kernel needs (passed by value).
@@ -207,7 +216,8 @@ cudaError_t launch_pack_spheres(const rr_sphere* d_sph, const uint32_t* d_order,
 
 // ---- render (rr_render.cu) --------------------------------------------------
 // slack: the instantiation with the per-ray culling slack (rr_render.cu RaySlack; chosen per frame by rr_api.cu frame_needs_slack)
-cudaError_t launch_render(const RenderParams& p, bool count_tests, bool slack, int sm_count, cudaStream_t s);
+// feat: RR_FEAT_* bits of the uploaded scene; the kernel instantiation without the code of absent features is launched
+cudaError_t launch_render(const RenderParams& p, bool count_tests, bool slack, int feat, int sm_count, cudaStream_t s);
 cudaError_t launch_primary(const RenderParams& p, bool slack, int sm_count, cudaStream_t s);
 void default_tuning(Tuning& t);
 size_t render_stack_bytes_per_warp(uint32_t stack_entries);

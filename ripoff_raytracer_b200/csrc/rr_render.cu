@@ -213,6 +213,8 @@ __device__ __forceinline__ float reflectance(V3 inDir, V3 n, float iorA, float i
 
 // One bounce of Trace() after the closest hit is known (src/Trace.cl:497-591).
 // Returns false when the path ends.  `bounce` is advanced as the reference does.
+// MATERIALS = false: the scene has only Solid and OneSided materials (RR_FEAT_MATERIALS); the other branches are left out.
+template <bool MATERIALS>
 __device__ __forceinline__ bool shade(const RenderParams& p, const SceneHit& hit, V3& origin, V3& dir, V3& throughput,
                                       V3& incoming, uint32_t& bounce, uint32_t& passes, uint32_t& rng) {
   if (!hit.did) return false;
@@ -221,7 +223,7 @@ __device__ __forceinline__ bool shade(const RenderParams& p, const SceneHit& hit
   const float4 m0 = __ldg(reinterpret_cast<const float4*>(M)), m1 = __ldg(reinterpret_cast<const float4*>(M) + 1),
                m2 = __ldg(reinterpret_cast<const float4*>(M) + 2);
   const int32_t type = __float_as_int(m0.x);
-  if (type == RR_MATERIAL_INVISIBLE) {
+  if (MATERIALS && type == RR_MATERIAL_INVISIBLE) {
     // `continue` without counting a bounce (:502-506).  Guard: when hit.point + dir*1e-6 rounds back
     // to hit.point the reference loops forever; the path is ended after RR_MAX_INVISIBLE_PASSES.
     if (++passes > RR_MAX_INVISIBLE_PASSES) return false;
@@ -233,7 +235,7 @@ __device__ __forceinline__ bool shade(const RenderParams& p, const SceneHit& hit
   float emissionStrength = m0.z;
   const float specProb = m1.w;
   const float reflectiveness = m0.w;
-  if (type == RR_MATERIAL_CHECKER) {  // :509-533
+  if (MATERIALS && type == RR_MATERIAL_CHECKER) {  // :509-533
     const float size = emissionStrength;
     const int xi = (int)floorf(hit.point.x / size);
     const int zi = (int)floorf(hit.point.z / size);
@@ -241,12 +243,12 @@ __device__ __forceinline__ bool shade(const RenderParams& p, const SceneHit& hit
     color = isEven ? color : emissionColor;
     emissionStrength = 0.0f;
   }
-  if (type == RR_MATERIAL_CHECKER || type == RR_MATERIAL_SOLID) {  // :525-532, :559-567
+  if ((MATERIALS && type == RR_MATERIAL_CHECKER) || type == RR_MATERIAL_SOLID) {  // :525-532, :559-567
     const bool isSpec = specProb >= random_value(rng);
     const V3 diffuseDir = normalize(hit.normal + random_direction(rng));
     const V3 specularDir = reflect3(dir, hit.normal);
     dir = normalize(lerp3(diffuseDir, specularDir, reflectiveness * (isSpec ? 1.0f : 0.0f)));
-  } else if (type == RR_MATERIAL_GLASSY) {  // :534-558
+  } else if (MATERIALS && type == RR_MATERIAL_GLASSY) {  // :534-558
     const float ior = m0.y;
     const float iorCur = hit.back ? ior : 1.0f;
     const float iorNext = hit.back ? 1.0f : ior;
@@ -372,14 +374,14 @@ __device__ __forceinline__ uint32_t ref_leaf_word(int32_t r) { return (uint32_t)
 // Every lane walks the whole chunk, so the loop is convergent.  Out of line: one copy serves shade, pixel and setup.
 // With a top level (`blocks` != nullptr, more than 32 meshes) the chunk is four blocks of eight meshes and a block
 // whose box the ray misses is skipped.
-template <bool SLACK>
+template <bool SLACK, bool TLAS>
 __device__ __noinline__ uint32_t scan_meshes_fn(const DMesh* __restrict__ meshes, const float4* __restrict__ blocks, int32_t base,
                                                 int32_t last_mesh, V3 winv, V3 wnoi, RaySlack<SLACK> wek, float tmax, unsigned* tests) {
   uint32_t mask = 0;
   const int32_t end = min(base + 32, last_mesh + 1);
   for (int32_t k0 = base; k0 < end; k0 += 8) {
     float tn;
-    if (blocks) {
+    if (TLAS && blocks) {
       const float4 blo = __ldg(blocks + 2 * (k0 >> 3)), bhi = __ldg(blocks + 2 * (k0 >> 3) + 1);
       if (tests) ++*tests;
       if (!box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, winv, wnoi, wek, tmax, tn)) continue;
@@ -426,8 +428,12 @@ __device__ __noinline__ int32_t next_chunk_fn(const float4* __restrict__ tlas, c
 __device__ __forceinline__ uint32_t smem_addr(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
 #endif
 
-template <bool COUNT, bool PRIMARY, bool SLACK>
+// FEAT: the scene features this instantiation contains code for (RR_FEAT_*, rr_internal.h).  The kernel's cost is
+// dominated by the code a warp streams through, so a scene without spheres, without Checker /
+// Glassy / Invisible materials and with at most 32 meshes runs an instantiation that is 8 KB (15 %) smaller.
+template <bool COUNT, bool PRIMARY, bool SLACK, int FEAT>
 __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p) {
+  constexpr bool F_SPHERES = (FEAT & RR_FEAT_SPHERES) != 0, F_MATERIALS = (FEAT & RR_FEAT_MATERIALS) != 0, F_TLAS = (FEAT & RR_FEAT_TLAS) != 0;
   extern __shared__ uint32_t pool_all[];
 #if RR_TOP_STAGE
   // Top of the largest hierarchy staged in shared memory (north_star: "shared-memory or TMA staging of the BVH top
@@ -548,7 +554,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
 
   auto scan_meshes = [&](int32_t base, const V3& winv, const V3& wnoi, const RaySlack<SLACK>& wek, float tmax) -> uint32_t {
     unsigned tests = 0;
-    const uint32_t mask = scan_meshes_fn<SLACK>(p.meshes, p.tlas_blocks, base, p.last_mesh, winv, wnoi, wek, tmax, COUNT ? &tests : nullptr);
+    const uint32_t mask = scan_meshes_fn<SLACK, F_TLAS>(p.meshes, p.tlas_blocks, base, p.last_mesh, winv, wnoi, wek, tmax, COUNT ? &tests : nullptr);
     if (COUNT) c_box += tests;
     return mask;
   };
@@ -559,7 +565,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     if (lprim == NO_PRIM) return;
     const DMesh* M = p.meshes + m;
     const int32_t mesh_index = __float_as_int(__ldg(&M->wmax.w));
-    if (mflags & RR_MF_SPHERES) {
+    if (F_SPHERES && (mflags & RR_MF_SPHERES)) {
       const int32_t mat = mesh_index + lprim;
       const int32_t type = __ldg(&p.materials[mat].type);
       if (!(type == RR_MATERIAL_ONESIDED && lback) && (lt < best_dst || (lt == best_dst && mesh_index < best_mesh))) {
@@ -596,7 +602,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       if (cand == 0) {
         int32_t base = (m & ~31) + 32;
         if (base > p.last_mesh) { key = K_H; return true; }
-        if (p.tlas) {  // skip the chunks (and groups of chunks) the ray does not enter before the closest hit so far
+        if (F_TLAS && p.tlas) {  // skip the chunks (and groups of chunks) the ray does not enter before the closest hit so far
           unsigned tests = 0;
           base = next_chunk_fn<SLACK>(p.tlas, p.tlas_levels, base >> 5, p.last_mesh >> 5, winv, wnoi, wek, best_dst, COUNT ? &tests : nullptr) << 5;
           if (COUNT) c_box += tests;
@@ -621,7 +627,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       }
       mflags = __float_as_uint(wlo.w);
       RaySlack<SLACK> lek = wek;
-      if (mflags & RR_MF_SPHERES) {
+      if (F_SPHERES && (mflags & RR_MF_SPHERES)) {
         lo = origin; ld = dir; linv = winv; lnoi = wnoi;
       } else {
         // WorldToLocalRay, src/Trace.cl:118-137
@@ -647,11 +653,11 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       const uint32_t first = __float_as_uint(blo.w), count = __float_as_uint(bhi.w);
       // The sphere set lives in world space and is the last entry in the tie order (highest mesh index): a sphere at or
       // beyond the closest hit so far can never win, so its walk starts with that distance as the bound.
-      lt = (mflags & RR_MF_SPHERES) ? best_dst : INFINITY;
+      lt = (F_SPHERES && (mflags & RR_MF_SPHERES)) ? best_dst : INFINITY;
       lprim = NO_PRIM; lback = false;
       sp = 0;
       if (count <= RR_DIRECT_MAX) {  // no hierarchy: the primitives are tested one by one in the leaf phase
-        pend_slot = (((mflags & RR_MF_SPHERES) ? 0u : first) << 2) | (count - 1u);  // leaf word: all 1 - 4 primitives at once
+        pend_slot = (((F_SPHERES && (mflags & RR_MF_SPHERES)) ? 0u : first) << 2) | (count - 1u);  // leaf word: all 1 - 4 primitives at once
         pend_cnt = 1;
         cur = REF_END;
       } else {
@@ -676,7 +682,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     PW(W_BMAT, s) = (uint32_t)best_mat | (best_back ? 0x80000000u : 0u);
     if (PRIMARY) CW(C_BPRIM, s) = (uint32_t)best_prim;
     PW(W_CAND, s) = cand;
-    PW(W_M, s) = (uint32_t)(m + 1) | (lback ? WM_BACK : 0u) | ((mflags & RR_MF_SPHERES) ? WM_SPHERES : 0u) |
+    PW(W_M, s) = (uint32_t)(m + 1) | (lback ? WM_BACK : 0u) | ((F_SPHERES && (mflags & RR_MF_SPHERES)) ? WM_SPHERES : 0u) |
                  ((mflags & RR_MF_CULL) ? WM_CULL : 0u);
     PST3(W_LOX, s, lo);
     PST3(W_LDX, s, ld);
@@ -939,7 +945,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         const uint32_t slot = leaf_slot;
         leaf_slot++;
         leaf_left--;
-        if (mw & WM_SPHERES) {
+        if (F_SPHERES && (mw & WM_SPHERES)) {
           // EXTENSION (the reference kernel has no sphere primitive): semantics of oracle/rr_oracle.c ray_sphere
           if (COUNT) c_sph++;
           const float4 cr = __ldg(p.sph_geom + slot);
@@ -1086,7 +1092,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
           hit.back = best_back;
           hit.material = best_mat;
           V3 throughput = CLD3(C_THR, s), incoming = CLD3(C_INC, s);
-          bool alive = shade(p, hit, origin, dir, throughput, incoming, bounce, passes, rng);
+          bool alive = shade<F_MATERIALS>(p, hit, origin, dir, throughput, incoming, bounce, passes, rng);
           alive = alive && bounce < p.max_bounces;
           if (alive) {
             CST3(C_THR, s, throughput);
@@ -1250,16 +1256,34 @@ static cudaError_t launch_persistent(K kernel, const RenderParams& p, int sm_cou
   return cudaGetLastError();
 }
 
-cudaError_t launch_render(const RenderParams& p, bool count_tests, bool slack, int sm_count, cudaStream_t s) {
-  if (count_tests) return slack ? launch_persistent(k_render<true, false, true>, p, sm_count, s) : launch_persistent(k_render<true, false, false>, p, sm_count, s);
-  return slack ? launch_persistent(k_render<false, false, true>, p, sm_count, s) : launch_persistent(k_render<false, false, false>, p, sm_count, s);
+// The production kernel exists once per feature set (without the per-ray slack) and once with everything (with it); the
+// instrumented and the primary-hit kernels only with everything.
+template <int FEAT>
+static cudaError_t launch_lean(const RenderParams& p, int sm_count, cudaStream_t s) {
+  return launch_persistent(k_render<false, false, false, FEAT>, p, sm_count, s);
+}
+cudaError_t launch_render(const RenderParams& p, bool count_tests, bool slack, int feat, int sm_count, cudaStream_t s) {
+  constexpr int ALL = RR_FEAT_ALL;
+  if (count_tests) return slack ? launch_persistent(k_render<true, false, true, ALL>, p, sm_count, s) : launch_persistent(k_render<true, false, false, ALL>, p, sm_count, s);
+  if (slack) return launch_persistent(k_render<false, false, true, ALL>, p, sm_count, s);
+  switch (feat & ALL) {
+    case 0: return launch_lean<0>(p, sm_count, s);
+    case 1: return launch_lean<1>(p, sm_count, s);
+    case 2: return launch_lean<2>(p, sm_count, s);
+    case 3: return launch_lean<3>(p, sm_count, s);
+    case 4: return launch_lean<4>(p, sm_count, s);
+    case 5: return launch_lean<5>(p, sm_count, s);
+    case 6: return launch_lean<6>(p, sm_count, s);
+    default: return launch_lean<7>(p, sm_count, s);
+  }
 }
 
 // Primary-ray closest hit per pixel (MakeRay + CalculateRayCollisionWithTriangle): the same kernel, stopped
 // at the first shade phase.
 cudaError_t launch_primary(const RenderParams& p, bool slack, int sm_count, cudaStream_t s) {
   if (!p.width || !p.height) return cudaSuccess;
-  return slack ? launch_persistent(k_render<false, true, true>, p, sm_count, s) : launch_persistent(k_render<false, true, false>, p, sm_count, s);
+  return slack ? launch_persistent(k_render<false, true, true, RR_FEAT_ALL>, p, sm_count, s)
+               : launch_persistent(k_render<false, true, false, RR_FEAT_ALL>, p, sm_count, s);
 }
 
 size_t render_stack_bytes_per_warp(uint32_t stack_entries) { return (size_t)stack_entries * POOL * sizeof(uint2); }
