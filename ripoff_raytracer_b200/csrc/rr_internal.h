@@ -19,7 +19,7 @@
 #define RR_LEAF_DEFAULT 2             // what rr_upload_scene builds with
 #endif
 #ifndef RR_LEAF_DEFAULT_SPHERES
-#define RR_LEAF_DEFAULT_SPHERES 2     // ... for the sphere hierarchy
+#define RR_LEAF_DEFAULT_SPHERES 1     // ... for the sphere hierarchy (one sphere per leaf measured best: C2 +6.6 %, C4 +2.8 % over two)
 #endif
 #define RR_MAX_PRIMS 0x1ffffff0ull    // ... and the first sorted slot in the 29 bits above them
 #define RR_TILE_W 8                   // default work tile: 8 x 4 pixels = one warp

@@ -330,6 +330,9 @@ constexpr int WARPS = NT / 32;
 constexpr int POOL = RR_POOL;    // path slots per warp (rr_internal.h)
 constexpr int ROUNDS = POOL / 32;
 enum { PH_PIXEL = 0, PH_SHADE = 1, PH_SETUP = 2, PH_TRAV = 3, PH_LEAF = 4 };
+#ifndef RR_LEAF_PIPELINE
+#define RR_LEAF_PIPELINE 0
+#endif
 #ifndef RR_ENTER_IN_SHADE
 #define RR_ENTER_IN_SHADE 0   // A/B switch: the shade phase enters the first candidate mesh of the next segment
 #endif
@@ -940,12 +943,13 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         // One primitive per round for a leaf of a hierarchy; the 2 - 4 primitives of a hierarchy-less mesh (the Cornell
         // quads) are tested back to back: a round trip through the vote per triangle costs more than the idle lanes.
         uint32_t leaf_slot = pend_slot >> 2, leaf_left = (pend_slot & 3u) + 1u;  // the postponed leaf: 1 - 4 consecutive sorted slots
+        // (one loop per primitive kind: a shared loop makes the compiler carry the running addresses of both kinds)
+        if (F_SPHERES && (mw & WM_SPHERES)) {
 #pragma unroll 1
         do {
         const uint32_t slot = leaf_slot;
         leaf_slot++;
         leaf_left--;
-        if (F_SPHERES && (mw & WM_SPHERES)) {
           // EXTENSION (the reference kernel has no sphere primitive): semantics of oracle/rr_oracle.c ray_sphere
           if (COUNT) c_sph++;
           const float4 cr = __ldg(p.sph_geom + slot);
@@ -974,12 +978,27 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
               }
             }
           }
+        } while (leaf_left > 0);
         } else {
+#if RR_LEAF_PIPELINE  // A/B switch: the next triangle of the leaf is requested before the current one is tested
+        const float4* gq = p.tri_geom + 3 * (size_t)leaf_slot;
+        float4 q0 = __ldg(gq), q1 = __ldg(gq + 1), q2 = __ldg(gq + 2);
+#endif
+#pragma unroll 1
+        do {
+        const uint32_t slot = leaf_slot;
+        leaf_slot++;
+        leaf_left--;
           // src/Trace.cl:276-317 with the distance test hoisted before the normal (same accept set) and a
           // total order (t, prim) instead of first-found-wins
           if (COUNT) c_tri++;
+#if RR_LEAF_PIPELINE
+          const float4 g0 = q0, g1 = q1, g2 = q2;
+          if (leaf_left > 0) { gq += 3; q0 = __ldg(gq); q1 = __ldg(gq + 1); q2 = __ldg(gq + 2); }
+#else
           const float4* gp = p.tri_geom + 3 * (size_t)slot;
           const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
+#endif
           const V3 A = xyz(g0), edge1 = xyz(g1), edge2 = xyz(g2);
           const V3 h = cross(ld, edge2);
           const float a = dot(edge1, h);
@@ -1013,8 +1032,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
               }
             }
           }
-        }
         } while (leaf_left > 0);
+        }
         pend_cnt = 0;
         if (accepted) {
           PSF(W_LT, s, lt);
