@@ -127,6 +127,7 @@ struct Tuning {
 #define RR_FEAT_TLAS 4        // more than 32 meshes: the implicit top level
 #define RR_FEAT_ALL 7
 
+#define RR_TRAV_KEEP_DEFAULT 20  // default of Tuning::trav_keep (a compile-time constant in the untuned kernels)
 #define RR_TLAS_MAX_LEVELS 14  // 4^13 chunks of 32 meshes: more than the 31-bit mesh index allows
 
 // Everything a render kernel needs (passed by value).

@@ -434,7 +434,7 @@ __device__ __forceinline__ uint32_t smem_addr(const void* q) { return (uint32_t)
 // FEAT: the scene features this instantiation contains code for (RR_FEAT_*, rr_internal.h).  The kernel's cost is
 // dominated by the code a warp streams through, so a scene without spheres, without Checker /
 // Glassy / Invisible materials and with at most 32 meshes runs an instantiation that is 8 KB (15 %) smaller.
-template <bool COUNT, bool PRIMARY, bool SLACK, int FEAT>
+template <bool COUNT, bool PRIMARY, bool SLACK, int FEAT, bool TUNED>
 __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p) {
   constexpr bool F_SPHERES = (FEAT & RR_FEAT_SPHERES) != 0, F_MATERIALS = (FEAT & RR_FEAT_MATERIALS) != 0, F_TLAS = (FEAT & RR_FEAT_TLAS) != 0;
   extern __shared__ uint32_t pool_all[];
@@ -492,10 +492,13 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   unsigned ph_runs[5] = {0, 0, 0, 0, 0}, ph_lanes[5] = {0, 0, 0, 0, 0};
   unsigned long long t_empty = 0;  // COUNT: %globaltimer when this warp found the tile queue empty
 
-  const uint32_t wP = p.tune.weight[PH_PIXEL], wH = p.tune.weight[PH_SHADE], wS = p.tune.weight[PH_SETUP],
-                 wT = p.tune.weight[PH_TRAV], wL = p.tune.weight[PH_LEAF];
-  const uint32_t trav_keep = p.tune.trav_keep;
-  const bool speculate = (p.tune.speculate & 1u) != 0;
+  // Scheduler knobs: compile-time constants (the defaults of default_tuning) unless rr_set_tuning changed them
+  // (TUNED: +1.5 % C4, +3.5 % C2 for not carrying them, profiles/ab_r02_fixed_tuning.jsonl)
+  const uint32_t wP = TUNED ? p.tune.weight[PH_PIXEL] : 1u, wH = TUNED ? p.tune.weight[PH_SHADE] : 1u,
+                 wS = TUNED ? p.tune.weight[PH_SETUP] : 1u, wT = TUNED ? p.tune.weight[PH_TRAV] : 1u,
+                 wL = TUNED ? p.tune.weight[PH_LEAF] : 1u;
+  const uint32_t trav_keep = TUNED ? p.tune.trav_keep : (uint32_t)RR_TRAV_KEEP_DEFAULT;
+  const bool speculate = TUNED ? (p.tune.speculate & 1u) != 0 : true;
 
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
@@ -1252,7 +1255,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
 
 void default_tuning(Tuning& t) {
   for (int k = 0; k < 5; ++k) t.weight[k] = 4;
-  t.trav_keep = 20;
+  t.trav_keep = RR_TRAV_KEEP_DEFAULT;
   t.speculate = 1;
   t.ctas_per_sm = 0;
 }
@@ -1275,16 +1278,22 @@ static cudaError_t launch_persistent(K kernel, const RenderParams& p, int sm_cou
   return cudaGetLastError();
 }
 
-// The production kernel exists once per feature set (without the per-ray slack) and once with everything (with it); the
-// instrumented and the primary-hit kernels only with everything.
+// The production kernel exists once per feature set (default knobs, no per-ray slack) and, with everything compiled in,
+// with the per-ray slack and / or run-time scheduler knobs; the instrumented and the primary-hit kernels only with everything.
+static bool default_knobs(const Tuning& t) {
+  for (int k = 1; k < 5; ++k)
+    if (t.weight[k] != t.weight[0]) return false;
+  return t.trav_keep == RR_TRAV_KEEP_DEFAULT && (t.speculate & 1u);
+}
 template <int FEAT>
 static cudaError_t launch_lean(const RenderParams& p, int sm_count, cudaStream_t s) {
-  return launch_persistent(k_render<false, false, false, FEAT>, p, sm_count, s);
+  return launch_persistent(k_render<false, false, false, FEAT, false>, p, sm_count, s);
 }
 cudaError_t launch_render(const RenderParams& p, bool count_tests, bool slack, int feat, int sm_count, cudaStream_t s) {
   constexpr int ALL = RR_FEAT_ALL;
-  if (count_tests) return slack ? launch_persistent(k_render<true, false, true, ALL>, p, sm_count, s) : launch_persistent(k_render<true, false, false, ALL>, p, sm_count, s);
-  if (slack) return launch_persistent(k_render<false, false, true, ALL>, p, sm_count, s);
+  if (count_tests) return slack ? launch_persistent(k_render<true, false, true, ALL, true>, p, sm_count, s) : launch_persistent(k_render<true, false, false, ALL, true>, p, sm_count, s);
+  if (!default_knobs(p.tune)) return slack ? launch_persistent(k_render<false, false, true, ALL, true>, p, sm_count, s) : launch_persistent(k_render<false, false, false, ALL, true>, p, sm_count, s);
+  if (slack) return launch_persistent(k_render<false, false, true, ALL, false>, p, sm_count, s);
   switch (feat & ALL) {
     case 0: return launch_lean<0>(p, sm_count, s);
     case 1: return launch_lean<1>(p, sm_count, s);
@@ -1301,8 +1310,8 @@ cudaError_t launch_render(const RenderParams& p, bool count_tests, bool slack, i
 // at the first shade phase.
 cudaError_t launch_primary(const RenderParams& p, bool slack, int sm_count, cudaStream_t s) {
   if (!p.width || !p.height) return cudaSuccess;
-  return slack ? launch_persistent(k_render<false, true, true, RR_FEAT_ALL>, p, sm_count, s)
-               : launch_persistent(k_render<false, true, false, RR_FEAT_ALL>, p, sm_count, s);
+  return slack ? launch_persistent(k_render<false, true, true, RR_FEAT_ALL, true>, p, sm_count, s)
+               : launch_persistent(k_render<false, true, false, RR_FEAT_ALL, true>, p, sm_count, s);
 }
 
 size_t render_stack_bytes_per_warp(uint32_t stack_entries) { return (size_t)stack_entries * POOL * sizeof(uint2); }
