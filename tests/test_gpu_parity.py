@@ -408,6 +408,9 @@ def test_command_line_driver_writes_the_same_bmp(knight_obj, tmp_path):
     p = subprocess.run([str(exe)], input=answers, text=True, capture_output=True, cwd=tmp_path, timeout=120)
     assert p.returncode == 0, p.stderr
     assert "Wrote output.bmp" in p.stdout
+    # the closing progress line of the reference's tile loops (src/image.hpp:343-344): all tiles, 0 ms remaining
+    tiles = ((W + 7) // 8) * ((H + 3) // 4)
+    assert f"Rendering tile {tiles} of {tiles} (100%)" in p.stdout and "0 ms remaining" in p.stdout
     r = rr.Renderer()
     r.upload(rr.default_scene(knight_obj))
     img = r.render_plain(rr.default_camera(W, H), W, H, spp, bounces)
