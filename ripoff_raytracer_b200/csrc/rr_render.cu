@@ -330,15 +330,6 @@ constexpr int WARPS = NT / 32;
 constexpr int POOL = RR_POOL;    // path slots per warp (rr_internal.h)
 constexpr int ROUNDS = POOL / 32;
 enum { PH_PIXEL = 0, PH_SHADE = 1, PH_SETUP = 2, PH_TRAV = 3, PH_LEAF = 4 };
-#ifndef RR_LEAF_PIPELINE
-#define RR_LEAF_PIPELINE 0
-#endif
-#ifndef RR_ENTER_IN_SHADE
-#define RR_ENTER_IN_SHADE 0   // A/B switch: the shade phase enters the first candidate mesh of the next segment
-#endif
-#ifndef RR_FINISH_IN_SHADE
-#define RR_FINISH_IN_SHADE 0  // A/B switch: the shade phase finishes the last mesh of a ray (rr_render.cu done_key)
-#endif
 // Vote key of a slot: one byte per phase, so that ONE warp reduction (REDUX) over the keys counts the
 // ready slots of every phase.  A slot that needs a pixel has key 0 and W_PIX == PIX_NEED.
 constexpr uint32_t K_T = 1u, K_L = 1u << 8, K_S = 1u << 16, K_H = 1u << 24;
@@ -546,17 +537,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     if (cur == REF_END && pend_cnt == 0) return K_S;  // mesh done: the setup phase finishes it and enters the next one
     return ((cur >= REF_POP && (speculate || pend_cnt == 0)) ? K_T : 0u) | (pend_cnt ? K_L : 0u);
   };
-#if RR_FINISH_IN_SHADE
-  // The walk of the LAST candidate mesh of a ray has ended: nothing is left to enter, so the slot goes straight to the
-  // shade phase, which finishes the mesh itself (one setup round per ray less).  mesh_word = W_M of the slot.
-  auto done_key = [&](uint32_t key, uint32_t mesh_word) -> uint32_t {
-    if (key != K_S || PW(W_CAND, s) != 0u) return key;
-    const int mesh_pos = (int)(mesh_word & WM_MESH) - 1;
-    return ((mesh_pos & ~31) + 32 > p.last_mesh) ? K_H : K_S;
-  };
-#else
-  auto done_key = [&](uint32_t key, uint32_t) -> uint32_t { return key; };
-#endif
 
   auto scan_meshes = [&](int32_t base, const V3& winv, const V3& wnoi, const RaySlack<SLACK>& wek, float tmax) -> uint32_t {
     unsigned tests = 0;
@@ -721,24 +701,13 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   };
   // shade / pixel start the next segment: reset the closest hit (src/Trace.cl:437-444), collect the candidate
   // meshes (convergent here: every lane of these phases does it) and hand the slot to the setup phase
-  auto store_new_ray = [&](bool enter_now) {
+  auto store_new_ray = [&]() {
     PST3(W_OX, s, origin);
     PST3(W_DX, s, dir);
     const V3 winv = mk(rcp_approx(dir.x), rcp_approx(dir.y), rcp_approx(dir.z));
     const V3 wnoi = mk(-(origin.x * winv.x), -(origin.y * winv.y), -(origin.z * winv.z));
     RaySlack<SLACK> wek;
     make_slack(wek, origin, winv);
-#if RR_ENTER_IN_SHADE
-    if (enter_now) {  // the shade phase enters the first candidate mesh itself: no setup round between shade and the first walk
-      cand = scan_meshes(0, winv, wnoi, wek, INFINITY);
-      m = 0; lback = false; mflags = 0u;
-      best_dst = INFINITY; best_mat = 0; best_back = false; best_mesh = 0x7fffffff; best_prim = -1;
-      lprim = NO_PRIM;
-      n_rays++;
-      store_ray_state(enter_next_mesh(winv, wnoi, wek));
-      return;
-    }
-#endif
     PW(W_CAND, s) = scan_meshes(0, winv, wnoi, wek, INFINITY);
     PW(W_M, s) = 1u;  // chunk 0, no backface flag
     PSF(W_BDST, s, INFINITY);
@@ -923,9 +892,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         PW(W_PSLOT, s) = pend_slot;
         PW(W_TOPN, s) = top.x;
         PW(W_TOPD, s) = top.y;
-        uint32_t key = trav_key();
-        if (RR_FINISH_IN_SHADE && key == K_S) key = done_key(key, PW(W_M, s));
-        PW(W_KEY, s) = key;
+        PW(W_KEY, s) = trav_key();
       }
     } else if (phase == PH_LEAF) {
       // ================= leaf tests =================
@@ -983,10 +950,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
           }
         } while (leaf_left > 0);
         } else {
-#if RR_LEAF_PIPELINE  // A/B switch: the next triangle of the leaf is requested before the current one is tested
-        const float4* gq = p.tri_geom + 3 * (size_t)leaf_slot;
-        float4 q0 = __ldg(gq), q1 = __ldg(gq + 1), q2 = __ldg(gq + 2);
-#endif
 #pragma unroll 1
         do {
         const uint32_t slot = leaf_slot;
@@ -995,13 +958,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
           // src/Trace.cl:276-317 with the distance test hoisted before the normal (same accept set) and a
           // total order (t, prim) instead of first-found-wins
           if (COUNT) c_tri++;
-#if RR_LEAF_PIPELINE
-          const float4 g0 = q0, g1 = q1, g2 = q2;
-          if (leaf_left > 0) { gq += 3; q0 = __ldg(gq); q1 = __ldg(gq + 1); q2 = __ldg(gq + 2); }
-#else
           const float4* gp = p.tri_geom + 3 * (size_t)slot;
           const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
-#endif
           const V3 A = xyz(g0), edge1 = xyz(g1), edge2 = xyz(g2);
           const V3 h = cross(ld, edge2);
           const float a = dot(edge1, h);
@@ -1052,7 +1010,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         }
         PW(W_SPC, s) = (uint32_t)sp | (pend_cnt << 8);
         PW(W_PSLOT, s) = pend_slot;
-        PW(W_KEY, s) = done_key(trav_key(), mw);
+        PW(W_KEY, s) = trav_key();
       }
     } else if (phase == PH_SETUP) {
       // ================= finish the current mesh, enter the next candidate (src/Trace.cl:444-482) =================
@@ -1082,18 +1040,6 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         best_mat = (int32_t)(bm & 0x7fffffffu);
         best_back = (bm >> 31) != 0u;
         if (PRIMARY) { best_mesh = min(best_mat, p.n_meshes); best_prim = (int32_t)CW(C_BPRIM, s); }
-#if RR_FINISH_IN_SHADE
-        lprim = (int32_t)PW(W_LPRIM, s);
-        if (lprim != NO_PRIM) {  // the last mesh walked still holds its closest hit: LocalToWorldHit + keep-min here (done_key)
-          load_mesh_word();
-          best_mesh = best_dst < INFINITY ? min(best_mat, p.n_meshes) : 0x7fffffff;
-          mflags = __float_as_uint(__ldg(&p.meshes[m].wmin.w));
-          lo = PLD3(W_LOX, s);
-          ld = PLD3(W_LDX, s);
-          lt = PF(W_LT, s);
-          finish_mesh();
-        }
-#endif
         pix = (int32_t)PW(W_PIX, s);
         if (PRIMARY) {
           if (p.hit_mesh) p.hit_mesh[pix] = best_dst < INFINITY ? best_mesh : -1;
@@ -1148,7 +1094,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
           CW(C_RNG, s) = rng;
           CW(C_SAMPLE, s) = sample;
           CW(C_BOUNCE, s) = bounce | (passes << 23);  // bounce <= max_bounces <= RR_MAX_BOUNCES, passes <= 257
-          store_new_ray(true);
+          store_new_ray();
         }
       }
       n_need += __popc(__ballot_sync(full, pixel_done));
@@ -1192,7 +1138,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             CSF(C_INC, s, 0.0f); CSF(C_INC1, s, 0.0f); CSF(C_INC2, s, 0.0f);
             origin = cam_pos;
             dir = pd;
-            store_new_ray(false);
+            store_new_ray();
             need = false;
           }
         }
