@@ -350,6 +350,13 @@ def test_edge_cases(renderer):
     with pytest.raises(_abi.RRError) as e:
         renderer.render(cam, 0, H, 1, 1)
     assert e.value.status in (1, 5)
+    with pytest.raises(_abi.RRError) as e:  # the bounce counter has 23 bits (rr_api.h)
+        renderer.render(cam, W, H, 1, 0x800000)
+    assert e.value.status == 1
+    # progress of an idle context: nothing is being rendered
+    done, total = C.c_uint64(7), C.c_uint64(7)
+    _abi.check(_abi.lib().rr_render_progress(renderer.h, C.byref(done), C.byref(total)), "rr_render_progress")
+    assert done.value == 0 and total.value == 0
 
 
 def test_statistical_parity_at_config_spp(renderer, knight_obj):
