@@ -224,8 +224,6 @@ __global__ void k_prepare_meshes(const rr_mesh* __restrict__ meshes, const uint3
     if (m.scale <= RR_EPSILON || count == 0) flags |= RR_MF_SKIP;                                             // :448
     if (pow2) flags |= RR_MF_POW2;
     if (m.scale == 1.0f) flags |= RR_MF_UNIT;
-    if (R[0] == 1.0f && R[1] == 0.0f && R[2] == 0.0f && R[3] == 0.0f && R[4] == 1.0f && R[5] == 0.0f && R[6] == 0.0f && R[7] == 0.0f && R[8] == 1.0f)
-      flags |= RR_MF_IDENT;
     float lo[3], hi[3];
     for (int k = 0; k < 3; ++k) { lo[k] = sb[k] - delta; hi[k] = sb[3 + k] + delta; }
     d.bmin = make_float4(lo[0], lo[1], lo[2], __uint_as_float(seg_sfirst[s]));

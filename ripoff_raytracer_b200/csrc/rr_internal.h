@@ -83,7 +83,6 @@ struct DMesh {
 #define RR_MF_POW2 4u      // scale is a power of two: x / scale == x * (1/scale) bit for bit
 #define RR_MF_UNIT 8u      // scale == 1: the division is the identity
 #define RR_MF_SPHERES 16u  // the sphere set (extension)
-#define RR_MF_IDENT 32u    // makeRotation came out as the identity matrix (pitch = yaw = roll = 0)
 #define RR_MF_TYPE_SHIFT 8
 
 struct DMaterial {

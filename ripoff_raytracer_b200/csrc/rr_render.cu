@@ -330,15 +330,6 @@ constexpr int WARPS = NT / 32;
 constexpr int POOL = RR_POOL;    // path slots per warp (rr_internal.h)
 constexpr int ROUNDS = POOL / 32;
 enum { PH_PIXEL = 0, PH_SHADE = 1, PH_SETUP = 2, PH_TRAV = 3, PH_LEAF = 4 };
-#ifndef RR_IDENT_SHORTCUT
-#define RR_IDENT_SHORTCUT 0
-#endif
-#ifndef RR_LAZY_NORMAL
-#define RR_LAZY_NORMAL 0
-#endif
-#if RR_IDENT_SHORTCUT && !RR_LAZY_NORMAL
-#error "RR_IDENT_SHORTCUT is written on top of RR_LAZY_NORMAL"
-#endif
 // Vote key of a slot: one byte per phase, so that ONE warp reduction (REDUX) over the keys counts the
 // ready slots of every phase.  A slot that needs a pixel has key 0 and W_PIX == PIX_NEED.
 constexpr uint32_t K_T = 1u, K_L = 1u << 8, K_S = 1u << 16, K_H = 1u << 24;
@@ -576,27 +567,12 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         const float4 r0 = __ldg(&M->r0), r1 = __ldg(&M->r1), r2 = __ldg(&M->r2);
         const V3 pos = mk(__ldg(&M->ri0.w), __ldg(&M->ri1.w), __ldg(&M->ri2.w));
         const V3 lp = (lo + ld * lt) * r0.w;
-#if RR_IDENT_SHORTCUT
-        const bool ident = (mflags & RR_MF_IDENT) != 0u;
-        const V3 wp = (ident ? lp : mk(dot(xyz(r0), lp), dot(xyz(r1), lp), dot(xyz(r2), lp))) + pos;
-#else
         const V3 wp = mk(dot(xyz(r0), lp), dot(xyz(r1), lp), dot(xyz(r2), lp)) + pos;
-#endif
-#if !RR_LAZY_NORMAL
         const V3 ln = CLD3(C_LNX, s);
         const V3 wn = normalize(mk(dot(xyz(r0), ln), dot(xyz(r1), ln), dot(xyz(r2), ln)));
-#endif
         const float wd = length(wp - origin);
         if (wd < best_dst || (wd == best_dst && mesh_index < best_mesh)) {
           best_dst = wd; best_mat = mesh_index; best_back = lback; best_mesh = mesh_index; best_prim = lprim;
-#if RR_LAZY_NORMAL  // A/B switch: the world normal only of a hit that wins
-          const V3 ln = CLD3(C_LNX, s);
-#if RR_IDENT_SHORTCUT
-          const V3 wn = normalize(ident ? ln : mk(dot(xyz(r0), ln), dot(xyz(r1), ln), dot(xyz(r2), ln)));
-#else
-          const V3 wn = normalize(mk(dot(xyz(r0), ln), dot(xyz(r1), ln), dot(xyz(r2), ln)));
-#endif
-#endif
           CST3(C_BPX, s, wp);
           CST3(C_BNX, s, wn);
         }
@@ -642,15 +618,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       } else {
         // WorldToLocalRay, src/Trace.cl:118-137
         const V3 rel = origin - mk(i0.w, i1.w, i2.w);
-#if RR_IDENT_SHORTCUT  // A/B switch: R == identity: R^T v == v for finite v (up to the sign of a zero)
-        if (mflags & RR_MF_IDENT) {
-          lo = rel; ld = dir;
-        } else
-#endif
-        {
         lo = mk(dot(xyz(i0), rel), dot(xyz(i1), rel), dot(xyz(i2), rel));
         ld = mk(dot(xyz(i0), dir), dot(xyz(i1), dir), dot(xyz(i2), dir));
-        }
         if (!(mflags & RR_MF_UNIT)) {
           const float scale = __ldg(&M->r0.w);
           if (mflags & RR_MF_POW2) {  // x / 2^k == x * 2^-k exactly
