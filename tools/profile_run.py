@@ -20,6 +20,7 @@ ap.add_argument("--spp", type=int, default=4)
 ap.add_argument("--bounces", type=int, default=0)
 ap.add_argument("--frames", type=int, default=1)
 ap.add_argument("--count", action="store_true")
+ap.add_argument("--generic", action="store_true", help="force the kernel instantiation with every scene feature compiled in (tuning bit 6)")
 a = ap.parse_args()
 kw = dict(width=a.width, height=a.height, spp=a.spp)
 if a.bounces:
@@ -27,6 +28,8 @@ if a.bounces:
 wl = workloads.WORKLOADS[a.workload](**kw)
 r = rr.Renderer((0,))
 r.upload(wl.scene)
+if a.generic:
+    r.set_tuning([4, 4, 4, 4, 4, 20, 1 | 64])
 for _ in range(a.frames):
     if a.count:
         _, _, st = r.render(wl.cam, wl.width, wl.height, wl.spp, wl.bounces, count_tests=True)
