@@ -183,7 +183,7 @@ namespace rr {
 // same sin/cos as the kernel would (reference src/Trace.cl:452-454 rebuilds it per ray).
 __global__ void k_prepare_meshes(const rr_mesh* __restrict__ meshes, const uint32_t* __restrict__ mesh_seg, int n_meshes,
                                  const float* __restrict__ seg_box, const uint32_t* __restrict__ seg_sfirst,
-                                 const uint32_t* __restrict__ seg_count, const rr_sphere* __restrict__ spheres,
+                                 const uint32_t* __restrict__ seg_root, const uint32_t* __restrict__ seg_count, const rr_sphere* __restrict__ spheres,
                                  int n_spheres, const float* __restrict__ sph_seg_box, uint32_t sph_node_base,
                                  const uint32_t* __restrict__ mesh_pos, DMesh* __restrict__ out,
                                  DMaterial* __restrict__ mats) {
@@ -226,7 +226,8 @@ __global__ void k_prepare_meshes(const rr_mesh* __restrict__ meshes, const uint3
     if (m.scale == 1.0f) flags |= RR_MF_UNIT;
     float lo[3], hi[3];
     for (int k = 0; k < 3; ++k) { lo[k] = sb[k] - delta; hi[k] = sb[3 + k] + delta; }
-    d.bmin = make_float4(lo[0], lo[1], lo[2], __uint_as_float(seg_sfirst[s]));
+    // .w: the root node of the segment's hierarchy, or (count <= RR_DIRECT_MAX: no hierarchy) its first sorted slot
+    d.bmin = make_float4(lo[0], lo[1], lo[2], __uint_as_float(count > RR_DIRECT_MAX ? seg_root[s] : seg_sfirst[s]));
     d.bmax = make_float4(hi[0], hi[1], hi[2], __uint_as_float(count));
     // world-space box of the (inflated) local root box: LocalToWorldHit of its 8 corners, then a generous slack
     float wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -534,8 +535,8 @@ static int prepare_meshes(Device& d, size_t n_meshes, size_t n_spheres) {
   cudaStream_t st = d.stream;
   const int n = (int)(n_meshes + n_spheres);
   auto launch = [&]() -> cudaError_t {
-    k_prepare_meshes<<<(n + 127) / 128, 128, 0, st>>>(d.meshes_in, d.mesh_seg, (int)n_meshes, d.tb.seg_box, d.tb.seg_sfirst,
-                                                      d.tb.seg_count, d.spheres, (int)n_spheres, d.sb.seg_box, (uint32_t)d.tb.n,
+    k_prepare_meshes<<<(n + 127) / 128, 128, 0, st>>>(d.meshes_in, d.mesh_seg, (int)n_meshes, d.tb.seg_box, d.tb.seg_sfirst, d.tb.seg_root,
+                                                      d.tb.seg_count, d.spheres, (int)n_spheres, d.sb.seg_box, (uint32_t)d.tb.n_nodes,
                                                       d.mesh_pos, d.meshes, d.materials);
     return cudaGetLastError();
   };
@@ -675,7 +676,9 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
   // primitives per leaf (1 .. RR_LEAF_MAX); RR_LEAF_MAX_PRIMS in the environment overrides the default for A/B runs
   uint32_t leaf_max = RR_LEAF_DEFAULT;
   if (const char* e = getenv("RR_LEAF_MAX_PRIMS")) leaf_max = (uint32_t)std::max(1, atoi(e));
-  RR_CUDA(lbvh_build(d.tb, d.tri_box, n_tris, plan.first.data(), plan.count.data(), (uint32_t)plan.first.size(), 0, leaf_max, st));
+  uint32_t top_cluster = RR_TOP_CLUSTER_DEFAULT;  // RR_TOP_CLUSTER in the environment overrides it (0: plain Karras top) for A/B runs
+  if (const char* e = getenv("RR_TOP_CLUSTER")) top_cluster = (uint32_t)std::max(0, atoi(e));
+  RR_CUDA(lbvh_build(d.tb, d.tri_box, n_tris, plan.first.data(), plan.count.data(), (uint32_t)plan.first.size(), 0, leaf_max, top_cluster, st));
   RR_CUDA(dev_malloc(&d.tri_geom, std::max<uint64_t>(d.tb.n, 1) * 48));
   RR_CUDA(dev_malloc(&d.tri_nrm, std::max<uint64_t>(d.tb.n, 1) * 48));
   RR_CUDA(launch_pack_tris(d.tris, d.tb.order, d.tb.n, d.tri_geom, d.tri_nrm, st));
@@ -683,14 +686,14 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
   uint32_t sf = 0, sc = (uint32_t)n_spheres;
   uint32_t sphere_leaf_max = RR_LEAF_DEFAULT_SPHERES;
   if (const char* e = getenv("RR_LEAF_MAX_SPHERES")) sphere_leaf_max = (uint32_t)std::max(1, atoi(e));
-  RR_CUDA(lbvh_build(d.sb, d.sph_box, n_spheres, &sf, &sc, n_spheres ? 1u : 0u, (int32_t)d.tb.n, sphere_leaf_max, st));
+  RR_CUDA(lbvh_build(d.sb, d.sph_box, n_spheres, &sf, &sc, n_spheres ? 1u : 0u, (int32_t)d.tb.n_nodes, sphere_leaf_max, 0, st));
   RR_CUDA(dev_malloc(&d.sph_geom, std::max<size_t>(n_spheres, 1) * 16));
   RR_CUDA(launch_pack_spheres(d.spheres, d.sb.order, d.sb.n, d.sph_geom, st));
-  // one node array: triangle hierarchies at [0, tb.n), the sphere hierarchy behind them
+  // one node array: triangle hierarchies at [0, tb.n_nodes) (Karras slots, then the SAH tops), the sphere hierarchy behind them
   const size_t node_bytes = RR_NODE_QUADS * sizeof(float4);
-  RR_CUDA(dev_malloc(&d.nodes, std::max<uint64_t>(d.tb.n + d.sb.n, 1) * node_bytes));
-  if (d.tb.n) RR_CUDA(cudaMemcpyAsync(d.nodes, d.tb.nodes, d.tb.n * node_bytes, cudaMemcpyDeviceToDevice, st));
-  if (d.sb.n) RR_CUDA(cudaMemcpyAsync(d.nodes + RR_NODE_QUADS * d.tb.n, d.sb.nodes, d.sb.n * node_bytes, cudaMemcpyDeviceToDevice, st));
+  RR_CUDA(dev_malloc(&d.nodes, std::max<uint64_t>(d.tb.n_nodes + d.sb.n_nodes, 1) * node_bytes));
+  if (d.tb.n_nodes) RR_CUDA(cudaMemcpyAsync(d.nodes, d.tb.nodes, d.tb.n_nodes * node_bytes, cudaMemcpyDeviceToDevice, st));
+  if (d.sb.n_nodes) RR_CUDA(cudaMemcpyAsync(d.nodes + RR_NODE_QUADS * d.tb.n_nodes, d.sb.nodes, d.sb.n_nodes * node_bytes, cudaMemcpyDeviceToDevice, st));
 #if RR_TOP_STAGE
   {  // the root of the largest triangle hierarchy and its inner children, copied out for the kernel to stage
     size_t big = 0;
@@ -701,6 +704,9 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
     }
     if (!plan.count.empty() && plan.count[big] > RR_DIRECT_MAX) {
       RR_CUDA(cudaStreamSynchronize(st));
+      uint32_t root = 0;  // the Karras root of the segment, or the root of its SAH-ordered top
+      RR_CUDA(cudaMemcpy(&root, d.tb.seg_root + big, 4, cudaMemcpyDeviceToHost));
+      big_sfirst = root;
       std::vector<float4> top(RR_NODE_QUADS * (size_t)RR_TOP_STAGE);
       RR_CUDA(cudaMemcpy(top.data(), d.nodes + RR_NODE_QUADS * big_sfirst, 128, cudaMemcpyDeviceToHost));
       uint32_t n_top = 1;
@@ -771,6 +777,9 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
   static_assert(3 * RR_MAX_DEPTH + 4 <= RR_STACK_MAX, "stack pointer must fit the slot word");
   {  // traversal stacks sized for THIS scene: a wide node pushes at most 3 children per level
     const uint32_t need = 3u * std::max(d.tb.wide_levels, d.sb.wide_levels) + 4u;
+    if (need > RR_STACK_MAX)
+      return fail(RR_ERR_BVH_DEPTH, "hierarchy of " + std::to_string(std::max(d.tb.wide_levels, d.sb.wide_levels)) +
+                                        " wide levels exceeds the traversal stack (" + std::to_string(RR_STACK_MAX) + " entries)");
     if (need > d.stack_entries || !d.stack) {
       cudaFree(d.cold);  // one block: cold slot words of every warp, then the stacks
       d.cold = nullptr; d.stack = nullptr;

@@ -13,6 +13,9 @@
 // exactly like the CPU statement).
 #include <math.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "rr_internal.h"
 
 namespace rr {
@@ -438,12 +441,124 @@ __global__ void k_refit(uint64_t n, const uint32_t* __restrict__ order, const fl
 // the segment's box_delta() so that culling is conservative (the closest hit then does not depend on the order
 // in which a traversal visits the nodes).  ref: inner = index in the combined node array (ref_offset added),
 // leaf = -((first slot << 2 | count - 1) + 2) (so that -1 is free for "pop", rr_render.cu ref_slot / ref_count).
-__global__ void k_wide_roots(const uint32_t* __restrict__ seg_sfirst, const uint32_t* __restrict__ seg_count, int n_segs,
+__global__ void k_wide_roots(const uint32_t* __restrict__ seg_root, const uint32_t* __restrict__ seg_count, int n_segs,
                              int32_t* __restrict__ frontier, unsigned int* __restrict__ count) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_segs) return;
-  if (seg_count[s] >= 2u) frontier[atomicAdd(count, 1u)] = (int32_t)seg_sfirst[s];  // the segment's root inner node
+  if (seg_count[s] >= 2u) frontier[atomicAdd(count, 1u)] = (int32_t)seg_root[s];  // the segment's root inner node
 }
+
+// ---- SAH-ordered top over the Karras subtrees (HLBVH) -----------------------------------------------------------
+// The Morton splits of the LBVH are worst at the top of a large hierarchy (on the 1 M-triangle bench mesh a full SAH
+// build needs 13 % fewer node visits, tools/bvh_quality_experiment.cpp).  For a large segment the Karras subtrees of
+// at most `T` primitives are therefore kept as they are ("clusters": 99.7 % of the nodes at T = 512) and only the few
+// thousand nodes above them are replaced: the cluster roots are listed here, the host builds a binned-SAH binary tree
+// over their boxes (lbvh_sah_top, a few thousand items) and the new nodes are appended behind the Karras nodes.  The
+// Karras products themselves (what rr_bvh_read returns and the build-order test compares) are not touched.
+__global__ void k_find_clusters(uint64_t n, const uint32_t* __restrict__ seg_sfirst, const uint32_t* __restrict__ seg_count, int n_segs,
+                                const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                const int32_t* __restrict__ parent, const uint32_t* __restrict__ range_count,
+                                const float* __restrict__ bounds, const uint32_t* __restrict__ order,
+                                const float* __restrict__ prim_box, uint32_t T, uint32_t min_count, uint32_t capacity,
+                                int32_t* __restrict__ c_ref, uint32_t* __restrict__ c_seg, uint32_t* __restrict__ c_cnt,
+                                float* __restrict__ c_box, unsigned int* __restrict__ counter) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const int s = seg_search(seg_sfirst, n_segs, (uint32_t)g);
+  const uint32_t first = seg_sfirst[s], N = seg_count[s];
+  if (N < min_count || g - first >= N - 1) return;  // small segment, or not an inner node of it
+  const uint32_t rc = range_count[g];
+  auto emit = [&](int32_t ref, uint32_t cnt, const float* box) {
+    const unsigned int k = atomicAdd(counter, 1u);
+    if (k >= capacity) return;
+    c_ref[k] = ref; c_seg[k] = (uint32_t)s; c_cnt[k] = cnt;
+    for (int a = 0; a < 6; ++a) c_box[6 * (size_t)k + a] = box[a];
+  };
+  if (rc <= T) {
+    const int32_t par = parent[g];
+    if (par >= 0 && range_count[par] > T) emit((int32_t)g, rc, bounds + 6 * g);
+  } else {  // a node that stays above the cut: a child that is a single primitive is a cluster of its own
+    const int32_t kids[2] = {left[g], right[g]};
+    for (int k = 0; k < 2; ++k)
+      if (kids[k] < 0) emit(kids[k], 1u, prim_box + 6 * (size_t)order[~kids[k]]);
+  }
+}
+
+namespace {
+struct TopItem { int32_t ref; uint32_t cnt; float box[6]; };
+struct TopNode { int32_t left, right; uint32_t cnt; float box[6]; };
+
+inline float top_area(const float* b) {
+  const float dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
+  return dx * dy + dy * dz + dz * dx;
+}
+inline void top_grow(float* b, const float* o) {
+  for (int a = 0; a < 3; ++a) { b[a] = std::min(b[a], o[a]); b[3 + a] = std::max(b[3 + a], o[3 + a]); }
+}
+inline void top_init(float* b) {
+  for (int a = 0; a < 3; ++a) { b[a] = INFINITY; b[3 + a] = -INFINITY; }
+}
+
+// Binned SAH (16 bins per axis, cost = box area x primitives) over items[lo, hi); appends the inner nodes to `out`
+// (children first) and returns the reference of the subtree root: an item's own reference, or node_base + index in `out`.
+int32_t lbvh_sah_top(std::vector<TopItem>& items, size_t lo, size_t hi, int32_t node_base, std::vector<TopNode>& out) {
+  if (hi - lo == 1) return items[lo].ref;
+  constexpr int NB = 16;
+  float box[6], cbox[6];
+  top_init(box); top_init(cbox);
+  uint32_t total = 0;
+  for (size_t i = lo; i < hi; ++i) {
+    top_grow(box, items[i].box);
+    float c[6];
+    for (int a = 0; a < 3; ++a) c[a] = c[3 + a] = 0.5f * (items[i].box[a] + items[i].box[3 + a]);
+    top_grow(cbox, c);
+    total += items[i].cnt;
+  }
+  float best = INFINITY;
+  int best_axis = -1, best_bin = -1;
+  for (int a = 0; a < 3; ++a) {
+    const float ext = cbox[3 + a] - cbox[a];
+    if (!(ext > 0.0f)) continue;
+    float bb[NB][6];
+    uint32_t bc[NB];
+    for (int k = 0; k < NB; ++k) { top_init(bb[k]); bc[k] = 0; }
+    for (size_t i = lo; i < hi; ++i) {
+      const float c = 0.5f * (items[i].box[a] + items[i].box[3 + a]);
+      const int k = std::min(NB - 1, (int)((c - cbox[a]) / ext * NB));
+      top_grow(bb[k], items[i].box);
+      bc[k] += items[i].cnt;
+    }
+    float la[NB], ra[NB], acc[6];
+    uint32_t lc[NB], rc[NB], c = 0;
+    top_init(acc);
+    for (int k = 0; k < NB; ++k) { top_grow(acc, bb[k]); c += bc[k]; la[k] = c ? top_area(acc) : 0.0f; lc[k] = c; }
+    top_init(acc); c = 0;
+    for (int k = NB - 1; k >= 0; --k) { top_grow(acc, bb[k]); c += bc[k]; ra[k] = c ? top_area(acc) : 0.0f; rc[k] = c; }
+    for (int k = 0; k + 1 < NB; ++k) {
+      if (!lc[k] || !rc[k + 1]) continue;
+      const float cost = la[k] * (float)lc[k] + ra[k + 1] * (float)rc[k + 1];
+      if (cost < best) { best = cost; best_axis = a; best_bin = k; }
+    }
+  }
+  size_t mid = (lo + hi) / 2;
+  if (best_axis >= 0) {
+    const float ext = cbox[3 + best_axis] - cbox[best_axis];
+    auto it = std::partition(items.begin() + lo, items.begin() + hi, [&](const TopItem& t) {
+      const float c = 0.5f * (t.box[best_axis] + t.box[3 + best_axis]);
+      return std::min(NB - 1, (int)((c - cbox[best_axis]) / ext * NB)) <= best_bin;
+    });
+    const size_t m = (size_t)(it - items.begin());
+    if (m > lo && m < hi) mid = m;
+  }
+  TopNode nd;
+  nd.left = lbvh_sah_top(items, lo, mid, node_base, out);
+  nd.right = lbvh_sah_top(items, mid, hi, node_base, out);
+  nd.cnt = total;
+  for (int a = 0; a < 6; ++a) nd.box[a] = box[a];
+  out.push_back(nd);
+  return node_base + (int32_t)out.size() - 1;
+}
+}  // namespace
 
 __device__ __forceinline__ float half_area(const float* __restrict__ b) {
   const float dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
@@ -456,7 +571,8 @@ __global__ void k_pack_wide(const int32_t* __restrict__ frontier, unsigned int n
                             const int32_t* __restrict__ right, const float* __restrict__ bounds,
                             const uint32_t* __restrict__ seg_sfirst, int n_segs, const float* __restrict__ seg_box,
                             int32_t ref_offset, const uint32_t* __restrict__ range_first,
-                            const uint32_t* __restrict__ range_count, uint32_t leaf_max, float4* __restrict__ nodes) {
+                            const uint32_t* __restrict__ range_count, uint32_t leaf_max, uint64_t n_karras,
+                            const uint32_t* __restrict__ top_seg, float4* __restrict__ nodes) {
   const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_front) return;
   const int32_t g = frontier[i];
@@ -483,7 +599,7 @@ __global__ void k_pack_wide(const int32_t* __restrict__ frontier, unsigned int n
       if (k == cnt) kids[k] = right[c];
     cnt++;
   }
-  const int s = seg_search(seg_sfirst, n_segs, (uint32_t)g);
+  const int s = (uint64_t)g >= n_karras ? (int)top_seg[(uint64_t)g - n_karras] : seg_search(seg_sfirst, n_segs, (uint32_t)g);
   float sb[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) sb[k] = __ldg(seg_box + 6 * s + k);
@@ -504,7 +620,7 @@ __global__ void k_pack_wide(const int32_t* __restrict__ frontier, unsigned int n
         ref[k] = kids[k] + ref_offset;
         next[atomicAdd(next_count, 1u)] = kids[k];
       } else {  // one primitive, or a whole subtree of at most leaf_max primitives
-        const uint32_t first = kids[k] >= 0 ? range_first[kids[k]] : (uint32_t)~kids[k];
+        const uint32_t first = kids[k] >= 0 ? range_first[kids[k]] : (uint32_t)~kids[k];  // (top nodes never get here: count > leaf_max)
         const uint32_t count = kids[k] >= 0 ? range_count[kids[k]] : 1u;
         ref[k] = -(int32_t)(((first << 2) | (count - 1u)) + 2u);
       }
@@ -569,7 +685,7 @@ __global__ void k_fill_i32(int32_t* p, uint64_t n, int32_t v) {
 // ---- host driver ----------------------------------------------------------------
 void lbvh_free(Lbvh& b) {
   dev_free(b.codes); dev_free(b.order); dev_free(b.left); dev_free(b.right); dev_free(b.parent); dev_free(b.bounds);
-  dev_free(b.seg_box); dev_free(b.seg_first); dev_free(b.seg_count); dev_free(b.seg_sfirst); dev_free(b.nodes);
+  dev_free(b.seg_box); dev_free(b.seg_first); dev_free(b.seg_count); dev_free(b.seg_sfirst); dev_free(b.seg_root); dev_free(b.nodes);
   b = Lbvh();
 }
 
@@ -579,7 +695,8 @@ static cudaError_t dalloc(T** p, uint64_t count) {
 }
 
 cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, const uint32_t* h_seg_first,
-                       const uint32_t* h_seg_count, uint32_t n_segs, int32_t ref_offset, uint32_t leaf_max, cudaStream_t st) {
+                       const uint32_t* h_seg_count, uint32_t n_segs, int32_t ref_offset, uint32_t leaf_max, uint32_t top_cluster,
+                       cudaStream_t st) {
   lbvh_free(out);
   leaf_max = leaf_max < 1u ? 1u : leaf_max > RR_LEAF_MAX ? RR_LEAF_MAX : leaf_max;
   out.n_segs = n_segs;
@@ -590,6 +707,13 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
     n += h_seg_count[s];
   }
   out.n = n;
+  out.n_nodes = n;
+  // room for the SAH-ordered top (top_cluster > 0): at most one new node per cluster, clusters bounded by `top_cap`
+  uint64_t big = 0;
+  for (uint32_t s = 0; s < n_segs; ++s)
+    if (top_cluster && h_seg_count[s] >= RR_TOP_MIN_CLUSTERS * (uint64_t)top_cluster) big += h_seg_count[s];
+  const uint32_t top_cap = big ? (uint32_t)std::min<uint64_t>(big, std::max<uint64_t>(4096, 16 * big / top_cluster)) : 0u;
+  const uint64_t n_alloc = n + top_cap;  // node-indexed arrays
   cudaError_t err = cudaSuccess;
   uint64_t *keys_a = nullptr, *keys_b = nullptr;
   uint32_t *vals_a = nullptr, *vals_b = nullptr, *seg_id = nullptr, *hist = nullptr;
@@ -597,7 +721,10 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
   int32_t* leaf_parent = nullptr;
   uint32_t *range_first = nullptr, *range_count = nullptr;
   unsigned int *flags = nullptr, *d_depth = nullptr, *front_count = nullptr;
-  int32_t *front_a = nullptr, *front_b = nullptr;
+  int32_t *front_a = nullptr, *front_b = nullptr, *c_ref = nullptr;
+  uint32_t *c_seg = nullptr, *c_cnt = nullptr, *top_seg = nullptr;
+  float* c_box = nullptr;
+  unsigned int* c_counter = nullptr;
   const uint32_t n_tiles = (uint32_t)((n_total + SORT_TILE - 1) / SORT_TILE);
 #define RR_TRY(x)                   \
   do {                              \
@@ -606,15 +733,16 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
   } while (0)
   RR_TRY(dalloc(&out.codes, n_total));
   RR_TRY(dalloc(&out.order, n_total));
-  RR_TRY(dalloc(&out.left, n));
-  RR_TRY(dalloc(&out.right, n));
+  RR_TRY(dalloc(&out.left, n_alloc));
+  RR_TRY(dalloc(&out.right, n_alloc));
   RR_TRY(dalloc(&out.parent, n));
-  RR_TRY(dalloc(&out.bounds, (n ? n : 1) * 6));
+  RR_TRY(dalloc(&out.bounds, (n_alloc ? n_alloc : 1) * 6));
+  RR_TRY(dalloc(&out.seg_root, n_segs));
   RR_TRY(dalloc(&out.seg_box, (uint64_t)(n_segs ? n_segs : 1) * 6));
   RR_TRY(dalloc(&out.seg_first, n_segs));
   RR_TRY(dalloc(&out.seg_count, n_segs));
   RR_TRY(dalloc(&out.seg_sfirst, n_segs));
-  RR_TRY(dalloc(&out.nodes, (n ? n : 1) * RR_NODE_QUADS));
+  RR_TRY(dalloc(&out.nodes, (n_alloc ? n_alloc : 1) * RR_NODE_QUADS));
   RR_TRY(dalloc(&keys_a, n_total));
   RR_TRY(dalloc(&keys_b, n_total));
   RR_TRY(dalloc(&vals_a, n_total));
@@ -623,14 +751,15 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
   RR_TRY(dalloc(&hist, (uint64_t)256 * (n_tiles ? n_tiles : 1) + 256));  // per-(digit, tile) counters + 256 digit totals
   RR_TRY(dalloc(&seg_box_ord, (uint64_t)(n_segs ? n_segs : 1) * 6));
   RR_TRY(dalloc(&leaf_parent, n));
-  RR_TRY(dalloc(&range_first, n));
-  RR_TRY(dalloc(&range_count, n));
+  RR_TRY(dalloc(&range_first, n_alloc));
+  RR_TRY(dalloc(&range_count, n_alloc));
   RR_TRY(dalloc(&flags, n));
   RR_TRY(dalloc(&d_depth, 1));
   if (n_segs) {
     RR_TRY(cudaMemcpyAsync(out.seg_first, h_seg_first, n_segs * 4, cudaMemcpyHostToDevice, st));
     RR_TRY(cudaMemcpyAsync(out.seg_count, h_seg_count, n_segs * 4, cudaMemcpyHostToDevice, st));
     RR_TRY(cudaMemcpyAsync(out.seg_sfirst, h_sfirst, n_segs * 4, cudaMemcpyHostToDevice, st));
+    RR_TRY(cudaMemcpyAsync(out.seg_root, h_sfirst, n_segs * 4, cudaMemcpyHostToDevice, st));  // root = the Karras root unless a SAH top replaces it
   }
   RR_TRY(cudaMemsetAsync(flags, 0, (n ? n : 1) * 4, st));
   RR_TRY(cudaMemsetAsync(d_depth, 0, 4, st));
@@ -678,13 +807,77 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
     k_refit<<<grid_for(n, 128), 128, 0, st>>>(n, out.order, d_prim_box, out.left, out.right, out.parent, leaf_parent,
                                               out.bounds, flags, d_depth);
     RR_TRY(cudaGetLastError());
+    if (top_cap) {  // SAH-ordered top over the Karras subtrees of the large segments (k_find_clusters)
+      RR_TRY(dalloc(&c_ref, top_cap));
+      RR_TRY(dalloc(&c_seg, top_cap));
+      RR_TRY(dalloc(&c_cnt, top_cap));
+      RR_TRY(dalloc(&c_box, (uint64_t)top_cap * 6));
+      RR_TRY(dalloc(&c_counter, 1));
+      RR_TRY(cudaMemsetAsync(c_counter, 0, 4, st));
+      k_find_clusters<<<grid_for(n, 128), 128, 0, st>>>(n, out.seg_sfirst, out.seg_count, (int)n_segs, out.left, out.right, out.parent,
+                                                        range_count, out.bounds, out.order, d_prim_box, top_cluster,
+                                                        RR_TOP_MIN_CLUSTERS * top_cluster, top_cap, c_ref, c_seg, c_cnt, c_box, c_counter);
+      RR_TRY(cudaGetLastError());
+      unsigned int K = 0;
+      RR_TRY(cudaMemcpyAsync(&K, c_counter, 4, cudaMemcpyDeviceToHost, st));
+      RR_TRY(cudaStreamSynchronize(st));
+      if (K >= 2 && K <= top_cap) {  // (more clusters than room: a degenerate hierarchy, keep the Karras top)
+        std::vector<int32_t> h_ref(K);
+        std::vector<uint32_t> h_seg(K), h_cnt(K);
+        std::vector<float> h_box((size_t)K * 6);
+        RR_TRY(cudaMemcpyAsync(h_ref.data(), c_ref, K * 4, cudaMemcpyDeviceToHost, st));
+        RR_TRY(cudaMemcpyAsync(h_seg.data(), c_seg, K * 4, cudaMemcpyDeviceToHost, st));
+        RR_TRY(cudaMemcpyAsync(h_cnt.data(), c_cnt, K * 4, cudaMemcpyDeviceToHost, st));
+        RR_TRY(cudaMemcpyAsync(h_box.data(), c_box, (size_t)K * 24, cudaMemcpyDeviceToHost, st));
+        RR_TRY(cudaStreamSynchronize(st));
+        std::vector<uint32_t> idx(K);
+        for (unsigned int k = 0; k < K; ++k) idx[k] = k;
+        // the kernel lists the clusters in atomic order: sort by (segment, reference) so that the top is the same every time
+        std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return h_seg[a] != h_seg[b] ? h_seg[a] < h_seg[b] : h_ref[a] < h_ref[b]; });
+        std::vector<TopNode> top;
+        std::vector<uint32_t> top_seg_h, roots(h_sfirst, h_sfirst + n_segs);
+        for (size_t a = 0; a < K;) {
+          size_t b = a;
+          std::vector<TopItem> items;
+          while (b < K && h_seg[idx[b]] == h_seg[idx[a]]) {
+            TopItem it;
+            it.ref = h_ref[idx[b]]; it.cnt = h_cnt[idx[b]];
+            for (int q = 0; q < 6; ++q) it.box[q] = h_box[6 * (size_t)idx[b] + q];
+            items.push_back(it);
+            ++b;
+          }
+          const size_t before = top.size();
+          const int32_t root = lbvh_sah_top(items, 0, items.size(), (int32_t)n, top);
+          if (root >= (int32_t)n) roots[h_seg[idx[a]]] = (uint32_t)root;
+          top_seg_h.insert(top_seg_h.end(), top.size() - before, h_seg[idx[a]]);
+          a = b;
+        }
+        const size_t M = top.size();  // < K <= top_cap
+        std::vector<int32_t> tl(M), tr(M);
+        std::vector<uint32_t> tc(M);
+        std::vector<float> tb(M * 6);
+        for (size_t k = 0; k < M; ++k) {
+          tl[k] = top[k].left; tr[k] = top[k].right; tc[k] = top[k].cnt;
+          for (int q = 0; q < 6; ++q) tb[6 * k + q] = top[k].box[q];
+        }
+        RR_TRY(dalloc(&top_seg, M ? M : 1));
+        RR_TRY(cudaMemcpyAsync(out.left + n, tl.data(), M * 4, cudaMemcpyHostToDevice, st));
+        RR_TRY(cudaMemcpyAsync(out.right + n, tr.data(), M * 4, cudaMemcpyHostToDevice, st));
+        RR_TRY(cudaMemcpyAsync(range_count + n, tc.data(), M * 4, cudaMemcpyHostToDevice, st));
+        RR_TRY(cudaMemcpyAsync(out.bounds + 6 * n, tb.data(), M * 24, cudaMemcpyHostToDevice, st));
+        RR_TRY(cudaMemcpyAsync(top_seg, top_seg_h.data(), M * 4, cudaMemcpyHostToDevice, st));
+        RR_TRY(cudaMemcpyAsync(out.seg_root, roots.data(), n_segs * 4, cudaMemcpyHostToDevice, st));
+        RR_TRY(cudaStreamSynchronize(st));  // the host vectors go out of scope
+        out.n_nodes = n + M;
+      }
+    }
     // 4-wide collapse, one launch per level of the wide hierarchy (the frontier size comes back to the host)
-    RR_TRY(dalloc(&front_a, n));
-    RR_TRY(dalloc(&front_b, n));
+    RR_TRY(dalloc(&front_a, n_alloc));
+    RR_TRY(dalloc(&front_b, n_alloc));
     RR_TRY(dalloc(&front_count, 2));
-    RR_TRY(cudaMemsetAsync(out.nodes, 0, n * RR_NODE_QUADS * sizeof(float4), st));
+    RR_TRY(cudaMemsetAsync(out.nodes, 0, n_alloc * RR_NODE_QUADS * sizeof(float4), st));
     RR_TRY(cudaMemsetAsync(front_count, 0, 8, st));
-    k_wide_roots<<<grid_for(n_segs, 128), 128, 0, st>>>(out.seg_sfirst, out.seg_count, (int)n_segs, front_a, front_count);
+    k_wide_roots<<<grid_for(n_segs, 128), 128, 0, st>>>(out.seg_root, out.seg_count, (int)n_segs, front_a, front_count);
     unsigned int h_count = 0;
     RR_TRY(cudaMemcpyAsync(&h_count, front_count, 4, cudaMemcpyDeviceToHost, st));
     RR_TRY(cudaStreamSynchronize(st));
@@ -695,7 +888,7 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
       RR_TRY(cudaMemsetAsync(cnt_out, 0, 4, st));
       k_pack_wide<<<grid_for(h_count, 128), 128, 0, st>>>(fin, h_count, fout, cnt_out, out.order, d_prim_box, out.left, out.right,
                                                           out.bounds, out.seg_sfirst, (int)n_segs, out.seg_box, ref_offset,
-                                                          range_first, range_count, leaf_max, out.nodes);
+                                                          range_first, range_count, leaf_max, n, top_seg, out.nodes);
       RR_TRY(cudaMemcpyAsync(&h_count, cnt_out, 4, cudaMemcpyDeviceToHost, st));
       RR_TRY(cudaStreamSynchronize(st));
       int32_t* t = fin; fin = fout; fout = t;
@@ -709,6 +902,7 @@ done:
   dev_free(keys_a); dev_free(keys_b); dev_free(vals_a); dev_free(vals_b); dev_free(seg_id); dev_free(hist);
   dev_free(seg_box_ord); dev_free(leaf_parent); dev_free(range_first); dev_free(range_count); dev_free(flags); dev_free(d_depth);
   dev_free(front_a); dev_free(front_b); dev_free(front_count);
+  dev_free(c_ref); dev_free(c_seg); dev_free(c_cnt); dev_free(c_box); dev_free(c_counter); dev_free(top_seg);
   free(h_sfirst);
 #undef RR_TRY
   return err;

@@ -5,7 +5,8 @@
 //
 // Builds, over the 1 012 000 triangles of the C4 mesh: the Morton / Karras LBVH (as csrc/rr_lbvh.cu), the same with
 // subtrees of <= 2 / 4 / 8 triangles collapsed into leaves, with 1-3 passes of bottom-up tree rotations (Kensler 2008),
-// and a 16-bin top-down SAH build as the quality ceiling.  Every tree is collapsed 4-wide by surface area (as
+// a 16-bin top-down SAH build as the quality ceiling, and the hybrid that was then built on the GPU (csrc/rr_lbvh.cu
+// k_find_clusters / lbvh_sah_top): Karras subtrees of <= T primitives kept as clusters, binned SAH over the clusters above them.  Every tree is collapsed 4-wide by surface area (as
 // k_pack_wide) and walked front to back by ~186 k path-like rays (camera rays of the C4 camera, then diffuse bounces
 // inside the Cornell walls); prints wide-node visits, box tests, leaf visits and triangle tests per ray.
 #include <algorithm>
@@ -175,6 +176,57 @@ Tree build_sah(int maxLeaf) {
     return me;
   };
   t.root = rec(0, n);
+  return t;
+}
+
+
+// ---------- hybrid: LBVH subtrees of <= T prims as clusters, binned SAH (over cluster boxes) above them
+Tree build_hybrid(const Tree& lb, int T) {
+  Tree t = lb;  // copy nodes/leaves; we add new top nodes
+  vector<int> clusters;  // refs (inner node or leaf) that are cluster roots
+  function<void(int)> cut = [&](int ref) {
+    if (ref < 0 || t.nodes[ref].count <= T) { clusters.push_back(ref); return; }
+    cut(t.nodes[ref].l); cut(t.nodes[ref].r);
+  };
+  cut(t.root);
+  int K = (int)clusters.size();
+  vector<int> idx(K);
+  for (int i = 0; i < K; ++i) idx[i] = i;
+  auto cbox = [&](int c) { return refbox(t, clusters[c]); };
+  auto ccnt = [&](int c) { return refcount(t, clusters[c]); };
+  function<int(int, int)> rec = [&](int lo, int hi) -> int {
+    if (hi - lo == 1) return clusters[idx[lo]];
+    Box b; b.init(); Box cb; cb.init();
+    for (int i = lo; i < hi; ++i) { Box x = cbox(idx[i]); b.grow(x); Box c; for (int k = 0; k < 3; ++k) c.lo[k] = c.hi[k] = 0.5f * (x.lo[k] + x.hi[k]); cb.grow(c); }
+    const int NB = 16;
+    float bestCost = 1e30f; int bestAxis = -1, bestBin = -1;
+    for (int a = 0; a < 3; ++a) {
+      float ext = cb.hi[a] - cb.lo[a];
+      if (!(ext > 0)) continue;
+      Box bb[NB]; int bc[NB];
+      for (int k = 0; k < NB; ++k) { bb[k].init(); bc[k] = 0; }
+      for (int i = lo; i < hi; ++i) { Box x = cbox(idx[i]); float c = 0.5f * (x.lo[a] + x.hi[a]); int k = min(NB - 1, (int)((c - cb.lo[a]) / ext * NB)); bb[k].grow(x); bc[k] += ccnt(idx[i]); }
+      float la[NB], ra[NB]; int lc[NB], rc[NB];
+      Box acc; acc.init(); int c = 0;
+      for (int k = 0; k < NB; ++k) { acc.grow(bb[k]); c += bc[k]; la[k] = c ? acc.area() : 0; lc[k] = c; }
+      acc.init(); c = 0;
+      for (int k = NB - 1; k >= 0; --k) { acc.grow(bb[k]); c += bc[k]; ra[k] = c ? acc.area() : 0; rc[k] = c; }
+      for (int k = 0; k < NB - 1; ++k) { if (!lc[k] || !rc[k + 1]) continue; float cost = la[k] * lc[k] + ra[k + 1] * rc[k + 1]; if (cost < bestCost) { bestCost = cost; bestAxis = a; bestBin = k; } }
+    }
+    int mid;
+    if (bestAxis < 0) mid = (lo + hi) / 2;
+    else {
+      float ext = cb.hi[bestAxis] - cb.lo[bestAxis];
+      mid = (int)(partition(idx.begin() + lo, idx.begin() + hi, [&](int c) { Box x = cbox(c); float cc = 0.5f * (x.lo[bestAxis] + x.hi[bestAxis]); int k = min(NB - 1, (int)((cc - cb.lo[bestAxis]) / ext * NB)); return k <= bestBin; }) - idx.begin());
+      if (mid == lo || mid == hi) mid = (lo + hi) / 2;
+    }
+    int l = rec(lo, mid), r = rec(mid, hi);
+    Node nd; nd.l = l; nd.r = r; nd.b = b; nd.count = refcount(t, l) + refcount(t, r);
+    t.nodes.push_back(nd);
+    return (int)t.nodes.size() - 1;
+  };
+  t.root = rec(0, K);
+  printf("   hybrid T=%d: %d clusters\n", T, K);
   return t;
 }
 
@@ -427,6 +479,14 @@ int main(int argc, char** argv) {
       char lab[64]; snprintf(lab, 64, "lbvh + rot pass %d (%d applied)", pass + 1, a);
       eval(lab, r);
       if (pass == 0 || pass == 2) { Tree c = r; collapse_leaves(c, 4, 0, 1); snprintf(lab, 64, "lbvh + rot x%d + leaf<=4", pass + 1); eval(lab, c); }
+    }
+  }
+  {
+    Tree lb = build_lbvh();
+    for (int T : {64, 512, 4096, 32768}) {
+      Tree h = build_hybrid(lb, T);
+      char lab[64]; snprintf(lab, 64, "hybrid SAH-over-clusters T=%d", T); eval(lab, h);
+      Tree c = h; collapse_leaves(c, 2, 0, 1); snprintf(lab, 64, "hybrid T=%d + leaf<=2", T); eval(lab, c);
     }
   }
   { Tree t = build_sah(1); eval("binned sah leaf=1", t); }
