@@ -783,3 +783,82 @@ def test_two_processes_share_queue_and_frame_over_ipc(knight_obj, tmp_path):
     for rank, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {rank}:\n{out}"
     assert "frame_equal=True" in outs[0] and "tiles_ok=True" in outs[0] and "misuse_reported=True" in outs[0], outs[0]
+
+
+# ------------------------------------------------- seeded random scenes: every kernel instantiation --
+def _random_scene(seed):
+    """Random meshes (shared and own triangle ranges), poses, scales, all five material types, optional spheres, 1 - 45
+    meshes: walks through the kernel's instantiations (scene features spheres / special materials / top level, with and
+    without the per-ray slack) and through hierarchies with and without an SAH-ordered top."""
+    rng = np.random.default_rng(seed)
+    s = rr.Scene()
+    bases = []
+    for k in range(int(rng.integers(1, 4))):
+        if rng.random() < 0.5:
+            v, n, f = scenes.displaced_icosphere(int(rng.integers(1, 4)), radius=float(rng.uniform(8, 60)), center=(0.0, 0.0, 0.0), seed=seed * 7 + k)
+        else:
+            v, n, f = scenes.uv_sphere(int(rng.integers(6, 20)), int(rng.integers(4, 10)), radius=float(rng.uniform(8, 60)), center=(0.0, 0.0, 0.0))
+        bases.append(s.add_triangles(scenes.mesh_triangles(v, n, f)))
+    if seed % 3 == 0:  # one large mesh: its hierarchy gets the SAH-ordered top (>= 16 384 triangles)
+        v, n, f = scenes.heightfield(96, size=500.0, height=40.0, base=0.0, seed=seed)
+        bases.append(s.add_triangles(scenes.mesh_triangles(v, n, f)))
+    side = 300.0
+    s.add_quad((-side, 0, -side), (side, 0, -side), (side, 0, side), (-side, 0, side), (0, 1, 0), (0.7, 0.7, 0.7))
+    s.add_quad((-side, side, -side), (side, side, -side), (side, side, side), (-side, side, side), (0, -1, 0), (1, 1, 1))
+    lm = s.mesh(s.n_meshes - 1)["material"]
+    lm["emissionColor"][0, :3] = 1.0
+    lm["emissionStrength"] = 4.0
+    types = [_abi.MATERIAL_SOLID] * 3 + ([_abi.MATERIAL_CHECKER, _abi.MATERIAL_GLASSY, _abi.MATERIAL_INVISIBLE, _abi.MATERIAL_ONESIDED] if seed % 2 else [_abi.MATERIAL_ONESIDED])
+    for k in range(int(rng.integers(1, 44 if seed % 4 == 1 else 12))):
+        m = np.zeros(1, _abi.MESH)
+        m["pos"][0, :3] = rng.uniform((-200, 10, -200), (200, 250, 200))
+        m["pitch"], m["yaw"], m["roll"] = rng.uniform(-3, 3, 3) * (rng.random(3) < 0.7)
+        m["scale"] = float(rng.choice([0.25, 0.5, 0.8, 1.0, 1.0, 1.3, 2.0]))
+        mm = m["material"]
+        mm["type"] = int(rng.choice(types))
+        mm["ior"] = float(rng.uniform(1.1, 1.7))
+        mm["color"][0, :3] = rng.uniform(0.2, 0.95, 3)
+        mm["emissionColor"][0, :3] = rng.uniform(0.0, 1.0, 3)
+        mm["emissionStrength"] = float(rng.choice([0.0, 0.0, 2.0, 25.0]))
+        mm["specularProbability"] = float(rng.uniform(0, 1))
+        mm["reflectiveness"] = float(rng.uniform(0, 1))
+        base = bases[int(rng.integers(0, len(bases)))]
+        if base is bases[-1] and seed % 3 == 0:
+            m["pos"][0, :3] = (0.0, 0.0, 0.0)
+            m["pitch"] = m["roll"] = 0.0
+            m["scale"] = 1.0
+        s.add_mesh(m, base)
+    if seed % 2 == 0:
+        sp = scenes.random_spheres(int(rng.integers(1, 30)), seed=seed, box=(350.0, 200.0, 350.0), radius=(4.0, 25.0))
+        sp["center"][:, 1] += 20.0
+        sp["material"]["type"] = rng.choice(types, size=len(sp))
+        sp["material"]["ior"] = 1.4
+        s.add_spheres(sp)
+    W, H = 112, 80
+    cam = np.zeros(1, _abi.CAMERA)
+    cam["position"][0, :3] = rng.uniform((-150, 40, -150), (150, 220, 150)) * (20.0 if seed % 5 == 4 else 1.0)  # sometimes far outside
+    look = -np.asarray(cam["position"][0, :3], np.float64) + (0.0, 100.0, 0.0)
+    cam["yaw"] = np.arctan2(look[0], look[2])
+    cam["pitch"] = -np.arcsin(look[1] / np.linalg.norm(look))
+    cam["roll"] = float(rng.uniform(-0.3, 0.3))
+    cam["fov"] = float(rng.uniform(40, 100))
+    cam["aspectRatio"] = np.float32(W) / np.float32(H)
+    return s, cam, W, H
+
+
+@pytest.mark.parametrize("seed", list(range(1, 13)))
+def test_random_scenes_are_bit_exact(seed):
+    s, cam, W, H = _random_scene(seed)
+    t, m, r, sp = s.arrays()
+    ren = rr.Renderer()
+    ren.upload(s)
+    o = Oracle(t, m, r, sp)
+    mesh, prim, dst = ren.primary_hits(cam, W, H)
+    om, op, od = o.primary(cam, W, H, threads=16)
+    assert np.array_equal(mesh, om) and np.array_equal(prim, op) and np.array_equal(bits(dst), bits(od)), f"seed {seed}: primary hits"
+    got, grad, st = ren.render(cam, W, H, 2, 10, radiance=True)
+    want, wrad, ost = o.render(cam, W, H, 2, 10, radiance=True, threads=16)
+    ren.close()
+    assert st["rays"] == ost["rays"], f"seed {seed}"
+    assert np.array_equal(bits(grad), bits(wrad)), f"seed {seed}: radiance"
+    assert_images_equal(got, want, f"seed {seed}")
