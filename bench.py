@@ -456,6 +456,9 @@ def main():
         "tile_queue": mode,
         "clocks": clk, "gpu_launches": args.steps * world, "roofline": roofline, "roofline_l2": roofline_l2,
         "roofline_bytes": roofline_bytes,
+        # the instrumented probe frame walks the same hierarchy: traversal-stack overflows must be (and are) 0; a non-zero
+        # count in any frame makes the library fail the render with RR_ERR_BVH_DEPTH
+        "stack_overflows": int(pst["stack_overflows"]),
     }
     if frame_equal is not None:
         line["frame_equal"] = frame_equal["equal"]
