@@ -173,6 +173,7 @@ struct rr_ctx {
   bool has_scene = false;
   bool peer_ok = false;  // devices 1.. can address device 0's memory
   rr::Tuning tune;
+  uint32_t pool_use = 0;  // rr_set_tuning value 8: path slots per warp that take pixels (0 = RR_POOL)
   std::atomic<uint64_t> progress_total{0};  // tiles of the frame being rendered (0: none)
   std::atomic<const unsigned long long*> progress_queue{nullptr};  // the counter its warps pop
 };
@@ -897,6 +898,7 @@ static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam
   p.stack_entries = d.stack_entries;
   p.cold = d.cold;
   p.stack_warps = d.stack_warps;
+  p.pool_use = ctx->pool_use ? std::min<uint32_t>(ctx->pool_use, RR_POOL) : RR_POOL;
   p.queue = d.queue;
   p.frame = d.frame;
   p.radiance = nullptr;
@@ -1225,7 +1227,8 @@ int rr_render(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height
 
 int rr_set_tuning(rr_ctx* ctx, const uint32_t* values, size_t n) {
   if (!ctx) return fail(RR_ERR_INVALID_ARGUMENT, "null context");
-  if (!values) { default_tuning(ctx->tune); return RR_OK; }
+  if (!values) { default_tuning(ctx->tune); ctx->pool_use = 0; return RR_OK; }
+  if (n > 8) ctx->pool_use = values[8];  // slots per warp in use (0 = all); not a scheduler knob: every instantiation honours it
   uint32_t* dst[8] = {&ctx->tune.weight[0], &ctx->tune.weight[1], &ctx->tune.weight[2], &ctx->tune.weight[3],
                       &ctx->tune.weight[4], &ctx->tune.trav_keep, &ctx->tune.speculate, &ctx->tune.ctas_per_sm};
   for (size_t k = 0; k < n && k < 8; ++k) *dst[k] = values[k];

@@ -168,6 +168,7 @@ struct RenderParams {
   uint32_t stack_entries;            // 3 per level of the deepest 4-wide hierarchy + slack
   uint32_t* cold;                    // cold slot words, RR_COLD_WORDS * RR_POOL per warp (scratch)
   uint32_t stack_warps;              // warps the scratch was sized for
+  uint32_t pool_use;                 // path slots per warp that take pixels (<= RR_POOL; the others stay idle for this frame)
   unsigned long long* queue;         // tile counter (may live in a peer GPU's memory): frame epoch << 48 | next tile
   uint32_t queue_epoch;              // epoch this launch expects in the counter (0 for a context-local queue)
   uint8_t* frame;                    // RGBA8 (may live in a peer GPU's memory)

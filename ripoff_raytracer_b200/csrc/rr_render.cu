@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   // warp-uniform state
   bool more_pixels = true;  // the tile queue or the warp's current tile still holds pixels
   if (lane < 8) tstate[lane] = lane == 2 ? 1u : 0u;
-  uint32_t n_need = POOL;  // slots waiting for a pixel
+  uint32_t n_need = p.pool_use;  // slots waiting for a pixel
   // statistics
   uint32_t n_rays = 0, n_tiles = 0;  // per lane / per warp: far below 2^32 even for an 8K, 1024-spp frame on one GPU
   unsigned c_box = 0, c_tri = 0, c_sph = 0;
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
     PW(W_KEY, lane + 32 * r) = 0u;
-    PW(W_PIX, lane + 32 * r) = (uint32_t)PIX_NEED;
+    PW(W_PIX, lane + 32 * r) = lane + 32 * r < p.pool_use ? (uint32_t)PIX_NEED : (uint32_t)PIX_IDLE;
   }
   __syncwarp();
 
