@@ -32,6 +32,20 @@ def golden_zoo():
 
 
 @pytest.fixture(scope="session")
+def golden_converged():
+    """The reference's default scene at 32 x 32, 2^18 spp, 50 bounces: radiance of its -ffast-math and of its strict
+    build (tests/golden/make_converged.py)."""
+    return dict(np.load(GOLDEN / "converged_ref.npz"))
+
+
+def psnr_radiance(a, b):
+    """PSNR of two float radiance images on the displayable range: clamped to [0, 1] (src/Trace.cl:646), peak 1."""
+    d = np.clip(a.astype(np.float64), 0, 1) - np.clip(b.astype(np.float64), 0, 1)
+    mse = float(np.mean(d * d))
+    return float("inf") if mse == 0 else 10.0 * np.log10(1.0 / mse)
+
+
+@pytest.fixture(scope="session")
 def golden_rng():
     return dict(np.load(GOLDEN / "rng.npz"))
 
