@@ -582,84 +582,96 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
   };
   // Enters the next candidate mesh (src/Trace.cl:444-463): world box against the closest hit so far,
   // WorldToLocalRay, root box.  Returns the slot's new key (traversal started, or K_H: no candidate left).
-  // One step of the search: false = look at the next candidate, true = done (`key` set).
-  auto enter_step = [&](const V3& winv, const V3& wnoi, const RaySlack<SLACK>& wek, uint32_t& key) -> bool {
-    {
-      if (cand == 0) {
-        int32_t base = (m & ~31) + 32;
-        if (base > p.last_mesh) { key = K_H; return true; }
-        if (F_TLAS && p.tlas) {  // skip the chunks (and groups of chunks) the ray does not enter before the closest hit so far
-          unsigned tests = 0;
-          base = next_chunk_fn<SLACK>(p.tlas, p.tlas_levels, base >> 5, p.last_mesh >> 5, winv, wnoi, wek, best_dst, COUNT ? &tests : nullptr) << 5;
-          if (COUNT) c_box += tests;
-          if (base > p.last_mesh) { key = K_H; return true; }
-        }
-        m = base;
-        cand = scan_meshes(base, winv, wnoi, wek, best_dst);
-        return false;
-      }
-      const int k = __ffs((int)cand) - 1;
-      cand &= cand - 1u;
-      m = (m & ~31) + k;
-      const DMesh* M = p.meshes + m;
-      // the whole mesh record is requested at once (one L1 round trip instead of three dependent ones)
-      const float4 wlo = __ldg(&M->wmin), whi = __ldg(&M->wmax);
-      const float4 i0 = __ldg(&M->ri0), i1 = __ldg(&M->ri1), i2 = __ldg(&M->ri2);
-      const float4 blo = __ldg(&M->bmin), bhi = __ldg(&M->bmax);
-      float tn;
-      if (best_dst < INFINITY) {  // a hit exists: the box may now lie behind it
-        if (COUNT) c_box++;
-        if (!box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, wek, best_dst, tn)) return false;
-      }
-      mflags = __float_as_uint(wlo.w);
-      RaySlack<SLACK> lek = wek;
-      if (F_SPHERES && (mflags & RR_MF_SPHERES)) {
-        lo = origin; ld = dir; linv = winv; lnoi = wnoi;
-      } else {
-        // WorldToLocalRay, src/Trace.cl:118-137
-        const V3 rel = origin - mk(i0.w, i1.w, i2.w);
-        lo = mk(dot(xyz(i0), rel), dot(xyz(i1), rel), dot(xyz(i2), rel));
-        ld = mk(dot(xyz(i0), dir), dot(xyz(i1), dir), dot(xyz(i2), dir));
-        if (!(mflags & RR_MF_UNIT)) {
-          const float scale = __ldg(&M->r0.w);
-          if (mflags & RR_MF_POW2) {  // x / 2^k == x * 2^-k exactly
-            const float is = __ldg(&M->r1.w);
-            lo = lo * is; ld = ld * is;
-          } else if (fabsf(scale) > RR_EPSILON) {
-            lo = lo / scale; ld = ld / scale;
+  // Two stages per trip.  (1) The cheap, divergent part: lanes look for their next candidate whose world box still lies in
+  // front of the closest hit so far (two loads and a box test per candidate; lanes differ in trips).  (2) The expensive
+  // part -- the mesh record, WorldToLocalRay with its normalisation, the root box -- runs ONCE for all lanes that found
+  // a candidate (structured control flow: every lane leaves stage 1 through the same exit, so they reconverge before
+  // stage 2), instead of once per trip of the search with whichever lanes got that far.
+  auto enter_next_mesh = [&](const V3& winv, const V3& wnoi, const RaySlack<SLACK>& wek) -> uint32_t {
+    uint32_t key = K_H;
+    bool searching = true;
+    do {
+      bool found = false;
+      while (searching && !found) {
+        if (cand == 0) {
+          int32_t base = (m & ~31) + 32;
+          if (F_TLAS && p.tlas && base <= p.last_mesh) {  // skip the chunks (and groups of chunks) the ray does not enter before the closest hit so far
+            unsigned tests = 0;
+            base = next_chunk_fn<SLACK>(p.tlas, p.tlas_levels, base >> 5, p.last_mesh >> 5, winv, wnoi, wek, best_dst, COUNT ? &tests : nullptr) << 5;
+            if (COUNT) c_box += tests;
+          }
+          if (base > p.last_mesh) {
+            searching = false;  // no candidate left: K_H
+          } else {
+            m = base;
+            cand = scan_meshes(base, winv, wnoi, wek, best_dst);
+          }
+        } else {
+          const int k = __ffs((int)cand) - 1;
+          cand &= cand - 1u;
+          m = (m & ~31) + k;
+          found = true;
+          if (best_dst < INFINITY) {  // a hit exists: the box may now lie behind it
+            const DMesh* M = p.meshes + m;
+            const float4 wlo = __ldg(&M->wmin), whi = __ldg(&M->wmax);
+            float tn;
+            if (COUNT) c_box++;
+            found = box_cull(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, winv, wnoi, wek, best_dst, tn);
           }
         }
-        ld = normalize(ld);
-        linv = mk(rcp_approx(ld.x), rcp_approx(ld.y), rcp_approx(ld.z));
-        lnoi = mk(-(lo.x * linv.x), -(lo.y * linv.y), -(lo.z * linv.z));
-        make_slack(lek, lo, linv);
       }
-      if (COUNT) c_box++;
-      if (!box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, linv, lnoi, lek, INFINITY, tn)) return false;
-      const uint32_t first = __float_as_uint(blo.w), count = __float_as_uint(bhi.w);
-      // The sphere set lives in world space and is the last entry in the tie order (highest mesh index): a sphere at or
-      // beyond the closest hit so far can never win, so its walk starts with that distance as the bound.
-      lt = (F_SPHERES && (mflags & RR_MF_SPHERES)) ? best_dst : INFINITY;
-      lprim = NO_PRIM; lback = false;
-      sp = 0;
-      if (count <= RR_DIRECT_MAX) {  // no hierarchy: the primitives are tested one by one in the leaf phase
-        pend_slot = (((F_SPHERES && (mflags & RR_MF_SPHERES)) ? 0u : first) << 2) | (count - 1u);  // leaf word: all 1 - 4 primitives at once
-        pend_cnt = 1;
-        cur = REF_END;
-      } else {
-        pend_cnt = 0;
-        cur = (int32_t)first;  // root node
+      if (found) {
+        const DMesh* M = p.meshes + m;
+        const float4 i0 = __ldg(&M->ri0), i1 = __ldg(&M->ri1), i2 = __ldg(&M->ri2);
+        const float4 blo = __ldg(&M->bmin), bhi = __ldg(&M->bmax);
+        mflags = __float_as_uint(__ldg(&M->wmin.w));
+        RaySlack<SLACK> lek = wek;
+        if (F_SPHERES && (mflags & RR_MF_SPHERES)) {
+          lo = origin; ld = dir; linv = winv; lnoi = wnoi;
+        } else {
+          // WorldToLocalRay, src/Trace.cl:118-137
+          const V3 rel = origin - mk(i0.w, i1.w, i2.w);
+          lo = mk(dot(xyz(i0), rel), dot(xyz(i1), rel), dot(xyz(i2), rel));
+          ld = mk(dot(xyz(i0), dir), dot(xyz(i1), dir), dot(xyz(i2), dir));
+          if (!(mflags & RR_MF_UNIT)) {
+            const float scale = __ldg(&M->r0.w);
+            if (mflags & RR_MF_POW2) {  // x / 2^k == x * 2^-k exactly
+              const float is = __ldg(&M->r1.w);
+              lo = lo * is; ld = ld * is;
+            } else if (fabsf(scale) > RR_EPSILON) {
+              lo = lo / scale; ld = ld / scale;
+            }
+          }
+          ld = normalize(ld);
+          linv = mk(rcp_approx(ld.x), rcp_approx(ld.y), rcp_approx(ld.z));
+          lnoi = mk(-(lo.x * linv.x), -(lo.y * linv.y), -(lo.z * linv.z));
+          make_slack(lek, lo, linv);
+        }
+        float tn;
+        if (COUNT) c_box++;
+        if (box_cull(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, linv, lnoi, lek, INFINITY, tn)) {
+          const uint32_t first = __float_as_uint(blo.w), count = __float_as_uint(bhi.w);
+          // The sphere set lives in world space and is the last entry in the tie order (highest mesh index): a sphere at or
+          // beyond the closest hit so far can never win, so its walk starts with that distance as the bound.
+          lt = (F_SPHERES && (mflags & RR_MF_SPHERES)) ? best_dst : INFINITY;
+          lprim = NO_PRIM; lback = false;
+          sp = 0;
+          if (count <= RR_DIRECT_MAX) {  // no hierarchy: the primitives are tested one by one in the leaf phase
+            pend_slot = (((F_SPHERES && (mflags & RR_MF_SPHERES)) ? 0u : first) << 2) | (count - 1u);  // leaf word: all 1 - 4 primitives at once
+            pend_cnt = 1;
+            cur = REF_END;
+          } else {
+            pend_cnt = 0;
+            cur = (int32_t)first;  // root node
 #if RR_TOP_STAGE
-        if (p.top_count && cur == p.top_root) cur = RR_TOP_TAG;  // the staged copy of this root
+            if (p.top_count && cur == p.top_root) cur = RR_TOP_TAG;  // the staged copy of this root
 #endif
+          }
+          key = trav_key();
+          searching = false;
+        }
       }
-      key = trav_key();
-      return true;
-    }
-  };
-  auto enter_next_mesh = [&](const V3& winv, const V3& wnoi, const RaySlack<SLACK>& wek) -> uint32_t {
-    uint32_t key = 0;
-    while (!enter_step(winv, wnoi, wek, key)) {}
+    } while (searching);
     return key;
   };
   // what setup and shade write back after finish_mesh / enter_next_mesh
