@@ -176,6 +176,7 @@ struct rr_ctx {
   uint32_t pool_use = 0;  // rr_set_tuning value 8: path slots per warp that take pixels (0 = RR_POOL)
   std::atomic<uint64_t> progress_total{0};  // tiles of the frame being rendered (0: none)
   std::atomic<const unsigned long long*> progress_queue{nullptr};  // the counter its warps pop
+  std::atomic<uint32_t> progress_items_per_tile{1};  // the counter counts pixels (RR_PIXEL_QUEUE): this many per tile
 };
 
 namespace rr {
@@ -894,6 +895,8 @@ static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam
   p.tiles_y = (H + p.tile_h - 1) / p.tile_h;
   p.tile_begin = 0;
   p.tile_stride = 1;
+  p.tile_pixels = p.tile_w * p.tile_h;
+  p.queue_items = p.tiles_x * p.tiles_y * p.tile_pixels;  // checked against 2^32 by render_frame
   p.stack = d.stack;
   p.stack_entries = d.stack_entries;
   p.cold = d.cold;
@@ -904,6 +907,9 @@ static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam
   p.radiance = nullptr;
   p.counters = d.counters;
 }
+
+// the queue counter hands out 32-bit work items (pixels in tile-major order, ragged border tiles padded)
+static bool too_many_items(const RenderParams& p) { return (uint64_t)p.tiles_x * p.tiles_y * p.tile_pixels > 0xffffffffull; }
 
 static int check_render_args(const rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t H, uint32_t spp, uint32_t bounces = 0) {
   if (!ctx || !cam) return fail(RR_ERR_INVALID_ARGUMENT, "null context or camera");
@@ -961,7 +967,9 @@ static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t 
   {
     RenderParams q;
     fill_params(ctx, d0, cam, W, H, spp, bounces, frame_index, tile_size, q);
+    if (too_many_items(q)) return fail(RR_ERR_INVALID_ARGUMENT, "image too large (its tiles hold more than 2^32 - 1 work items)");
     ctx->progress_queue.store(mode == 1 ? d0.shared_queue : d0.queue);
+    ctx->progress_items_per_tile.store(RR_PIXEL_QUEUE ? q.tile_pixels : 1u);
     ctx->progress_total.store((uint64_t)q.tiles_x * q.tiles_y);
   }
   for (size_t k = 0; k < nd; ++k) {
@@ -977,7 +985,11 @@ static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t 
     } else {
       p.queue = d0.queue;  // peers pop device 0's counter
       p.frame = d0.frame;
-      if (mode == 2) { p.tile_begin = rank; p.tile_stride = world; }
+      if (mode == 2) {  // this rank's tiles: rank, rank + world, ...
+        p.tile_begin = rank; p.tile_stride = world;
+        const uint64_t tiles = (uint64_t)p.tiles_x * p.tiles_y;
+        p.queue_items = (uint32_t)((tiles > rank ? (tiles - rank + world - 1) / world : 0) * p.tile_pixels);
+      }
     }
     if (want_radiance) p.radiance = d.radiance;
     RR_CUDA(cudaEventRecord(d.ev0, d.stream));
@@ -1253,7 +1265,8 @@ int rr_render_progress(rr_ctx* ctx, uint64_t* tiles_popped, uint64_t* tiles_tota
   RR_CUDA(cudaSetDevice(d.ordinal));
   RR_CUDA(cudaMemcpyAsync(d.poll_host, src, sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.poll_stream));
   RR_CUDA(cudaStreamSynchronize(d.poll_stream));
-  const uint64_t popped = *d.poll_host & ((1ull << RR_QUEUE_EPOCH_SHIFT) - 1ull);  // every warp's last, failing pop counts too
+  // (every warp's last, failing pop counts too, hence the clamp)
+  const uint64_t popped = (*d.poll_host & ((1ull << RR_QUEUE_EPOCH_SHIFT) - 1ull)) / std::max<uint32_t>(ctx->progress_items_per_tile.load(), 1u);
   *tiles_popped = popped < total ? popped : total;
   return RR_OK;
 }
@@ -1371,13 +1384,14 @@ int rr_primary_hits(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t 
   Device& d = ctx->dev[0];
   RR_CUDA(cudaSetDevice(d.ordinal));
   const size_t n = (size_t)width * height;
+  RenderParams p;
+  fill_params(ctx, d, cam, width, height, 1, 1, 0, 0, p);
+  if (too_many_items(p)) return fail(RR_ERR_INVALID_ARGUMENT, "image too large (its tiles hold more than 2^32 - 1 work items)");
   int32_t *dm = nullptr, *dp = nullptr;
   float* dd = nullptr;
   cudaError_t e = cudaMalloc(&dm, n * 4);
   if (e == cudaSuccess) e = cudaMalloc(&dp, n * 4);
   if (e == cudaSuccess) e = cudaMalloc(&dd, n * 4);
-  RenderParams p;
-  fill_params(ctx, d, cam, width, height, 1, 1, 0, 0, p);
   p.hit_mesh = dm; p.hit_prim = dp; p.hit_dst = dd;
   if (e == cudaSuccess) e = cudaMemsetAsync(d.queue, 0, sizeof(unsigned long long), d.stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(d.counters, 0, sizeof(Counters), d.stream);

@@ -12,7 +12,7 @@
 #define RR_STACK_MAX 200               // traversal stack entries at most: a 4-wide node pushes up to 3 per level
 #define RR_MAX_INVISIBLE_PASSES 256u   // pass-throughs of Invisible surfaces per path before it is ended
 #define RR_MAX_BOUNCES 0x7fffffu       // the bounce counter shares a 32-bit slot word with the 9-bit pass counter
-#define RR_QUEUE_EPOCH_SHIFT 48        // tile counter word: frame epoch (16 bits) << 48 | tiles popped
+#define RR_QUEUE_EPOCH_SHIFT 48        // queue counter word: frame epoch (16 bits) << 48 | work items (pixels in tile-major order) handed out
 #define RR_DIRECT_MAX 4               // segments this small are tested without a hierarchy
 #define RR_LEAF_MAX 4                 // primitives per leaf of a hierarchy at most (the leaf reference keeps count - 1 in 2 bits)
 #ifndef RR_LEAF_DEFAULT
@@ -41,6 +41,9 @@
 #ifndef RR_TOP_STAGE
 #define RR_TOP_STAGE 0    // > 0: this many nodes of the top of the largest hierarchy are staged in shared memory (A/B switch)
 #endif
+#ifndef RR_PIXEL_QUEUE
+#define RR_PIXEL_QUEUE 1  // 1: the counter hands out PIXELS (tile-major order), a warp takes exactly as many as it has free slots;
+#endif                    // 0: a warp pops whole tiles and consumes them as slots free up (round 1; A/B switch)
 #define RR_TOP_TAG 0x40000000  // node references at or above this value address the staged copy
 #define RR_POOL_WORDS 28  // 32-bit words of one slot in shared memory
 #define RR_COLD_WORDS 25  // ... and in the per-warp global scratch
@@ -164,6 +167,7 @@ struct RenderParams {
   int32_t frame_index;
   uint32_t tile_w, tile_h, tiles_x, tiles_y;
   uint32_t tile_begin, tile_stride;  // static partition: this rank renders tile_begin + k*tile_stride ...
+  uint32_t tile_pixels, queue_items; // RR_PIXEL_QUEUE: tile_w * tile_h, and the work items of this launch (its tiles x tile_pixels, < 2^32)
   uint2* stack;                      // traversal stacks, stack_entries * RR_POOL entries per warp (scratch)
   uint32_t stack_entries;            // 3 per level of the deepest 4-wide hierarchy + slack
   uint32_t* cold;                    // cold slot words, RR_COLD_WORDS * RR_POOL per warp (scratch)

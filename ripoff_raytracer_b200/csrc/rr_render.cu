@@ -1114,9 +1114,62 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       // ================= hand a pixel to every slot that needs one =================
       if (COUNT) { ph_runs[PH_PIXEL]++; ph_lanes[PH_PIXEL] += n_sel; }
       bool need = s >= 0;
+      bool queue_empty = false;
+#if RR_PIXEL_QUEUE
+      // The counter hands out PIXELS, numbered tile by tile (item i = pixel i % tile_pixels of the launch's tile
+      // i / tile_pixels), and the warp takes exactly as many as it has free slots: ONE atomic per run of this phase, as
+      // with whole tiles (a run hands out ~27 pixels), but no warp sits on the unstarted rest of a tile when the queue
+      // runs dry -- those pixels would start up to a third of a pixel lifetime late and stretch the drain of the frame
+      // (DESIGN.md section 6).  Items of a ragged border tile that fall outside the image are skipped.
+      for (;;) {
+        const unsigned mb = __ballot_sync(full, need);
+        if (mb == 0u) break;
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd_system(p.queue, (unsigned long long)__popc(mb));
+        t = __shfl_sync(full, t, 0);
+        if ((uint32_t)(t >> RR_QUEUE_EPOCH_SHIFT) != p.queue_epoch) {  // see pop_tile
+          if (lane == 0) atomicAdd(&p.counters->queue_errors, 1ull);
+          queue_empty = true;
+          break;
+        }
+        t &= (1ull << RR_QUEUE_EPOCH_SHIFT) - 1ull;
+        if (t >= (unsigned long long)p.queue_items) { queue_empty = true; break; }
+        const unsigned long long it = t + __popc(mb & lanes_below);
+        bool first_of_tile = false;
+        if (need && it < (unsigned long long)p.queue_items) {
+          const uint32_t item = (uint32_t)it, seq = item / p.tile_pixels, k = item - seq * p.tile_pixels;
+          const uint32_t tile = p.tile_begin + seq * p.tile_stride;
+          const uint32_t x = (tile % p.tiles_x) * p.tile_w + k % p.tile_w, y = (tile / p.tiles_x) * p.tile_h + k / p.tile_w;
+          first_of_tile = k == 0u;
+          if (x < p.width && y < p.height) {
+            pix = (int32_t)(y * p.width + x);
+            if (!PRIMARY && p.max_bounces == 0) {  // no segment is ever traced: the pixel is black
+              reinterpret_cast<uint32_t*>(p.frame)[pix] = tonemap_rgba(mk(0, 0, 0));
+              if (p.radiance) { p.radiance[3 * (size_t)pix] = 0.0f; p.radiance[3 * (size_t)pix + 1] = 0.0f; p.radiance[3 * (size_t)pix + 2] = 0.0f; }
+            } else {
+              PW(W_PIX, s) = (uint32_t)pix;
+              CW(C_RNG, s) = make_seed((uint32_t)pix, p.frame_index, 0u);  // src/Trace.cl:631-632
+              const V3 pd = primary_dir(p.cam, x, y, p.width, p.height);   // once per pixel, :634-636
+              CST3(C_PD, s, pd);
+              CSF(C_ACC, s, 0.0f); CSF(C_ACC1, s, 0.0f); CSF(C_ACC2, s, 0.0f);
+              CW(C_SAMPLE, s) = 0u;
+              CW(C_BOUNCE, s) = 0u;
+              CSF(C_THR, s, 1.0f); CSF(C_THR1, s, 1.0f); CSF(C_THR2, s, 1.0f);
+              CSF(C_INC, s, 0.0f); CSF(C_INC1, s, 0.0f); CSF(C_INC2, s, 0.0f);
+              origin = cam_pos;
+              dir = pd;
+              store_new_ray();
+              need = false;
+            }
+          }
+        }
+        n_tiles += __popc(__ballot_sync(full, first_of_tile));  // a tile is counted by the warp that takes its first pixel
+      }
+      more_pixels = !queue_empty;
+      if (COUNT && queue_empty && t_empty == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_empty));
+#else
       // the tile state lives in shared memory between two runs of this (rare) phase, not in six registers
       uint32_t tile_x0 = tstate[0], tile_y0 = tstate[1], tile_w = tstate[2], tile_next = tstate[3], tile_pixels = tstate[4];
-      bool queue_empty = false;
       while (__any_sync(full, need)) {
         if (tile_next >= tile_pixels) {
           if (queue_empty) break;
@@ -1160,6 +1213,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
       if (COUNT && queue_empty && t_empty == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_empty));
       __syncwarp();
       if (lane == 0) { tstate[0] = tile_x0; tstate[1] = tile_y0; tstate[2] = tile_w; tstate[3] = tile_next; tstate[4] = tile_pixels; }
+#endif
       const bool got = s >= 0 && !need;
       n_need -= __popc(__ballot_sync(full, got));
       if (need) PW(W_PIX, s) = (uint32_t)PIX_IDLE;  // the queue is empty
