@@ -44,6 +44,12 @@
 #ifndef RR_PIXEL_QUEUE
 #define RR_PIXEL_QUEUE 1  // 1: the counter hands out PIXELS (tile-major order), a warp takes exactly as many as it has free slots;
 #endif                    // 0: a warp pops whole tiles and consumes them as slots free up (round 1; A/B switch)
+#ifndef RR_ADAPTIVE_KEEP
+#define RR_ADAPTIVE_KEEP 1  // node-step runs that start with few lanes keep stepping until a quarter of them has finished (A/B switch)
+#endif
+#ifndef RR_KEEP_NUM
+#define RR_KEEP_NUM 3       // ... threshold = RR_KEEP_NUM / 4 of the lanes the run started with
+#endif
 #define RR_TOP_TAG 0x40000000  // node references at or above this value address the staged copy
 #define RR_POOL_WORDS 28  // 32-bit words of one slot in shared memory
 #define RR_COLD_WORDS 25  // ... and in the per-warp global scratch

@@ -820,6 +820,15 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
           break;
         }
       };
+      // The loop is left when fewer than `keep` lanes can still step (the others idle meanwhile).  With a full pool that is
+      // trav_keep of the ~25 lanes a run starts with; a run that starts with fewer (a warp whose pool is draining: the
+      // tail of a frame) would leave after every single node and pay a vote + gather per step, so its
+      // threshold is three quarters of the lanes it started with.
+#if RR_ADAPTIVE_KEEP
+      const uint32_t keep = min(trav_keep, max(((uint32_t)n_sel * (uint32_t)RR_KEEP_NUM) >> 2, 1u));
+#else
+      const uint32_t keep = trav_keep;
+#endif
       uint32_t active;
       do {
         const bool step = mine && cur >= REF_POP && (speculate || pend_cnt == 0);
@@ -897,7 +906,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
           resolve(next);  // the one copy of the pop / postpone logic
         }
         active = __popc(__ballot_sync(full, mine && cur >= REF_POP && (speculate || pend_cnt == 0)));
-      } while (active >= trav_keep);
+      } while (active >= keep);
       if (mine) {
         PW(W_CUR, s) = (uint32_t)cur;
         PW(W_SPC, s) = (uint32_t)sp | (pend_cnt << 8);
