@@ -202,14 +202,14 @@ typedef struct rr_stats {
   uint64_t box_tests;    /* ray/AABB tests                                  */
   uint64_t tri_tests;    /* ray/triangle tests                              */
   uint64_t sphere_tests; /* ray/sphere tests                                */
-  uint64_t tiles;        /* tiles this context rendered                     */
+  uint64_t tiles;        /* tiles whose first pixel this context took from the queue (sums to the tiles of the frame over all ranks) */
   float render_ms;       /* device time of the render kernel(s), CUDA events */
   float build_ms;        /* device time of the last LBVH build              */
   /* warp-scheduler statistics of the instrumented kernel (count_tests != 0): how often each phase
    * (0 pixel, 1 shade, 2 mesh setup, 3 node step, 4 leaf test) ran in a warp, and the lanes active in it */
   uint64_t phase_runs[5];
   uint64_t phase_lanes[5];
-  /* drain of the persistent slot pool (instrumented kernel): time between a warp's first failed tile pop (no new
+  /* drain of the persistent slot pool (instrumented kernel): time between a warp's first failed queue pop (no new
    * pixels) and its exit -- mean and maximum over the warps, milliseconds.  A pixel's samples are serial
    * (src/Trace.cl:632, 639-642), so this tail does not shrink with more GPUs: DESIGN.md section 6. */
   float tail_avg_ms;
@@ -222,9 +222,11 @@ typedef struct rr_stats {
  * rgba_out: width*height*4 bytes, row 0 = top, RGBA, alpha = 255
  * (src/image.hpp:267-271).  Blocking.  frameIndex is kernel arg 7, which the
  * reference always evaluates to 0 (src/image.hpp:228).  tile_size == 0 picks
- * the library default (8 x 4 pixels, the unit one warp pops from the tile
- * queue); larger values are honoured up to 32 x 32.  The image does not depend
- * on it.
+ * the library default (8 x 4 pixels); larger values are honoured up to 32 x 32.
+ * The queue hands out the pixels of the frame tile by tile (row-major tiles,
+ * row-major pixels inside a tile) and a warp takes as many as it has free path
+ * slots at a time, so a tile only sets the ORDER of the pixels (and the unit of
+ * rr_render_strided and of the progress line).  The image does not depend on it.
  * Supported geometry range: the closest hit is the brute-force minimum over all primitives (the hierarchy only
  * culls) as long as ray origins -- the camera and every hit point, taken into each mesh's local space, i.e.
  * (origin - pos) / scale -- stay within 10^4 times the mesh's extent; the library switches to a kernel with a
@@ -307,11 +309,14 @@ int rr_bvh_read(rr_ctx* ctx, int which, uint64_t* codes, uint32_t* order, int32_
 
 /* ------------------------------------------------------------------------
  * Multi-GPU tile queue (replaces the mutex-guarded std::queue of
- * src/image.hpp:280-350).  One process per GPU: rank 0 owns a 64-bit tile
- * counter and the frame buffer in its HBM and exports CUDA IPC handles; the
- * other ranks import them and their persistent CTAs pop tiles with
- * system-scope atomics and store finished pixels straight into rank 0's frame
- * over NVLink.  handle buffers are RR_IPC_HANDLE_BYTES each.
+ * src/image.hpp:280-350).  One process per GPU: rank 0 owns a 64-bit queue
+ * counter (frame epoch << 48 | pixels handed out, in tile-major order) and the
+ * frame buffer in its HBM and exports CUDA IPC handles; the other ranks import
+ * them and their persistent warps take pixels with system-scope atomics (one
+ * atomicAdd per warp and refill: exactly as many pixels as it has free path
+ * slots, so no rank sits on unstarted pixels when the queue runs dry) and store
+ * finished pixels straight into rank 0's frame over NVLink.  handle buffers are
+ * RR_IPC_HANDLE_BYTES each.
  * ---------------------------------------------------------------------- */
 #define RR_IPC_HANDLE_BYTES 64
 /* Rank 0: allocates the shared frame (width*height*4 bytes, an allocation of its own that no later render of this

@@ -992,6 +992,37 @@ static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t 
       }
     }
     if (want_radiance) p.radiance = d.radiance;
+#ifdef RR_L2_PIN_EXPERIMENT
+    {  // A/B only: one array of the scene in a persisting-L2 access window (RR_L2_PIN = nodes | geom | nrm | cold)
+      const char* what = getenv("RR_L2_PIN");
+      if (what) {
+        const char* mb = getenv("RR_L2_PIN_MB");
+        const char* ratio = getenv("RR_L2_PIN_RATIO");
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, d.ordinal);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, d.ordinal);
+        size_t carve = mb ? (size_t)atoi(mb) << 20 : (size_t)max_persist;
+        carve = std::min(carve, (size_t)max_persist);
+        RR_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+        void* base = nullptr; size_t bytes = 0;
+        if (!strcmp(what, "nodes")) { base = d.nodes; bytes = (d.tb.n_nodes + d.sb.n_nodes) * 128; }
+        else if (!strcmp(what, "geom")) { base = d.tri_geom; bytes = d.tb.n * 48; }
+        else if (!strcmp(what, "nrm")) { base = d.tri_nrm; bytes = d.tb.n * 48; }
+        else if (!strcmp(what, "cold")) { base = d.cold; bytes = (size_t)d.stack_warps * render_cold_bytes_per_warp(); }
+        bytes = std::min(bytes, (size_t)max_window);
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        av.accessPolicyWindow.base_ptr = base;
+        av.accessPolicyWindow.num_bytes = bytes;
+        av.accessPolicyWindow.hitRatio = ratio ? (float)atof(ratio) : 1.0f;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        RR_CUDA(cudaStreamSetAttribute(d.stream, cudaStreamAttributeAccessPolicyWindow, &av));
+        static bool said = false;
+        if (!said) { fprintf(stderr, "L2 pin: %s, %zu MB window, carve-out %zu MB (max %d MB, max window %d MB), ratio %.2f\n", what, bytes >> 20, carve >> 20, max_persist >> 20, max_window >> 20, av.accessPolicyWindow.hitRatio); said = true; }
+      }
+    }
+#endif
     RR_CUDA(cudaEventRecord(d.ev0, d.stream));
     RR_CUDA(launch_render(p, count_tests, frame_needs_slack(ctx, d, cam), scene_features(ctx, d), d.sm_count, d.stream));
     RR_CUDA(cudaEventRecord(d.ev1, d.stream));

@@ -47,6 +47,12 @@
 #ifndef RR_ADAPTIVE_KEEP
 #define RR_ADAPTIVE_KEEP 1  // node-step runs that start with few lanes keep stepping until a quarter of them has finished (A/B switch)
 #endif
+#ifndef RR_STREAM_NRM
+#define RR_STREAM_NRM 0   // 1: vertex normals are loaded with the evict-first policy (LDG.E.EF): fetched once per accepted hit, rarely reused
+#endif
+#ifndef RR_STREAM_GEOM
+#define RR_STREAM_GEOM 0  // 1: ... and the triangle positions too (A/B switch)
+#endif
 #ifndef RR_KEEP_NUM
 #define RR_KEEP_NUM 3       // ... threshold = RR_KEEP_NUM / 4 of the lanes the run started with
 #endif

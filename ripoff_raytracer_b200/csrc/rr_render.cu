@@ -12,9 +12,10 @@
 // the hierarchy is walked in.
 //
 // Structure -- a warp-synchronous state machine:
-//   * persistent warps pop 8x4-pixel tiles from one 64-bit atomic counter (the
-//     reference's mutex-guarded std::queue, src/image.hpp:286-314); a lane that
-//     finishes its pixel takes the next pixel of the warp's tile;
+//   * persistent warps take pixels from one 64-bit atomic counter (the reference's
+//     mutex-guarded std::queue of tiles, src/image.hpp:286-314): the counter numbers
+//     the pixels tile by tile (8x4 tiles) and a warp adds exactly as many as it has
+//     free path slots, one atomic per refill;
 //   * per pixel the spp samples run serially in the lane because the RNG state
 //     is carried across samples (src/Trace.cl:632,639-642);
 //   * every lane is in one of five phases (pixel, shade, mesh setup, node step,
@@ -980,7 +981,11 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
           // total order (t, prim) instead of first-found-wins
           if (COUNT) c_tri++;
           const float4* gp = p.tri_geom + 3 * (size_t)slot;
+#if RR_STREAM_GEOM
+          const float4 g0 = __ldcs(gp), g1 = __ldcs(gp + 1), g2 = __ldcs(gp + 2);
+#else
           const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
+#endif
           const V3 A = xyz(g0), edge1 = xyz(g1), edge2 = xyz(g2);
           const V3 h = cross(ld, edge2);
           const float a = dot(edge1, h);
@@ -996,7 +1001,11 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
                 const int32_t prim = (int32_t)__float_as_uint(g0.w);
                 if (t > RR_EPSILON && (t < lt || (t == lt && lprim != NO_PRIM && prim < lprim))) {
                   const float4* np = p.tri_nrm + 3 * (size_t)slot;
+#if RR_STREAM_NRM
+                  const float4 n0 = __ldcs(np), n1 = __ldcs(np + 1), n2 = __ldcs(np + 2);
+#else
                   const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+#endif
                   n3 = normalize(xyz(n0) * (1.0f - u - v) + xyz(n1) * u + xyz(n2) * v);
                   bool back = false;
                   bool ok = true;

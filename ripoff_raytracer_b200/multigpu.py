@@ -2,9 +2,10 @@
 
 Replaces the reference's `multiThreadedCompute` (src/image.hpp:280-350: one std::thread per device popping
 `(tileX, tileY)` from a mutex-guarded std::queue, merging tiles into a shared `pixels` under a second mutex).
-Here rank 0 owns ONE 64-bit tile counter and the frame in its HBM; the other ranks attach to both with CUDA IPC
-handles and their persistent warps pop tiles with system-scope atomics and store pixels straight into rank 0's
-frame over NVLink (csrc/rr_render.cu pop_tile, csrc/rr_api.cu rr_queue_*).  What is left for the host is: ship
+Here rank 0 owns ONE 64-bit queue counter and the frame in its HBM; the other ranks attach to both with CUDA IPC
+handles and their persistent warps take pixels (numbered tile by tile; a warp adds as many as it has free path
+slots) with system-scope atomics and store them straight into rank 0's frame over NVLink (csrc/rr_render.cu pixel
+phase, csrc/rr_api.cu rr_queue_*).  What is left for the host is: ship
 128 bytes of handles, agree on the mode, and -- only when peer access is unavailable -- a static partition plus
 one reduce.  `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) carries those few bytes; no collective
 touches the data path in "shared" mode.

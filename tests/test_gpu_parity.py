@@ -14,7 +14,7 @@ import pytest
 
 import ripoff_raytracer_b200 as rr
 from oracle.pyoracle import Oracle
-from ripoff_raytracer_b200 import _abi, scenes
+from ripoff_raytracer_b200 import _abi, multigpu, scenes
 
 pytestmark = pytest.mark.gpu
 
@@ -584,6 +584,41 @@ def test_progressive_average_matches_reference_golden(renderer, golden_small, go
     assert st["samples"] == W * H * spp * frames
     with pytest.raises(_abi.RRError):  # size differs from the reset
         renderer.accum_add_frame(g["cam"], W + 1, H, spp, bounces, frame_index=1)
+
+
+def test_pixel_queue_ragged_tiles_and_static_partition(renderer, golden_small):
+    """The queue hands out pixels in tile-major order (rr_render.cu, pixel phase): items of a ragged border tile that
+    fall outside the image are skipped, every tile is counted once, and the static partition (rank r renders the tiles
+    r, r + world, ...) paints exactly its own tiles -- the union over the ranks is the whole frame."""
+    g = golden_small
+    renderer.upload_arrays(g["tris"], g["meshes"], g["ranges"])
+    o = Oracle(g["tris"], g["meshes"], g["ranges"])
+    for W, H in [(37, 23), (8, 4), (9, 5), (1, 130)]:
+        cam = g["cam"].copy()
+        cam["aspectRatio"] = np.float32(W) / np.float32(H)
+        want = o.render(cam, W, H, 2, 6)[0]
+        for tile, (tw, th) in [(0, (8, 4)), (5, (5, 5)), (32, (32, 32)), (512, (32, 32))]:
+            got, _, st = renderer.render(cam, W, H, 2, 6, tile=tile)
+            assert np.array_equal(got, want), (W, H, tile)
+            assert st["tiles"] == -(-W // tw) * -(-H // th), (W, H, tile)
+        world = 3
+        union = np.zeros((H, W, 4), np.uint8)
+        tiles = rays = 0
+        for rank in range(world):
+            st = renderer.render_strided(cam, W, H, 2, 6, rank, world)
+            part = renderer.read_frame(W, H)
+            tx, ty = multigpu.tile_grid(W, H)
+            mine = np.zeros((H, W), bool)
+            for t in multigpu.strided_tiles(rank, world, tx * ty):
+                x0, y0, w, h = multigpu.tile_rect(int(t), W, H)
+                union[y0:y0 + h, x0:x0 + w] = part[y0:y0 + h, x0:x0 + w]
+                mine[y0:y0 + h, x0:x0 + w] = True
+            painted = part[..., 3] != 0  # the strided render clears the frame first; a rendered pixel has alpha 255
+            assert np.array_equal(painted, mine), (W, H, rank)
+            tiles += st["tiles"]
+            rays += st["rays"]
+        assert np.array_equal(union, want), (W, H)
+        assert tiles == -(-W // 8) * -(-H // 4)
 
 
 def test_progressive_ragged_sizes_vs_oracle(renderer, golden_small):
