@@ -72,3 +72,9 @@ if a.grid == "default":
             t = list(base); t[i] = w
             run(t, f"{name}={w}")
     run(base, "base again")
+elif a.grid == "pixel":  # weight of the pixel phase: how many free slots a warp collects before it refills
+    for w in (5, 6, 8, 12, 16, 3):
+        t = list(base); t[5] = 20; t[0] = w
+        run(t, f"wP={w} keep=20")
+    t = list(base); t[5] = 20
+    run(t, "base keep=20")
