@@ -861,6 +861,16 @@ static int scene_features(const rr_ctx* ctx, const Device& d) {
   return f;
 }
 
+// Tiles of a launch and the multiplier of the scattered tile order (RR_TILE_ORDER 2): about 0.618 n, made coprime to n
+static void set_queue_tiles(RenderParams& p, uint32_t n) {
+  p.queue_tiles = std::max<uint32_t>(n, 1u);
+  uint32_t m = (uint32_t)((double)p.queue_tiles * 0.6180339887498949) | 1u;
+  auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; };
+  while (gcd(m, p.queue_tiles) != 1u) m += 2u;
+  p.tile_mul = m % p.queue_tiles;
+  if (p.queue_tiles == 1u) p.tile_mul = 0u;
+}
+
 static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam, uint32_t W, uint32_t H, uint32_t spp,
                         uint32_t bounces, int32_t frame_index, uint32_t tile_size, RenderParams& p) {
   memset(&p, 0, sizeof(p));
@@ -897,6 +907,7 @@ static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam
   p.tile_stride = 1;
   p.tile_pixels = p.tile_w * p.tile_h;
   p.queue_items = p.tiles_x * p.tiles_y * p.tile_pixels;  // checked against 2^32 by render_frame
+  set_queue_tiles(p, p.tiles_x * p.tiles_y);
   p.stack = d.stack;
   p.stack_entries = d.stack_entries;
   p.cold = d.cold;
@@ -989,6 +1000,7 @@ static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t 
         p.tile_begin = rank; p.tile_stride = world;
         const uint64_t tiles = (uint64_t)p.tiles_x * p.tiles_y;
         p.queue_items = (uint32_t)((tiles > rank ? (tiles - rank + world - 1) / world : 0) * p.tile_pixels);
+        set_queue_tiles(p, p.queue_items / p.tile_pixels);
       }
     }
     if (want_radiance) p.radiance = d.radiance;

@@ -47,6 +47,9 @@
 #ifndef RR_ADAPTIVE_KEEP
 #define RR_ADAPTIVE_KEEP 1  // node-step runs that start with few lanes keep stepping until a quarter of them has finished (A/B switch)
 #endif
+#ifndef RR_TILE_ORDER
+#define RR_TILE_ORDER 0   // order in which the queue hands out the tiles of a launch: 0 row-major, 1 reversed, 2 scattered (A/B switch)
+#endif
 #ifndef RR_STREAM_NRM
 #define RR_STREAM_NRM 0   // 1: vertex normals are loaded with the evict-first policy (LDG.E.EF): fetched once per accepted hit, rarely reused
 #endif
@@ -180,6 +183,7 @@ struct RenderParams {
   uint32_t tile_w, tile_h, tiles_x, tiles_y;
   uint32_t tile_begin, tile_stride;  // static partition: this rank renders tile_begin + k*tile_stride ...
   uint32_t tile_pixels, queue_items; // RR_PIXEL_QUEUE: tile_w * tile_h, and the work items of this launch (its tiles x tile_pixels, < 2^32)
+  uint32_t queue_tiles, tile_mul;    // tiles of this launch; RR_TILE_ORDER 2: multiplier of the tile permutation (coprime to queue_tiles)
   uint2* stack;                      // traversal stacks, stack_entries * RR_POOL entries per warp (scratch)
   uint32_t stack_entries;            // 3 per level of the deepest 4-wide hierarchy + slack
   uint32_t* cold;                    // cold slot words, RR_COLD_WORDS * RR_POOL per warp (scratch)

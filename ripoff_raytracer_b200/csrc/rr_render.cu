@@ -1155,7 +1155,14 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
         const unsigned long long it = t + __popc(mb & lanes_below);
         bool first_of_tile = false;
         if (need && it < (unsigned long long)p.queue_items) {
-          const uint32_t item = (uint32_t)it, seq = item / p.tile_pixels, k = item - seq * p.tile_pixels;
+          const uint32_t item = (uint32_t)it, seq0 = item / p.tile_pixels, k = item - seq0 * p.tile_pixels;
+#if RR_TILE_ORDER == 1    // last tile first
+          const uint32_t seq = p.queue_tiles - 1u - seq0;
+#elif RR_TILE_ORDER == 2  // scattered: a multiplicative permutation of the launch's tiles (tile_mul is coprime to their number)
+          const uint32_t seq = (uint32_t)(((unsigned long long)seq0 * p.tile_mul) % p.queue_tiles);
+#else
+          const uint32_t seq = seq0;
+#endif
           const uint32_t tile = p.tile_begin + seq * p.tile_stride;
           const uint32_t x = (tile % p.tiles_x) * p.tile_w + k % p.tile_w, y = (tile / p.tiles_x) * p.tile_h + k / p.tile_w;
           first_of_tile = k == 0u;
