@@ -7,6 +7,7 @@
 // RR_ERR_CUDA when there is none.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -645,9 +646,20 @@ static int prepare_meshes(Device& d, size_t n_meshes, size_t n_spheres) {
   return RR_OK;
 }
 
+static void upload_mark(cudaStream_t st, const char* what) {  // RR_BUILD_TIMING=1: see rr_lbvh.cu build_mark
+  static const bool on = getenv("RR_BUILD_TIMING") != nullptr;
+  static std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+  if (!on) return;
+  cudaStreamSynchronize(st);
+  const auto now = std::chrono::steady_clock::now();
+  fprintf(stderr, "[upload] %-40s %8.1f us\n", what, std::chrono::duration<double, std::micro>(now - last).count());
+  last = now;
+}
+
 static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput* indexed, size_t n_tris, const rr_mesh* meshes,
                          size_t n_meshes, const SegPlan& plan, const rr_sphere* spheres, size_t n_spheres) {
   RR_CUDA(cudaSetDevice(d.ordinal));
+  upload_mark(d.stream, "(since the last upload)");
   free_scene(d);
   cudaStream_t st = d.stream;
   RR_CUDA(dev_malloc(&d.tris, std::max<size_t>(n_tris, 1) * sizeof(rr_triangle)));
@@ -673,6 +685,7 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
     RR_CUDA(cudaGetLastError());
   }
   if (n_spheres) RR_CUDA(cudaMemcpyAsync(d.spheres, spheres, n_spheres * sizeof(rr_sphere), cudaMemcpyHostToDevice, st));
+  upload_mark(st, "(free, alloc) + H2D of the scene");
   RR_CUDA(cudaEventRecord(d.ev0, st));
   RR_CUDA(launch_tri_boxes(d.tris, n_tris, d.tri_box, st));
   // primitives per leaf (1 .. RR_LEAF_MAX); RR_LEAF_MAX_PRIMS in the environment overrides the default for A/B runs
@@ -681,6 +694,7 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
   uint32_t top_cluster = RR_TOP_CLUSTER_DEFAULT;  // RR_TOP_CLUSTER in the environment overrides it (0: plain Karras top) for A/B runs
   if (const char* e = getenv("RR_TOP_CLUSTER")) top_cluster = (uint32_t)std::max(0, atoi(e));
   RR_CUDA(lbvh_build(d.tb, d.tri_box, n_tris, plan.first.data(), plan.count.data(), (uint32_t)plan.first.size(), 0, leaf_max, top_cluster, st));
+  upload_mark(st, "triangle LBVH");
   RR_CUDA(dev_malloc(&d.tri_geom, std::max<uint64_t>(d.tb.n, 1) * 48));
   RR_CUDA(dev_malloc(&d.tri_nrm, std::max<uint64_t>(d.tb.n, 1) * 48));
   RR_CUDA(launch_pack_tris(d.tris, d.tb.order, d.tb.n, d.tri_geom, d.tri_nrm, st));
@@ -691,6 +705,7 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
   RR_CUDA(lbvh_build(d.sb, d.sph_box, n_spheres, &sf, &sc, n_spheres ? 1u : 0u, (int32_t)d.tb.n_nodes, sphere_leaf_max, 0, st));
   RR_CUDA(dev_malloc(&d.sph_geom, std::max<size_t>(n_spheres, 1) * 16));
   RR_CUDA(launch_pack_spheres(d.spheres, d.sb.order, d.sb.n, d.sph_geom, st));
+  upload_mark(st, "pack triangles, sphere LBVH");
   // one node array: triangle hierarchies at [0, tb.n_nodes) (Karras slots, then the SAH tops), the sphere hierarchy behind them
   const size_t node_bytes = RR_NODE_QUADS * sizeof(float4);
   RR_CUDA(dev_malloc(&d.nodes, std::max<uint64_t>(d.tb.n_nodes + d.sb.n_nodes, 1) * node_bytes));
@@ -774,6 +789,7 @@ static int upload_device(Device& d, const rr_triangle* tris, const IndexedInput*
     }
   }
   RR_CUDA(cudaEventElapsedTime(&d.build_ms, d.ev0, d.ev1));
+  upload_mark(st, "node array, meshes, top level");
   dev_free(d.tb.nodes); d.tb.nodes = nullptr;  // copied into d.nodes
   dev_free(d.sb.nodes); d.sb.nodes = nullptr;
   static_assert(3 * RR_MAX_DEPTH + 4 <= RR_STACK_MAX, "stack pointer must fit the slot word");

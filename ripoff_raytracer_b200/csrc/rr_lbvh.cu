@@ -13,6 +13,9 @@
 // exactly like the CPU statement).
 #include <math.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <vector>
 
@@ -694,9 +697,21 @@ static cudaError_t dalloc(T** p, uint64_t count) {
   return dev_malloc(p, (count ? count : 1) * sizeof(T));  // cached: a re-upload of a scene of the same size allocates nothing
 }
 
+// RR_BUILD_TIMING=1 in the environment: host wall clock of the build phases on stderr (each mark synchronises the stream)
+static void build_mark(cudaStream_t st, const char* what) {
+  static const bool on = getenv("RR_BUILD_TIMING") != nullptr;
+  static std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+  if (!on) return;
+  cudaStreamSynchronize(st);
+  const auto now = std::chrono::steady_clock::now();
+  fprintf(stderr, "[build] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(now - last).count());
+  last = now;
+}
+
 cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, const uint32_t* h_seg_first,
                        const uint32_t* h_seg_count, uint32_t n_segs, int32_t ref_offset, uint32_t leaf_max, uint32_t top_cluster,
                        cudaStream_t st) {
+  build_mark(st, "(before the build)");
   lbvh_free(out);
   leaf_max = leaf_max < 1u ? 1u : leaf_max > RR_LEAF_MAX ? RR_LEAF_MAX : leaf_max;
   out.n_segs = n_segs;
@@ -755,6 +770,7 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
   RR_TRY(dalloc(&range_count, n_alloc));
   RR_TRY(dalloc(&flags, n));
   RR_TRY(dalloc(&d_depth, 1));
+  build_mark(st, "allocations");
   if (n_segs) {
     RR_TRY(cudaMemcpyAsync(out.seg_first, h_seg_first, n_segs * 4, cudaMemcpyHostToDevice, st));
     RR_TRY(cudaMemcpyAsync(out.seg_count, h_seg_count, n_segs * 4, cudaMemcpyHostToDevice, st));
@@ -796,6 +812,7 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
       }
     }
     RR_TRY(cudaGetLastError());
+    build_mark(st, "boxes, morton, radix sort");
     RR_TRY(cudaMemcpyAsync(out.codes, kin, n_total * 8, cudaMemcpyDeviceToDevice, st));
     RR_TRY(cudaMemcpyAsync(out.order, vin, n_total * 4, cudaMemcpyDeviceToDevice, st));
   }
@@ -807,6 +824,7 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
     k_refit<<<grid_for(n, 128), 128, 0, st>>>(n, out.order, d_prim_box, out.left, out.right, out.parent, leaf_parent,
                                               out.bounds, flags, d_depth);
     RR_TRY(cudaGetLastError());
+    build_mark(st, "karras + refit");
     if (top_cap) {  // SAH-ordered top over the Karras subtrees of the large segments (k_find_clusters)
       RR_TRY(dalloc(&c_ref, top_cap));
       RR_TRY(dalloc(&c_seg, top_cap));
@@ -871,6 +889,7 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
         out.n_nodes = n + M;
       }
     }
+    build_mark(st, "SAH top (host)");
     // 4-wide collapse, one launch per level of the wide hierarchy (the frontier size comes back to the host)
     RR_TRY(dalloc(&front_a, n_alloc));
     RR_TRY(dalloc(&front_b, n_alloc));
@@ -895,6 +914,7 @@ cudaError_t lbvh_build(Lbvh& out, const float* d_prim_box, uint64_t n_total, con
       level++;
     }
     out.wide_levels = (uint32_t)level;
+    build_mark(st, "wide collapse (per level)");
   }
   RR_TRY(cudaMemcpyAsync(&out.max_depth, d_depth, 4, cudaMemcpyDeviceToHost, st));
   RR_TRY(cudaStreamSynchronize(st));
