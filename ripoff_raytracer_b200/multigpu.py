@@ -37,6 +37,23 @@ def tile_rect(tile: int, width: int, height: int, tile_w: int = 8, tile_h: int =
     return x0, y0, min(tile_w, width - x0), min(tile_h, height - y0)
 
 
+def queue_items(width: int, height: int, tile_w: int = 8, tile_h: int = 4, rank: int = 0, world: int = 1) -> int:
+    """Work items the queue counter of one launch runs through (csrc/rr_api.cu fill_params / render_frame): the pixels of
+    its tiles, ragged border tiles padded to tile_w x tile_h (the padding items are skipped by the kernel)."""
+    tx, ty = tile_grid(width, height, tile_w, tile_h)
+    return len(strided_tiles(rank, world, tx * ty)) * tile_w * tile_h
+
+
+def item_pixel(item: int, width: int, height: int, tile_w: int = 8, tile_h: int = 4, rank: int = 0, world: int = 1):
+    """Item -> (x, y) of the pixel the kernel renders for it, or None for a padding item (csrc/rr_render.cu, pixel phase):
+    items are numbered tile by tile (the launch's tiles in ascending order), row-major inside a tile."""
+    tx, _ = tile_grid(width, height, tile_w, tile_h)
+    seq, k = divmod(item, tile_w * tile_h)
+    tile = rank + seq * world
+    x, y = (tile % tx) * tile_w + k % tile_w, (tile // tx) * tile_h + k // tile_w
+    return (x, y) if x < width and y < height else None
+
+
 def exchange_handles(dist, rank: int, export_fn, device=None):
     """Rank 0 exports (queue handle, frame handle); every rank gets both.  128 bytes over the process group."""
     import torch

@@ -81,3 +81,25 @@ def test_tile_partition_covers_every_tile_once():
     assert multigpu.tile_grid(3840, 2160) == (480, 540)
     assert multigpu.tile_rect(479, 3840, 2160) == (3832, 0, 8, 4)
     assert multigpu.tile_rect(4, 37, 18) == (32, 0, 5, 4)
+
+
+def test_queue_items_cover_every_pixel_once():
+    """The queue counter hands out pixels numbered tile by tile (include/rr_api.h, csrc/rr_render.cu pixel phase): over all
+    ranks of a static partition, and for the shared queue (world 1), every pixel of the frame appears exactly once and the
+    padding items of ragged border tiles map to no pixel."""
+    for (W, H), (tw, th) in [((37, 23), (8, 4)), ((8, 4), (8, 4)), ((9, 5), (5, 5)), ((1, 130), (32, 32)), ((64, 32), (8, 4))]:
+        for world in (1, 3):
+            seen = np.zeros((H, W), np.int32)
+            padding = 0
+            for rank in range(world):
+                n = multigpu.queue_items(W, H, tw, th, rank, world)
+                assert n % (tw * th) == 0
+                for item in range(n):
+                    px = multigpu.item_pixel(item, W, H, tw, th, rank, world)
+                    if px is None:
+                        padding += 1
+                    else:
+                        seen[px[1], px[0]] += 1
+            assert np.all(seen == 1), (W, H, tw, th, world)
+            tx, ty = multigpu.tile_grid(W, H, tw, th)
+            assert padding == tx * ty * tw * th - W * H
