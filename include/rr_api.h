@@ -345,6 +345,15 @@ int rr_render_shared(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t
 int rr_render_strided(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp,
                       uint32_t max_bounces, int32_t frame_index, uint32_t tile_size, uint32_t rank, uint32_t world,
                       rr_stats* stats_out);
+/* Measurement hooks of the cost-ordered queue experiment.
+ * rr_render_cost: renders the frame with the instrumented kernel and returns, per pixel, the path segments its spp samples
+ * traced (the pixel's cost; the image goes to the context's frame buffer as usual).
+ * rr_set_tile_order: the following renders of this context hand out exactly the n_tiles tiles of the table (row-major tile
+ * numbers of the frame they will render, 8 x 4 pixels unless a tile_size is passed), in that order -- every rank of a
+ * shared-queue frame has to set the same table; n_tiles = 0 restores the row-major order. */
+int rr_render_cost(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_bounces,
+                   uint32_t* segments_out);
+int rr_set_tile_order(rr_ctx* ctx, const uint32_t* tiles, uint32_t n_tiles);
 /* Device pointer of the local frame buffer (for an NCCL gather by the caller). */
 int rr_frame_device_ptr(rr_ctx* ctx, uint64_t* ptr_out, uint64_t* bytes_out);
 

@@ -140,6 +140,8 @@ SYMBOLS = {
     "rr_accum_last_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rr_render_progressive": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _i32, _u32, _u32, _vp, C.POINTER(Stats)]),
     "rr_primary_hits": (C.c_int, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
+    "rr_render_cost": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp]),
+    "rr_set_tile_order": (C.c_int, [_vp, _vp, _u32]),
     "rr_bvh_size": (C.c_int, [_vp, C.c_int, C.POINTER(_u64)]),
     "rr_bvh_read": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rr_queue_export": (C.c_int, [_vp, _u32, _u32, _vp, _vp]),

@@ -327,6 +327,21 @@ class Renderer:
         check(lib().rr_primary_hits(self.h, ptr(cam), width, height, ptr(mesh), ptr(prim), ptr(dst)), "rr_primary_hits")
         return mesh, prim, dst
 
+    def render_cost(self, cam, width, height, spp, bounces):
+        """Path segments per pixel (instrumented kernel): the cost map of the cost-ordered queue experiment."""
+        cam = np.ascontiguousarray(cam, CAMERA)
+        cost = np.zeros((height, width), np.uint32)
+        check(lib().rr_render_cost(self.h, ptr(cam), width, height, spp, bounces, ptr(cost)), "rr_render_cost")
+        return cost
+
+    def set_tile_order(self, tiles=None):
+        """The following renders hand out exactly these tiles (row-major tile numbers), in this order; None: row-major."""
+        if tiles is None or len(tiles) == 0:
+            check(lib().rr_set_tile_order(self.h, None, 0), "rr_set_tile_order")
+            return
+        t = np.ascontiguousarray(tiles, np.uint32)
+        check(lib().rr_set_tile_order(self.h, ptr(t), len(t)), "rr_set_tile_order")
+
     def bvh(self, which=0):
         n = C.c_uint64()
         check(lib().rr_bvh_size(self.h, which, C.byref(n)), "rr_bvh_size")

@@ -152,6 +152,8 @@ struct Device {
   uint32_t stack_warps = 0;
   uint32_t stack_entries = 0;           // per slot: 3 per level of the deepest wide hierarchy + slack
   unsigned long long* queue = nullptr;  // local tile counter
+  uint32_t* tile_order = nullptr;       // rr_set_tile_order: the launch's tiles in hand-out order (nullptr: row-major)
+  uint32_t tile_order_n = 0;
   Counters* counters = nullptr;
   // shared (multi-process) attachments.  The exporter's shared frame is an allocation of its own (never d.frame, which
   // ensure_frame may free and move); shared_bytes bounds what rr_render_shared may write through either mapping.
@@ -924,6 +926,11 @@ static void fill_params(const rr_ctx* ctx, const Device& d, const rr_camera* cam
   p.tile_pixels = p.tile_w * p.tile_h;
   p.queue_items = p.tiles_x * p.tiles_y * p.tile_pixels;  // checked against 2^32 by render_frame
   set_queue_tiles(p, p.tiles_x * p.tiles_y);
+  if (d.tile_order) {  // a caller-supplied hand-out order: the launch renders exactly the tiles of the table
+    p.tile_order = d.tile_order;
+    p.queue_items = d.tile_order_n * p.tile_pixels;
+    set_queue_tiles(p, d.tile_order_n);
+  }
   p.stack = d.stack;
   p.stack_entries = d.stack_entries;
   p.cold = d.cold;
@@ -1012,7 +1019,7 @@ static int render_frame(rr_ctx* ctx, const rr_camera* cam, uint32_t W, uint32_t 
     } else {
       p.queue = d0.queue;  // peers pop device 0's counter
       p.frame = d0.frame;
-      if (mode == 2) {  // this rank's tiles: rank, rank + world, ...
+      if (mode == 2 && !p.tile_order) {  // this rank's tiles: rank, rank + world, ... (a tile-order table already names the tiles)
         p.tile_begin = rank; p.tile_stride = world;
         const uint64_t tiles = (uint64_t)p.tiles_x * p.tiles_y;
         p.queue_items = (uint32_t)((tiles > rank ? (tiles - rank + world - 1) / world : 0) * p.tile_pixels);
@@ -1190,7 +1197,7 @@ void rr_destroy(rr_ctx* ctx) {
     }
     if (d.poll_stream) cudaStreamDestroy(d.poll_stream);
     if (d.poll_host) cudaFreeHost(d.poll_host);
-    cudaFree(d.frame); cudaFree(d.radiance); cudaFree(d.accum); cudaFree(d.queue); cudaFree(d.counters); cudaFree(d.cold);
+    cudaFree(d.frame); cudaFree(d.radiance); cudaFree(d.accum); cudaFree(d.queue); cudaFree(d.tile_order); cudaFree(d.counters); cudaFree(d.cold);
     dev_trim(d.ordinal);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
@@ -1433,6 +1440,49 @@ int rr_render_progressive(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uin
     total.render_ms += st.render_ms; total.build_ms = st.build_ms;
   }
   if (stats_out) *stats_out = total;
+  return RR_OK;
+}
+
+int rr_set_tile_order(rr_ctx* ctx, const uint32_t* tiles, uint32_t n_tiles) {
+  if (!ctx || (n_tiles && !tiles)) return fail(RR_ERR_INVALID_ARGUMENT, "null argument");
+  for (Device& d : ctx->dev) {
+    RR_CUDA(cudaSetDevice(d.ordinal));
+    RR_CUDA(cudaStreamSynchronize(d.stream));
+    cudaFree(d.tile_order);
+    d.tile_order = nullptr; d.tile_order_n = 0;
+    if (n_tiles) {
+      RR_CUDA(cudaMalloc(&d.tile_order, (size_t)n_tiles * 4));
+      RR_CUDA(cudaMemcpy(d.tile_order, tiles, (size_t)n_tiles * 4, cudaMemcpyHostToDevice));
+      d.tile_order_n = n_tiles;
+    }
+  }
+  return RR_OK;
+}
+
+int rr_render_cost(rr_ctx* ctx, const rr_camera* cam, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_bounces,
+                   uint32_t* segments_out) {
+  int rc = check_render_args(ctx, cam, width, height, spp, max_bounces);
+  if (rc) return rc;
+  if (!segments_out) return fail(RR_ERR_INVALID_ARGUMENT, "null output");
+  Device& d = ctx->dev[0];
+  RR_CUDA(cudaSetDevice(d.ordinal));
+  rc = ensure_frame(d, width, height, false);
+  if (rc) return rc;
+  RenderParams p;
+  fill_params(ctx, d, cam, width, height, spp, max_bounces, 0, 0, p);
+  if (too_many_items(p)) return fail(RR_ERR_INVALID_ARGUMENT, "image too large (its tiles hold more than 2^32 - 1 work items)");
+  const size_t n = (size_t)width * height;
+  uint32_t* dc = nullptr;
+  cudaError_t e = cudaMalloc(&dc, n * 4);
+  p.cost = dc;
+  if (e == cudaSuccess) e = cudaMemsetAsync(dc, 0, n * 4, d.stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d.queue, 0, sizeof(unsigned long long), d.stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d.counters, 0, sizeof(Counters), d.stream);
+  if (e == cudaSuccess) e = launch_render(p, true, frame_needs_slack(ctx, d, cam), RR_FEAT_ALL, d.sm_count, d.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+  if (e == cudaSuccess) e = cudaMemcpy(segments_out, dc, n * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dc);
+  RR_CUDA(e);
   return RR_OK;
 }
 

@@ -184,6 +184,8 @@ struct RenderParams {
   uint32_t tile_begin, tile_stride;  // static partition: this rank renders tile_begin + k*tile_stride ...
   uint32_t tile_pixels, queue_items; // RR_PIXEL_QUEUE: tile_w * tile_h, and the work items of this launch (its tiles x tile_pixels, < 2^32)
   uint32_t queue_tiles, tile_mul;    // tiles of this launch; RR_TILE_ORDER 2: multiplier of the tile permutation (coprime to queue_tiles)
+  const uint32_t* tile_order;        // nullptr, or the launch's tiles in the order the queue hands them out (rr_set_tile_order)
+  uint32_t* cost;                    // instrumented kernel: path segments per pixel (rr_render_cost), or nullptr
   uint2* stack;                      // traversal stacks, stack_entries * RR_POOL entries per warp (scratch)
   uint32_t stack_entries;            // 3 per level of the deepest 4-wide hierarchy + slack
   uint32_t* cold;                    // cold slot words, RR_COLD_WORDS * RR_POOL per warp (scratch)

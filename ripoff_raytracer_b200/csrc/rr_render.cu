@@ -727,6 +727,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
     PW(W_BMAT, s) = 0u;
     PW(W_LPRIM, s) = (uint32_t)NO_PRIM;
     if (PRIMARY) CW(C_BPRIM, s) = 0xffffffffu;
+    else if (COUNT) CW(C_BPRIM, s) = CW(C_BPRIM, s) + 1u;  // instrumented kernel: path segments of the slot's pixel so far (rr_render_cost)
     n_rays++;
     PW(W_KEY, s) = K_S;
   };
@@ -1101,6 +1102,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             if (sample >= p.spp) {
               const V3 c = accum / (float)p.spp;
               reinterpret_cast<uint32_t*>(p.frame)[pix] = tonemap_rgba(c);
+              if (COUNT && p.cost) p.cost[pix] = CW(C_BPRIM, s);
               if (p.radiance) {
                 p.radiance[3 * (size_t)pix] = c.x;
                 p.radiance[3 * (size_t)pix + 1] = c.y;
@@ -1163,7 +1165,8 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
 #else
           const uint32_t seq = seq0;
 #endif
-          const uint32_t tile = p.tile_begin + seq * p.tile_stride;
+          // (a caller-supplied order of the launch's tiles, rr_set_tile_order: measurement of cost-ordered queues)
+          const uint32_t tile = p.tile_order ? __ldg(p.tile_order + seq) : p.tile_begin + seq * p.tile_stride;
           const uint32_t x = (tile % p.tiles_x) * p.tile_w + k % p.tile_w, y = (tile / p.tiles_x) * p.tile_h + k / p.tile_w;
           first_of_tile = k == 0u;
           if (x < p.width && y < p.height) {
@@ -1173,6 +1176,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
               if (p.radiance) { p.radiance[3 * (size_t)pix] = 0.0f; p.radiance[3 * (size_t)pix + 1] = 0.0f; p.radiance[3 * (size_t)pix + 2] = 0.0f; }
             } else {
               PW(W_PIX, s) = (uint32_t)pix;
+              if (COUNT && !PRIMARY) CW(C_BPRIM, s) = 0u;
               CW(C_RNG, s) = make_seed((uint32_t)pix, p.frame_index, 0u);  // src/Trace.cl:631-632
               const V3 pd = primary_dir(p.cam, x, y, p.width, p.height);   // once per pixel, :634-636
               CST3(C_PD, s, pd);
@@ -1218,6 +1222,7 @@ __global__ void __launch_bounds__(NT, RR_MIN_CTAS) k_render(const RenderParams p
             if (p.radiance) { p.radiance[3 * (size_t)pix] = 0.0f; p.radiance[3 * (size_t)pix + 1] = 0.0f; p.radiance[3 * (size_t)pix + 2] = 0.0f; }
           } else {
             PW(W_PIX, s) = (uint32_t)pix;
+            if (COUNT && !PRIMARY) CW(C_BPRIM, s) = 0u;
             CW(C_RNG, s) = make_seed((uint32_t)pix, p.frame_index, 0u);  // src/Trace.cl:631-632
             const V3 pd = primary_dir(p.cam, x, y, p.width, p.height);   // once per pixel, :634-636
             CST3(C_PD, s, pd);

@@ -621,6 +621,37 @@ def test_pixel_queue_ragged_tiles_and_static_partition(renderer, golden_small):
         assert tiles == -(-W // 8) * -(-H // 4)
 
 
+def test_tile_order_table_and_cost_map(renderer, golden_small):
+    """rr_set_tile_order: any permutation of the frame's tiles renders the same image (pixels are independent, the queue
+    only fixes who takes which); a partial table renders exactly its tiles.  rr_render_cost: the per-pixel path segments
+    add up to the rays the render reports."""
+    g = golden_small
+    renderer.upload_arrays(g["tris"], g["meshes"], g["ranges"])
+    W, H = 45, 26
+    cam = g["cam"].copy()
+    cam["aspectRatio"] = np.float32(W) / np.float32(H)
+    want, _, st0 = renderer.render(cam, W, H, 3, 8)
+    tx, ty = multigpu.tile_grid(W, H)
+    perm = np.random.default_rng(5).permutation(tx * ty).astype(np.uint32)
+    try:
+        renderer.set_tile_order(perm)
+        got, _, st = renderer.render(cam, W, H, 3, 8)
+        assert np.array_equal(got, want) and st["rays"] == st0["rays"] and st["tiles"] == tx * ty
+        renderer.set_tile_order(perm[:7])
+        renderer.render_strided(cam, W, H, 3, 8, 0, 1)  # (clears the frame first)
+        part = renderer.read_frame(W, H)
+        mine = np.zeros((H, W), bool)
+        for t in perm[:7]:
+            x0, y0, w, h = multigpu.tile_rect(int(t), W, H)
+            mine[y0:y0 + h, x0:x0 + w] = True
+        assert np.array_equal(part[..., 3] != 0, mine) and np.array_equal(part[mine], want[mine])
+    finally:
+        renderer.set_tile_order(None)
+    cost = renderer.render_cost(cam, W, H, 3, 8)
+    assert cost.shape == (H, W) and int(cost.sum()) == st0["rays"] and cost.min() >= 3
+    assert np.array_equal(renderer.read_frame(W, H), want)
+
+
 def test_progressive_ragged_sizes_vs_oracle(renderer, golden_small):
     """The accumulation kernel handles four pixels per thread; sizes with W*H % 4 != 0 exercise its tail."""
     g = golden_small
